@@ -1,0 +1,163 @@
+/*
+ * uavca.h — C-ABI of the B200-native batched UAV collision-avoidance environment step.
+ *
+ * The reference (dazchi/gym-uav-collision-avoidance) has no FFI: its boundary is the Python gym API of
+ * two classes.  Every entry point below names the reference interface it replaces (file:line relative to
+ * the reference checkout):
+ *
+ *   uavca_step_multi   <- MultiUAVWorld2D.step            gym_uav_collision_avoidance/envs/multi_uav_world_2d.py:177-241
+ *                         UAVAgent.step/finish/uavs_in_range  gym_uav_collision_avoidance/envs/uav_agent.py:23-64
+ *   uavca_step_single  <- UAVWorld2D.step                 gym_uav_collision_avoidance/envs/uav_world_2d.py:137-173
+ *   uavca_reset        <- MultiUAVWorld2D.reset :116-175 / UAVWorld2D.reset uav_world_2d.py:119-135
+ *   uavca_observe      <- MultiUAVWorld2D._get_obs :60-109 / UAVWorld2D._get_obs uav_world_2d.py:77-112
+ *   uavca_map_action   <- caller-side action mapping      test_sac_multi.py:77-80, test_pytorch_multi.py:80
+ *   uavca_stats        <- env.steps / target_reach_count / collision_count  multi_uav_world_2d.py:166-168,209,221,238
+ *   uavca_config       <- constructor kwargs              multi_uav_world_2d.py:13-28, uav_world_2d.py:14-26
+ *
+ * Conventions: plain C, int return codes (0 = ok, negative = error, text via uavca_last_error()); no
+ * exceptions cross the boundary.  Unless a parameter is documented as HOST memory, every pointer is a
+ * DEVICE pointer borrowed for the duration of the call (the caller — PyTorch — owns all memory).  Every
+ * call takes a cudaStream_t (passed as void*) and is asynchronous on it.  A handle is bound to one device,
+ * is not thread-safe; distinct handles are independent.  There is no CPU fallback: without a usable CUDA
+ * device uavca_create fails.
+ */
+#ifndef UAVCA_H_
+#define UAVCA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UAVCA_VERSION 100
+
+/* world kinds */
+#define UAVCA_KIND_MULTI 0  /* MultiUAVWorld2D: N UAVs per env, 10-feature observation */
+#define UAVCA_KIND_SINGLE 1 /* UAVWorld2D: one UAV per env, 4-feature observation */
+
+/* action modes (what the `action` tensor holds) */
+#define UAVCA_ACTION_CARTESIAN 0 /* env action [vx, vy] in m/s — what env.step() takes */
+#define UAVCA_ACTION_POLAR 1     /* policy output in [-1,1]^2: v=(a0/2+0.5)*scale, th=a1*pi (test_sac_multi.py:77-80) */
+#define UAVCA_ACTION_SCALED 2    /* policy output in [-1,1]^2: a*action_space.high (test_pytorch_multi.py:80) */
+
+/* auto-reset trigger bits (0 = never reset inside step) */
+#define UAVCA_RESET_ON_DONE0 1    /* training protocol: dones[0] (test_sac_multi.py:111-113) */
+#define UAVCA_RESET_ON_ALL_DONE 2 /* evaluation protocol: all(dones) (test_sac_multi.py:115-117) */
+#define UAVCA_RESET_ON_ANY_DONE 4 /* any UAV done (single-UAV world: its done flag, run.py:14-15) */
+
+/* where an auto-reset or uavca_reset takes the new episode from */
+#define UAVCA_SOURCE_PHILOX 0 /* counter-based Philox4x32-10 keyed by (seed, global env index, episode) */
+#define UAVCA_SOURCE_POOL 1   /* host-supplied reset states (parity runs): uavca_set_reset_pool */
+
+/* per-UAV flag bits in the state (`flags` array) */
+#define UAVCA_FLAG_PARKED 1   /* UAVAgent.done latch (uav_agent.py:19,39) */
+#define UAVCA_FLAG_COLLIDED 2 /* UAVAgent.collided latch (uav_agent.py:20; multi_uav_world_2d.py:210) */
+
+#define UAVCA_OBS_DIM_MULTI 10
+#define UAVCA_OBS_DIM_SINGLE 4
+#define UAVCA_MAX_AGENTS 32 /* one env never spans more than a warp */
+
+typedef struct uavca_config {
+  int32_t kind;                 /* UAVCA_KIND_* */
+  int32_t num_envs;             /* B, environments held by THIS handle (this GPU's shard) */
+  int32_t num_agents;           /* N, UAVs per env (1..32); must be 1 for UAVCA_KIND_SINGLE */
+  int32_t reset_mode;           /* UAVCA_RESET_* bits */
+  int32_t max_episode_steps;    /* also reset when env steps >= this; 0 = no limit */
+  int32_t reset_source;         /* UAVCA_SOURCE_* */
+  int32_t circular;             /* multi reset: deterministic ring layout (multi_uav_world_2d.py:157-163) */
+  int32_t single_f32_first_step;/* single world: replicate the float32 first-step quotient the reference
+                                   produces when handed float32 actions (uav_world_2d.py:122,142) */
+  int64_t env_index_base;       /* global index of env 0 of this shard (Philox streams are shard-invariant) */
+  uint64_t seed;                /* Philox key */
+  double x_size, y_size;        /* box, centred on the origin */
+  double max_speed;             /* per-component speed bound */
+  double max_acceleration;      /* per-component acceleration bound */
+  double tau;                   /* seconds per step (0.02 in the reference) */
+  double collider_radius;       /* soft collision when d <= 2*collider_radius */
+  double hard_collision_radius; /* HARD_COLLISION_RADIUS (multi_uav_world_2d.py:8) */
+  double d_sense;               /* neighbour sensing range (strict <) */
+  double reach_distance;        /* 0.5  (multi_uav_world_2d.py:218, uav_world_2d.py:159) */
+  double reach_speed;           /* 0.2  (multi_uav_world_2d.py:218) */
+  double polar_scale;           /* action scale of UAVCA_ACTION_POLAR: ||action_space.high|| (multi) or high[0] (single) */
+} uavca_config;
+
+/* Byte offsets of the structure-of-arrays fields inside one state blob (all 256-byte aligned).
+ * M = num_envs * num_agents.  The blob is allocated by the caller (uavca_state_layout gives its size). */
+typedef struct uavca_layout {
+  size_t total_bytes;
+  size_t stats;   /* uint64[8]: episodes, reach, collisions, steps summed over FINISHED episodes, 4 spare */
+  size_t pos;     /* float  [M][2]  UAV location          (float32 in the reference after reset) */
+  size_t vel;     /* double [M][2]  UAV velocity          (float64 in the reference) */
+  size_t tgt;     /* float  [M][2]  target location */
+  size_t init;    /* float  [M]     init_distance */
+  size_t prev;    /* float  [M]     prev_distance */
+  size_t flags;   /* uint8  [M]     UAVCA_FLAG_* */
+  size_t steps;   /* int32  [B]     env.steps */
+  size_t reach;   /* int32  [B]     env.target_reach_count */
+  size_t coll;    /* int32  [B]     env.collision_count */
+  size_t episode; /* uint32 [B]     episodes started by this env (Philox counter word) */
+} uavca_layout;
+
+typedef struct uavca_handle uavca_handle;
+
+const char* uavca_last_error(void);
+int uavca_version(void);
+
+/* Fill *cfg with the reference defaults of the given world kind (ctor defaults cited above). */
+int uavca_default_config(int kind, uavca_config* cfg);
+
+int uavca_create(const uavca_config* cfg, int device, uavca_handle** out);
+int uavca_destroy(uavca_handle* h);
+int uavca_get_config(const uavca_handle* h, uavca_config* out);
+int uavca_state_layout(const uavca_handle* h, uavca_layout* out);
+
+/* Host-supplied reset states: `pool_state` is a state blob laid out for `pool_envs` environments (same N).
+ * With reset_source = UAVCA_SOURCE_POOL env b starting its e-th episode copies pool env
+ * (env_index_base + b + e) % pool_envs.  The pool is borrowed until replaced or the handle is destroyed. */
+int uavca_set_reset_pool(uavca_handle* h, const void* pool_state, int32_t pool_envs);
+/* Layout of a pool blob holding `pool_envs` environments. */
+int uavca_pool_layout(const uavca_handle* h, int32_t pool_envs, uavca_layout* out);
+
+/* Start a new episode in every env (mask == NULL) or in envs with mask[b] != 0, and write their
+ * observations (rows of other envs are left untouched).  obs: float [B][N][obs_dim]. */
+int uavca_reset(uavca_handle* h, void* state, const uint8_t* mask, float* obs, void* stream);
+
+/* Recompute the observation of the current state (after the caller edited the state). */
+int uavca_observe(uavca_handle* h, const void* state, float* obs, void* stream);
+
+/* action: float [B][N][2]; obs: float [B][N][10]; reward: float [B][N]; done: uint8 [B][N].
+ * obs is the observation the policy acts on next (post-reset for envs that auto-reset this step).
+ * final_obs (nullable): the step's own next-observation before any reset (what the replay buffer stores).
+ * reset_mask (nullable): uint8 [B], 1 where the env auto-reset this step. */
+int uavca_step_multi(uavca_handle* h, void* state, const float* action, int action_mode, int evaluate,
+                     float* obs, float* reward, uint8_t* done, float* final_obs, uint8_t* reset_mask,
+                     void* stream);
+
+/* action: float [B][2]; obs: float [B][4]; reward: float [B]; done: uint8 [B];
+ * distance (nullable): float [B] = info["distance"]. */
+int uavca_step_single(uavca_handle* h, void* state, const float* action, int action_mode, float* obs,
+                      float* reward, uint8_t* done, float* distance, float* final_obs, uint8_t* reset_mask,
+                      void* stream);
+
+/* The caller-side action mapping on its own: in/out float [B][N][2]. */
+int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* out, void* stream);
+
+/* out8 (device int64[8]): episodes finished, reach, collisions, steps over finished episodes; then the
+ * same three counters summed over the episodes in flight (reach, collisions, steps) and B. */
+int uavca_stats(uavca_handle* h, const void* state, int64_t* out8, void* stream);
+
+/* End-to-end form with HOST buffers (pinned for full speed): copies the actions in, steps, copies
+ * obs/reward/done out, pipelined in chunks over internal streams, and returns when the outputs are in
+ * host memory.  `state` stays on the device.  Works for both kinds (obs_dim from the config). */
+int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int action_mode, int evaluate,
+                    float* host_obs, float* host_reward, uint8_t* host_done);
+
+/* Launch bookkeeping: number of kernels this handle has launched so far. */
+int64_t uavca_launch_count(const uavca_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAVCA_H_ */

@@ -1,0 +1,191 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (where /root/reference exists):
+
+    python -m oracle.gen_golden            # rewrites tests/golden/*.npz
+
+Every file holds seeded initial states, the float32 actions that were fed (to the reference as float64
+up-casts), and what the literal reference returned at every step: float64 observations and
+rewards, done flags, and the float32 positions / float64 velocities / flags / counters after the step.
+tests/test_oracle_golden.py replays the same inputs through oracle/uav_oracle.c and demands exact equality;
+the GPU parity tests replay them through the CUDA path.
+
+Scenarios mix wide-box random actions (out-of-bounds events) with a noisy go-to-goal controller in a crowded
+region (soft/hard collisions, goal reaches, parked UAVs being hit), both env kinds, evaluate=True, and the
+"reset when dones[0]" training protocol with host-supplied reset states (pool).
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+from . import oracle as O
+from . import ref_loader as R
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+MULTI_CASES = [
+    # name, N, envs, steps, seed, evaluate, reset_mode, max_episode_steps
+    dict(name="multi_n1", N=1, E=6, T=200, seed=101, evaluate=0, reset_mode=0, max_steps=0),
+    dict(name="multi_n2", N=2, E=6, T=250, seed=102, evaluate=0, reset_mode=0, max_steps=0),
+    dict(name="multi_n5_reset_done0", N=5, E=8, T=400, seed=105, evaluate=0, reset_mode=O.RESET_ON_DONE0, max_steps=150),
+    dict(name="multi_n8", N=8, E=8, T=400, seed=108, evaluate=0, reset_mode=0, max_steps=0),
+    dict(name="multi_n10_eval_reset_all", N=10, E=4, T=300, seed=110, evaluate=1, reset_mode=O.RESET_ON_ALL_DONE, max_steps=0),
+    dict(name="multi_n32", N=32, E=2, T=120, seed=132, evaluate=0, reset_mode=0, max_steps=0),
+]
+SINGLE_CASES = [
+    dict(name="single_f64_actions", E=12, T=400, seed=201, f32=0),
+    dict(name="single_f32_actions", E=12, T=400, seed=202, f32=1),
+]
+POOL = 16
+
+
+def _actions_multi(rng, st: O.State, b: int, N: int, controller: bool):
+    if controller:
+        a = (st.tgt[b] - st.pos[b]) * 1.5 + rng.normal(0, 0.3, size=(N, 2))
+        return np.clip(a, -10, 10).astype(np.float32)
+    return rng.uniform(-10, 10, size=(N, 2)).astype(np.float32)
+
+
+def run_reference_multi(case) -> dict:
+    _, MultiUAVWorld2D = R.load_reference()
+    N, E, T = case["N"], case["E"], case["T"]
+    rng = np.random.default_rng(case["seed"])
+    # odd envs: crowded region + controller; even envs: full box + random actions
+    regions = [None if b % 2 == 0 else max(3.0, 0.75 * N ** 0.5 * 2.0) for b in range(E)]
+    init = O.State(E, N)
+    for b in range(E):
+        s = O.sample_multi_states(1, N, rng, region=regions[b])
+        for f in O.State.FIELDS[:-1]:
+            getattr(init, f)[b] = getattr(s, f)[0]
+    pool = O.State(POOL, N)
+    for p in range(POOL):
+        s = O.sample_multi_states(1, N, rng, region=regions[p % E])
+        for f in O.State.FIELDS[:-1]:
+            getattr(pool, f)[p] = getattr(s, f)[0]
+
+    envs = [MultiUAVWorld2D(num_agents=N) for _ in range(E)]
+    cur = init.copy()
+    for b, env in enumerate(envs):
+        env.reset()
+        R.inject_multi(env, cur.pos[b], cur.vel[b], cur.tgt[b], cur.init[b], cur.prev[b], cur.flags[b])
+    episode = np.ones(E, np.int64)  # episode counter after the initial "reset" (matches the oracle/device: 1)
+    out = dict(
+        action=np.zeros((T, E, N, 2), np.float32), obs=np.zeros((T, E, N, 10)), final_obs=np.zeros((T, E, N, 10)),
+        reward=np.zeros((T, E, N)), done=np.zeros((T, E, N), np.uint8), reset_mask=np.zeros((T, E), np.uint8),
+        pos=np.zeros((T, E, N, 2), np.float32), vel=np.zeros((T, E, N, 2)), flags=np.zeros((T, E, N), np.uint8),
+        prev=np.zeros((T, E, N), np.float32), steps=np.zeros((T, E), np.int32), reach=np.zeros((T, E), np.int32),
+        coll=np.zeros((T, E), np.int32),
+    )
+    obs0 = np.stack([np.stack([env._get_obs(a) for a in env.agent_list]) for env in envs])
+    for t in range(T):
+        for b, env in enumerate(envs):
+            a = _actions_multi(rng, cur, b, N, controller=(b % 2 == 1))
+            out["action"][t, b] = a
+            o, r, d, _ = env.step([a[i].astype(np.float64) for i in range(N)], evaluate=bool(case["evaluate"]))
+            o = np.stack(o)
+            out["final_obs"][t, b] = o
+            out["reward"][t, b] = np.array(r, dtype=np.float64)
+            out["done"][t, b] = np.array(d, dtype=np.uint8)
+            rs = False
+            if case["reset_mode"] & O.RESET_ON_DONE0:
+                rs |= bool(d[0])
+            if case["reset_mode"] & O.RESET_ON_ALL_DONE:
+                rs |= all(d)
+            if case["max_steps"] > 0:
+                rs |= env.steps >= case["max_steps"]
+            if rs:
+                p = (b + int(episode[b])) % POOL
+                env.reset()  # zeroes the counters exactly as the reference does (:166-168)
+                R.inject_multi(env, pool.pos[p], pool.vel[p], pool.tgt[p], pool.init[p], pool.prev[p], pool.flags[p])
+                episode[b] += 1
+                o = np.stack([env._get_obs(ag) for ag in env.agent_list])
+            out["reset_mask"][t, b] = rs
+            out["obs"][t, b] = o
+            pos, vel, tgt, ini, prv, flg = R.extract_multi(env)
+            cur.pos[b], cur.vel[b], cur.tgt[b], cur.init[b], cur.prev[b], cur.flags[b] = pos, vel, tgt, ini, prv, flg
+            out["pos"][t, b], out["vel"][t, b], out["flags"][t, b], out["prev"][t, b] = pos, vel, flg, prv
+            out["steps"][t, b], out["reach"][t, b], out["coll"][t, b] = env.steps, env.target_reach_count, env.collision_count
+    meta = dict(kind="multi", **case, pool=POOL)
+    res = dict(meta=np.array(json.dumps(meta)), obs0=obs0)
+    for f in ("pos", "vel", "tgt", "init", "prev", "flags"):
+        res["init_" + f] = getattr(init, f)
+        res["pool_" + f] = getattr(pool, f)
+    res.update(out)
+    return res
+
+
+def run_reference_single(case) -> dict:
+    UAVWorld2D, _ = R.load_reference()
+    E, T = case["E"], case["T"]
+    rng = np.random.default_rng(case["seed"])
+    init = O.sample_single_states(E, rng)
+    pool = O.sample_single_states(POOL, rng)
+    envs = [UAVWorld2D() for _ in range(E)]
+    cur = init.copy()
+    for b, env in enumerate(envs):
+        env.reset()
+        R.inject_single(env, cur.pos[b, 0], cur.vel[b, 0], cur.tgt[b, 0], cur.init[b, 0], cur.prev[b, 0], vel_f32=True)
+    episode = np.ones(E, np.int64)
+    out = dict(
+        action=np.zeros((T, E, 1, 2), np.float32), obs=np.zeros((T, E, 1, 4)), final_obs=np.zeros((T, E, 1, 4)),
+        reward=np.zeros((T, E, 1)), done=np.zeros((T, E, 1), np.uint8), reset_mask=np.zeros((T, E), np.uint8),
+        pos=np.zeros((T, E, 1, 2), np.float32), vel=np.zeros((T, E, 1, 2)), prev=np.zeros((T, E, 1), np.float32),
+        steps=np.zeros((T, E), np.int32), distance=np.zeros((T, E), np.float32),
+    )
+    obs0 = np.stack([env._get_obs() for env in envs])[:, None, :]
+    for t in range(T):
+        for b, env in enumerate(envs):
+            if b % 2 == 1:
+                a = np.clip((cur.tgt[b, 0] - cur.pos[b, 0]) * 0.8 + rng.normal(0, 0.5, 2), -12, 12).astype(np.float32)
+            else:
+                a = rng.uniform(-12, 12, 2).astype(np.float32)
+            out["action"][t, b, 0] = a
+            o, r, d, info = env.step(a if case["f32"] else a.astype(np.float64))
+            out["final_obs"][t, b, 0] = o
+            out["reward"][t, b, 0] = np.float64(r)
+            out["done"][t, b, 0] = d
+            out["distance"][t, b] = info["distance"]
+            if d:
+                p = (b + int(episode[b])) % POOL
+                env.reset()
+                R.inject_single(env, pool.pos[p, 0], pool.vel[p, 0], pool.tgt[p, 0], pool.init[p, 0], pool.prev[p, 0],
+                                vel_f32=True)
+                episode[b] += 1
+                o = env._get_obs()
+            out["reset_mask"][t, b] = d
+            out["obs"][t, b, 0] = o
+            pos, vel, tgt, ini, prv = R.extract_single(env)
+            cur.pos[b, 0], cur.vel[b, 0], cur.tgt[b, 0], cur.init[b, 0], cur.prev[b, 0] = pos, vel, tgt, ini, prv
+            out["pos"][t, b, 0], out["vel"][t, b, 0], out["prev"][t, b, 0] = pos, vel, prv
+            out["steps"][t, b] = env.steps
+    meta = dict(kind="single", **case, pool=POOL, reset_mode=O.RESET_ON_ANY_DONE)
+    res = dict(meta=np.array(json.dumps(meta)), obs0=obs0)
+    for f in ("pos", "vel", "tgt", "init", "prev", "flags"):
+        res["init_" + f] = getattr(init, f)
+        res["pool_" + f] = getattr(pool, f)
+    res.update(out)
+    return res
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for case in MULTI_CASES:
+        res = run_reference_multi(case)
+        path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+        if res["reset_mask"].sum() == 0:
+            del res["final_obs"]  # identical to obs when nothing reset
+        np.savez_compressed(path, **res)
+        print(f"{case['name']}: done-events={int(res['done'].sum())} resets={int(res['reset_mask'].sum())} "
+              f"reach={int(res['reach'].max())} coll={int(res['coll'].max())} -> {os.path.getsize(path) / 1e6:.2f} MB")
+    for case in SINGLE_CASES:
+        res = run_reference_single(case)
+        path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+        np.savez_compressed(path, **res)
+        print(f"{case['name']}: resets={int(res['reset_mask'].sum())} -> {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()

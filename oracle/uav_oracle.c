@@ -1,0 +1,582 @@
+/*
+ * uav_oracle.c — CPU restatement of the reference environment step.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle for the CUDA path: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may build, load or call it.  The product package never does.
+ *
+ * Parity pinning: the reference ships no golden vectors or tests.  This restatement is
+ * pinned by executing the unmodified reference in the build container (oracle/ref_loader.py) and comparing
+ * bit-for-bit: oracle/gen_golden.py writes the tests/golden npz files from the literal reference and
+ * tests/test_oracle_golden.py replays them through this file (flags, float32 positions, float64 velocities,
+ * float64 rewards and float64 observations all compared for exact equality).
+ *
+ * Each function cites the reference lines it restates (paths relative to the reference checkout,
+ * gym_uav_collision_avoidance/envs/...).  Semantics, operation order and dtypes follow the reference as it
+ * executes under NumPy 2 (NEP 50 weak Python scalars); the code shape does not.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math -pthread (see oracle/Makefile).  -ffp-contract=off matters:
+ * every fused multiply-add below is an explicit fma() where the reference's BLAS has one.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../include/uavca.h"
+
+#include <pthread.h>
+#include <unistd.h>
+
+#define PI_D 3.141592653589793 /* math.pi */
+
+typedef struct uavo_state {
+  float* pos;        /* [B][N][2] */
+  double* vel;       /* [B][N][2] */
+  float* tgt;        /* [B][N][2] */
+  float* init;       /* [B][N] */
+  float* prev;       /* [B][N] */
+  uint8_t* flags;    /* [B][N] */
+  int32_t* steps;    /* [B] */
+  int32_t* reach;    /* [B] */
+  int32_t* coll;     /* [B] */
+  uint32_t* episode; /* [B] */
+  uint64_t* stats;   /* [8] */
+} uavo_state;
+
+/* ---- numpy primitives as they execute in the reference ---------------------------------------------- */
+
+/* np.linalg.norm of a float32 2-vector: sqrtf(x*x + y*y), products and sum rounded separately
+ * (OpenBLAS sdot on 2 elements + sqrt). */
+static inline float n32(float dx, float dy) {
+  float a = dx * dx;
+  float b = dy * dy;
+  float s = a + b;
+  return sqrtf(s);
+}
+static inline float s32(float dx, float dy) {
+  float a = dx * dx;
+  float b = dy * dy;
+  return a + b;
+}
+
+/* np.linalg.norm of a float64 2-vector: the ddot kernel fuses the second product. */
+static inline double n64(double x, double y) { return sqrt(fma(y, y, x * x)); }
+
+static inline double clipd(double v, double lo, double hi) {
+  /* np.clip == minimum(maximum(v, lo), hi); NaN propagates */
+  if (v != v) return v;
+  if (v < lo) v = lo;
+  if (v > hi) v = hi;
+  return v;
+}
+
+static inline double wrap(double x) { return atan2(sin(x), cos(x)); }
+
+/* ---- Philox4x32-10 (Salmon et al., SC'11), the on-device reset stream ------------------------------- */
+
+static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                 uint32_t out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* 53-bit uniform in [0,1) from two words (same construction as numpy's random_sample). */
+static inline double u53(uint32_t a, uint32_t b) {
+  return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+enum { STREAM_POS = 0, STREAM_TGT = 1, STREAM_VEL = 2 };
+
+/* One draw of np.random.uniform(low, high, size=(2,)).astype(float32): low + (high-low)*u per component. */
+static inline void draw_pair(const uavca_config* c, int64_t env_global, uint32_t episode, int stream, int uav,
+                             uint32_t attempt, double lo_x, double hi_x, double lo_y, double hi_y, float* x, float* y) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)env_global, episode, ((uint32_t)stream << 16) | (uint32_t)uav, attempt,
+                (uint32_t)c->seed, (uint32_t)(c->seed >> 32), r);
+  double ux = u53(r[0], r[1]);
+  double uy = u53(r[2], r[3]);
+  double rx = (hi_x - lo_x) * ux;
+  double ry = (hi_y - lo_y) * uy;
+  *x = (float)(lo_x + rx);
+  *y = (float)(lo_y + ry);
+}
+
+#define MAX_RESET_ATTEMPTS 4096u
+
+/* ---- observation: MultiUAVWorld2D._get_obs, multi_uav_world_2d.py:60-109 ---------------------------- */
+
+static void obs_multi(const uavca_config* c, const float* pos, const double* vel, const float* tgt, int N, int i,
+                      double* o) {
+  const double vm2 = n64(c->max_speed, c->max_speed);      /* np.linalg.norm(agent.max_speed)  :62 */
+  const double diag = n64(c->x_size, c->y_size);           /* self.map_diagonal_size           :17 */
+  const float dsense32 = (float)c->d_sense;                /* python scalar, weak -> float32   :77 */
+  const double vx = vel[2 * i], vy = vel[2 * i + 1];
+  const float px = pos[2 * i], py = pos[2 * i + 1];
+  const double th = atan2(vy, vx);                          /* :63 */
+  o[0] = n64(vx, vy) / vm2;                                 /* :62 */
+  o[1] = th / PI_D;                                         /* :64 */
+  const float tdx = tgt[2 * i] - px, tdy = tgt[2 * i + 1] - py;
+  o[2] = (double)n32(tdx, tdy) / diag;                      /* :67-68 */
+  o[3] = wrap(atan2((double)tdy, (double)tdx) - th) / PI_D; /* :69-72 */
+
+  /* uavs_in_range (uav_agent.py:44-64): in-range neighbours ascending by float32 distance.  Exact-distance
+   * ties have no defined order in the reference (unstable argsort); we refine the order by (squared
+   * distance, index), which agrees with the reference whenever it is defined. */
+  int j1 = -1, j2 = -1;
+  float s1 = INFINITY, s2 = INFINITY;
+  for (int j = 0; j < N; ++j) {
+    if (j == i) continue;
+    float s = s32(pos[2 * j] - px, pos[2 * j + 1] - py);
+    if (s < s1) { s2 = s1; j2 = j1; s1 = s; j1 = j; }
+    else if (s < s2) { s2 = s; j2 = j; }
+  }
+  const int nb[2] = {j1, j2};
+  const float sq[2] = {s1, s2};
+  int have = 1;
+  for (int k = 0; k < 2; ++k) {
+    double* ok = o + 4 + 3 * k;
+    float d = 0.f;
+    if (have && nb[k] >= 0) { d = sqrtf(sq[k]); have = d < dsense32; } else have = 0;
+    if (have) {
+      int j = nb[k];
+      float dx = pos[2 * j] - px, dy = pos[2 * j + 1] - py;
+      ok[0] = (double)(d / dsense32);                                    /* :77 float32 quotient */
+      ok[1] = wrap(atan2((double)dy, (double)dx) - th) / PI_D;           /* :78-81 */
+      ok[2] = wrap(atan2(vel[2 * j + 1], vel[2 * j]) - th) / PI_D;       /* :82-85 */
+    } else {
+      ok[0] = 1.0;                                                        /* :77 */
+      ok[1] = wrap((PI_D + th) - th) / PI_D;                              /* :78-81 (+1, 0.99.. or -1) */
+      ok[2] = wrap(th - th) / PI_D;                                       /* :82-85 */
+    }
+  }
+}
+
+/* ---- observation: UAVWorld2D._get_obs, uav_world_2d.py:77-112 --------------------------------------- */
+
+static void obs_single(const uavca_config* c, const float* pos, const double* vel, const float* tgt, int vel_is_f32,
+                       double* o) {
+  const double diag = n64(c->x_size, c->y_size);             /* :17 */
+  const double vx = vel[0], vy = vel[1];
+  /* right after reset() the speed is a float32 array (:122) and its norm is a float32 norm */
+  const double speed = vel_is_f32 ? (double)n32((float)vx, (float)vy) : n64(vx, vy);
+  const double th = atan2(vy, vx);                           /* :89 */
+  const float tdx = tgt[0] - pos[0], tdy = tgt[1] - pos[1];
+  o[0] = speed / c->max_speed;                               /* :88 */
+  o[1] = th / PI_D;                                          /* :90 */
+  o[2] = (double)n32(tdx, tdy) / diag;                       /* :96-97 */
+  o[3] = wrap(atan2((double)tdy, (double)tdx) - th) / PI_D;  /* :91-94 */
+}
+
+/* ---- action mapping done by the callers: test_sac_multi.py:77-80, test_pytorch_multi.py:80 ---------- */
+
+static inline void map_action(const uavca_config* c, int mode, float a0, float a1, float* ox, float* oy) {
+  if (mode == UAVCA_ACTION_POLAR) {
+    float v = (a0 / 2.0f + 0.5f) * (float)c->polar_scale;
+    float th = a1 * (float)PI_D;
+    *ox = v * (float)cos((double)th);
+    *oy = v * (float)sin((double)th);
+  } else if (mode == UAVCA_ACTION_SCALED) {
+    *ox = a0 * (float)c->max_speed;
+    *oy = a1 * (float)c->max_speed;
+  } else {
+    *ox = a0; *oy = a1;
+  }
+}
+
+/* ---- reset: MultiUAVWorld2D.reset, multi_uav_world_2d.py:116-175 ------------------------------------ */
+
+static void reset_env_multi(const uavca_config* c, uavo_state* s, const uavo_state* pool, int pool_envs, int b) {
+  const int N = c->num_agents;
+  float* pos = s->pos + (size_t)b * N * 2;
+  double* vel = s->vel + (size_t)b * N * 2;
+  float* tgt = s->tgt + (size_t)b * N * 2;
+  float* init = s->init + (size_t)b * N;
+  float* prev = s->prev + (size_t)b * N;
+  uint8_t* flags = s->flags + (size_t)b * N;
+  const int64_t env_global = c->env_index_base + b;
+  const uint32_t ep = s->episode[b];
+
+  /* fold the finished episode into the running totals */
+  if (s->stats && ep > 0) {
+    s->stats[0] += 1;
+    s->stats[1] += (uint64_t)s->reach[b];
+    s->stats[2] += (uint64_t)s->coll[b];
+    s->stats[3] += (uint64_t)s->steps[b];
+  }
+
+  if (c->reset_source == UAVCA_SOURCE_POOL && pool && pool_envs > 0) {
+    const size_t p = (size_t)((env_global + (int64_t)ep) % pool_envs);
+    memcpy(pos, pool->pos + p * N * 2, sizeof(float) * N * 2);
+    memcpy(vel, pool->vel + p * N * 2, sizeof(double) * N * 2);
+    memcpy(tgt, pool->tgt + p * N * 2, sizeof(float) * N * 2);
+    memcpy(init, pool->init + p * N, sizeof(float) * N);
+    memcpy(prev, pool->prev + p * N, sizeof(float) * N);
+    memcpy(flags, pool->flags + p * N, N);
+  } else {
+    const double lox = -c->x_size / 2.0, hix = c->x_size / 2.0; /* :19-20 */
+    const double loy = -c->y_size / 2.0, hiy = c->y_size / 2.0;
+    const float two_r = (float)(2.0 * c->collider_radius);      /* float32 norm <= python float: weak */
+    for (int i = 0; i < N; ++i) {                               /* :118-123 */
+      vel[2 * i] = 0.0; vel[2 * i + 1] = 0.0; flags[i] = 0;
+    }
+    for (int i = 0; i < N; ++i) {                               /* :126-137 */
+      for (uint32_t a = 0;; ++a) {
+        float x, y;
+        draw_pair(c, env_global, ep, STREAM_POS, i, a, lox, hix, loy, hiy, &x, &y);
+        int rej = 0;
+        for (int j = 0; j < i && !rej; ++j) rej = n32(pos[2 * j] - x, pos[2 * j + 1] - y) <= two_r;
+        if (!rej || a + 1 >= MAX_RESET_ATTEMPTS) { pos[2 * i] = x; pos[2 * i + 1] = y; break; }
+      }
+    }
+    for (int i = 0; i < N; ++i) {                               /* :140-155 */
+      for (uint32_t a = 0;; ++a) {
+        float x, y;
+        draw_pair(c, env_global, ep, STREAM_TGT, i, a, lox, hix, loy, hiy, &x, &y);
+        int rej = n32(x - pos[2 * i], y - pos[2 * i + 1]) <= two_r;
+        for (int j = 0; j < i && !rej; ++j) rej = n32(tgt[2 * j] - x, tgt[2 * j + 1] - y) <= two_r;
+        if (!rej || a + 1 >= MAX_RESET_ATTEMPTS) { tgt[2 * i] = x; tgt[2 * i + 1] = y; break; }
+      }
+    }
+    if (c->circular) {
+      /* :157-163 ring layout.  The reference keeps these as float64 arrays; this framework stores
+       * positions as float32, so the ring is rounded once here (documented deviation). */
+      for (int i = 0; i < N; ++i) {
+        double theta = 2 * i * PI_D / N;
+        pos[2 * i] = (float)(20.0 * cos(theta));
+        pos[2 * i + 1] = (float)(20.0 * sin(theta));
+        tgt[2 * i] = (float)(23.0 * cos(theta + PI_D));
+        tgt[2 * i + 1] = (float)(23.0 * sin(theta + PI_D));
+      }
+    }
+    for (int i = 0; i < N; ++i) {
+      init[i] = n32(tgt[2 * i] - pos[2 * i], tgt[2 * i + 1] - pos[2 * i + 1]); /* :154 */
+      prev[i] = init[i];                                                        /* :155 */
+    }
+  }
+  s->steps[b] = 0; s->reach[b] = 0; s->coll[b] = 0; /* :166-168 */
+  s->episode[b] = ep + 1;
+}
+
+/* ---- reset: UAVWorld2D.reset, uav_world_2d.py:119-135 ----------------------------------------------- */
+
+static void reset_env_single(const uavca_config* c, uavo_state* s, const uavo_state* pool, int pool_envs, int b) {
+  float* pos = s->pos + (size_t)b * 2;
+  double* vel = s->vel + (size_t)b * 2;
+  float* tgt = s->tgt + (size_t)b * 2;
+  const int64_t env_global = c->env_index_base + b;
+  const uint32_t ep = s->episode[b];
+  if (s->stats && ep > 0) {
+    s->stats[0] += 1;
+    s->stats[1] += (uint64_t)s->reach[b];
+    s->stats[2] += (uint64_t)s->coll[b];
+    s->stats[3] += (uint64_t)s->steps[b];
+  }
+  if (c->reset_source == UAVCA_SOURCE_POOL && pool && pool_envs > 0) {
+    const size_t p = (size_t)((env_global + (int64_t)ep) % pool_envs);
+    memcpy(pos, pool->pos + p * 2, sizeof(float) * 2);
+    memcpy(vel, pool->vel + p * 2, sizeof(double) * 2);
+    memcpy(tgt, pool->tgt + p * 2, sizeof(float) * 2);
+    s->init[b] = pool->init[p];
+    s->prev[b] = pool->prev[p];
+    s->flags[b] = pool->flags[p];
+  } else {
+    const double lox = -c->x_size / 2.0, hix = c->x_size / 2.0;
+    const double loy = -c->y_size / 2.0, hiy = c->y_size / 2.0;
+    float x, y;
+    draw_pair(c, env_global, ep, STREAM_POS, 0, 0, lox, hix, loy, hiy, &x, &y);           /* :121 */
+    pos[0] = x; pos[1] = y;
+    draw_pair(c, env_global, ep, STREAM_VEL, 0, 0, -c->max_speed, c->max_speed, -c->max_speed, c->max_speed, &x, &y); /* :122 */
+    vel[0] = (double)x; vel[1] = (double)y;
+    draw_pair(c, env_global, ep, STREAM_TGT, 0, 0, lox, hix, loy, hiy, &x, &y);           /* :126 */
+    tgt[0] = x; tgt[1] = y;
+    s->init[b] = n32(tgt[0] - pos[0], tgt[1] - pos[1]);                                    /* :129 */
+    s->prev[b] = s->init[b];                                                               /* :130 */
+    s->flags[b] = 0;
+  }
+  s->steps[b] = 0; s->reach[b] = 0; s->coll[b] = 0;                                        /* :131 */
+  s->episode[b] = ep + 1;
+}
+
+/* ---- step: MultiUAVWorld2D.step (multi_uav_world_2d.py:177-241) + UAVAgent (uav_agent.py:23-64) ----- */
+
+static void step_env_multi(const uavca_config* c, uavo_state* s, int b, const float* action, int action_mode,
+                           int evaluate, double* obs, double* reward, uint8_t* done) {
+  const int N = c->num_agents;
+  float* pos = s->pos + (size_t)b * N * 2;
+  double* vel = s->vel + (size_t)b * N * 2;
+  const float* tgt = s->tgt + (size_t)b * N * 2;
+  const float* init = s->init + (size_t)b * N;
+  float* prev = s->prev + (size_t)b * N;
+  uint8_t* flags = s->flags + (size_t)b * N;
+  const double tau = c->tau, amax = c->max_acceleration, vmax = c->max_speed;
+  const double vm2 = n64(vmax, vmax);                         /* np.linalg.norm(agent.max_speed) :183 */
+  const float two_r = (float)(2.0 * c->collider_radius);      /* :203 weak python float vs float32 */
+  const float two_h = (float)(2.0 * c->hard_collision_radius);/* :207 */
+  const float dsense32 = (float)c->d_sense;                   /* uav_agent.py:52 */
+  const float reach32 = (float)c->reach_distance;             /* :218 */
+  const double lox = -c->x_size / 2.0, hix = c->x_size / 2.0, loy = -c->y_size / 2.0, hiy = c->y_size / 2.0;
+
+  for (int i = 0; i < N; ++i) { /* sequential: UAV i sees j<i moved, j>i not yet moved (:181) */
+    const int parked = flags[i] & UAVCA_FLAG_PARKED;
+    float prev_d, dist;
+    if (parked) {                                             /* uav_agent.py:24-25 returns ints 0, 0 */
+      prev_d = 0.f; dist = 0.f;
+    } else {
+      float ax, ay;
+      map_action(c, action_mode, action[2 * i], action[2 * i + 1], &ax, &ay);
+      double dvx = clipd(((double)ax - vel[2 * i]) / tau, -amax, amax);       /* uav_agent.py:26 */
+      double dvy = clipd(((double)ay - vel[2 * i + 1]) / tau, -amax, amax);
+      double vx = clipd(vel[2 * i] + dvx * tau, -vmax, vmax);                 /* :27 */
+      double vy = clipd(vel[2 * i + 1] + dvy * tau, -vmax, vmax);
+      pos[2 * i] = (float)((double)pos[2 * i] + vx * tau);                    /* :28-29 float32 += float64 */
+      pos[2 * i + 1] = (float)((double)pos[2 * i + 1] + vy * tau);
+      vel[2 * i] = vx; vel[2 * i + 1] = vy;                                   /* :30 */
+      prev_d = prev[i];                                                       /* :32 */
+      dist = n32(tgt[2 * i] - pos[2 * i], tgt[2 * i + 1] - pos[2 * i + 1]);   /* :33 */
+    }
+    const float px = pos[2 * i], py = pos[2 * i + 1];
+    const float tdx = tgt[2 * i] - px, tdy = tgt[2 * i + 1] - py;
+    double dth = atan2((double)tdy, (double)tdx) - atan2(vel[2 * i + 1], vel[2 * i]); /* :184-185 */
+    dth = wrap(dth);                                                                   /* :186 */
+
+    double m = vm2 / (double)init[i];                          /* :189 float64 / float32 */
+    if (1.0 < m) m = 1.0;                                      /* python min(x, 1) */
+    double r = 0.0 - 0.01 * m;
+    r += 50.0 * ((double)(prev_d - dist) / vm2);               /* :190 float32 subtraction first */
+    {
+      float q = dist / (1.5f * init[i]);                       /* :192/:194 float32 product and quotient */
+      float f = (r > 0) ? (1.0f - q) : (1.0f + q);
+      r *= (double)f;
+    }
+    r -= 0.01 * fabs(dth);                                     /* :195 */
+
+    /* nearest in-range neighbour on the mixed old/new positions (:198-210; testing the two nearest of an
+     * ascending list is the same as testing the minimum) */
+    float smin = INFINITY;
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      float sj = s32(pos[2 * j] - px, pos[2 * j + 1] - py);
+      if (sj < smin) smin = sj;
+    }
+    int collision = 0;
+    if (smin < INFINITY) {
+      float dmin = sqrtf(smin);
+      if (dmin < dsense32) {
+        if (dmin <= two_r) { r = -2.0; collision = 1; }        /* :203-205 */
+        if (dmin <= two_h && !parked && !(flags[i] & UAVCA_FLAG_COLLIDED)) { /* :207-210 */
+          s->coll[b] += 1;
+          flags[i] |= UAVCA_FLAG_COLLIDED;
+        }
+      }
+    }
+    const double speed = n64(vel[2 * i], vel[2 * i + 1]);      /* :214 */
+    const int oob = !((double)px >= lox && (double)px <= hix && (double)py >= loy && (double)py <= hiy); /* :213,224 */
+    int d;
+    if (dist < reach32 && !collision && speed < c->reach_speed) { /* :218 */
+      d = 1;
+      if (!parked) s->reach[b] += 1;                           /* :220-221 */
+      flags[i] |= UAVCA_FLAG_PARKED;                           /* finish(): uav_agent.py:38-42 */
+      double nv = n64(vel[2 * i], vel[2 * i + 1]);
+      double fx = vel[2 * i] / nv * 0.001, fy = vel[2 * i + 1] / nv * 0.001;
+      if (fx != fx || fy != fy) { fx = 0.0; fy = 0.0; }
+      vel[2 * i] = fx; vel[2 * i + 1] = fy;
+      r += 10.0;                                               /* :223 */
+    } else if (oob) {
+      d = evaluate ? 0 : 1;                                    /* :225 */
+    } else {
+      d = 0;
+    }
+    prev[i] = dist;                                            /* :229 */
+    reward[i] = r;
+    done[i] = (uint8_t)d;
+  }
+  for (int i = 0; i < N; ++i) obs_multi(c, pos, vel, tgt, N, i, obs + 10 * i); /* :233-235 */
+  s->steps[b] += 1;                                            /* :238 */
+}
+
+/* ---- step: UAVWorld2D.step, uav_world_2d.py:137-173 ------------------------------------------------- */
+
+static void step_env_single(const uavca_config* c, uavo_state* s, int b, const float* action, int action_mode,
+                            double* obs, double* reward, uint8_t* done, float* distance) {
+  float* pos = s->pos + (size_t)b * 2;
+  double* vel = s->vel + (size_t)b * 2;
+  const float* tgt = s->tgt + (size_t)b * 2;
+  const double tau = c->tau, amax = c->max_acceleration, vmax = c->max_speed;
+  const double lox = -c->x_size / 2.0, hix = c->x_size / 2.0, loy = -c->y_size / 2.0, hiy = c->y_size / 2.0;
+  float ax, ay;
+  map_action(c, action_mode, action[0], action[1], &ax, &ay);
+  double qx, qy;
+  if (c->single_f32_first_step && s->steps[b] == 0) {
+    /* float32 action minus the float32 reset speed, divided by the weak python float tau: all float32 */
+    qx = (double)((ax - (float)vel[0]) / (float)tau);
+    qy = (double)((ay - (float)vel[1]) / (float)tau);
+  } else {
+    qx = ((double)ax - vel[0]) / tau;
+    qy = ((double)ay - vel[1]) / tau;
+  }
+  double dvx = clipd(qx, -amax, amax), dvy = clipd(qy, -amax, amax);   /* :142 */
+  double vx = clipd(vel[0] + dvx * tau, -vmax, vmax);                  /* :144 */
+  double vy = clipd(vel[1] + dvy * tau, -vmax, vmax);
+  pos[0] = (float)((double)pos[0] + vx * tau);                         /* :145-146 */
+  pos[1] = (float)((double)pos[1] + vy * tau);
+  vel[0] = vx; vel[1] = vy;                                            /* :147 */
+  const float tdx = tgt[0] - pos[0], tdy = tgt[1] - pos[1];
+  const float dist = n32(tdx, tdy);                                    /* :150 */
+  float r = 0.0f - 1.0f / s->init[b];                                  /* :152-153 float32 */
+  r = r + 10.0f * (s->prev[b] - dist);                                 /* :154 float32 */
+  double dth = wrap(atan2((double)tdy, (double)tdx) - atan2(vy, vx));  /* :155-156 */
+  r = r - (float)(0.1 * fabs(dth));                                    /* :157 python float is weak -> float32 */
+  const int oob = !((double)pos[0] >= lox && (double)pos[0] <= hix && (double)pos[1] >= loy && (double)pos[1] <= hiy);
+  int d;
+  if (dist < (float)c->reach_distance) { d = 1; r = r + 1000.0f; }     /* :159-161 */
+  else if (oob) d = 1;                                                 /* :162-163 */
+  else d = 0;
+  obs_single(c, pos, vel, tgt, 0, obs);                                /* :168 */
+  if (distance) *distance = dist;                                      /* :169 info["distance"] */
+  s->steps[b] += 1;                                                    /* :170 */
+  s->prev[b] = dist;                                                   /* :172 */
+  *reward = (double)r;
+  *done = (uint8_t)d;
+}
+
+/* ---- minimal pthread parallel-for over environments -------------------------------------------------- */
+
+typedef void (*env_fn)(void* ctx, int b);
+typedef struct { env_fn fn; void* ctx; int lo, hi; } pf_job;
+static void* pf_run(void* p) {
+  pf_job* j = (pf_job*)p;
+  for (int b = j->lo; b < j->hi; ++b) j->fn(j->ctx, b);
+  return 0;
+}
+static void parallel_for(env_fn fn, void* ctx, int B, int nthreads) {
+  if (nthreads > 64) nthreads = 64;
+  if (nthreads <= 1 || B < 2 * nthreads) { pf_job j = {fn, ctx, 0, B}; pf_run(&j); return; }
+  pthread_t th[64];
+  pf_job jobs[64];
+  int per = (B + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    int lo = t * per, hi = lo + per; if (lo > B) lo = B; if (hi > B) hi = B;
+    jobs[t] = (pf_job){fn, ctx, lo, hi};
+    pthread_create(&th[t], 0, pf_run, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
+}
+
+/* ---- batched entry points --------------------------------------------------------------------------- */
+
+typedef struct {
+  const uavca_config* c; uavo_state* s; const float* action; int action_mode; int evaluate;
+  double* obs; double* reward; uint8_t* done; float* distance; double* final_obs;
+} step_ctx;
+static void step_multi_body(void* p, int b) {
+  step_ctx* x = (step_ctx*)p;
+  const int N = x->c->num_agents;
+  step_env_multi(x->c, x->s, b, x->action + (size_t)b * N * 2, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
+                 x->reward + (size_t)b * N, x->done + (size_t)b * N);
+  if (x->final_obs) memcpy(x->final_obs + (size_t)b * N * 10, x->obs + (size_t)b * N * 10, sizeof(double) * N * 10);
+}
+static void step_single_body(void* p, int b) {
+  step_ctx* x = (step_ctx*)p;
+  step_env_single(x->c, x->s, b, x->action + (size_t)b * 2, x->action_mode, x->obs + (size_t)b * 4, x->reward + b,
+                  x->done + b, x->distance ? x->distance + b : 0);
+  if (x->final_obs) memcpy(x->final_obs + (size_t)b * 4, x->obs + (size_t)b * 4, sizeof(double) * 4);
+}
+
+static int want_reset(const uavca_config* c, const uint8_t* done, int N, int steps) {
+  int any = 0, all = 1;
+  for (int i = 0; i < N; ++i) { any |= done[i]; all &= done[i]; }
+  if ((c->reset_mode & UAVCA_RESET_ON_DONE0) && done[0]) return 1;
+  if ((c->reset_mode & UAVCA_RESET_ON_ALL_DONE) && all) return 1;
+  if ((c->reset_mode & UAVCA_RESET_ON_ANY_DONE) && any) return 1;
+  if (c->max_episode_steps > 0 && steps >= c->max_episode_steps) return 1;
+  return 0;
+}
+
+int uavo_reset(const uavca_config* c, uavo_state* s, const uavo_state* pool, int pool_envs, const uint8_t* mask,
+               double* obs) {
+  const int N = c->num_agents;
+  for (int b = 0; b < c->num_envs; ++b) { /* serial: the totals in stats are shared */
+    if (mask && !mask[b]) continue;
+    if (c->kind == UAVCA_KIND_SINGLE) {
+      reset_env_single(c, s, pool, pool_envs, b);
+      if (obs) obs_single(c, s->pos + (size_t)b * 2, s->vel + (size_t)b * 2, s->tgt + (size_t)b * 2, 1, obs + (size_t)b * 4);
+    } else {
+      reset_env_multi(c, s, pool, pool_envs, b);
+      if (obs)
+        for (int i = 0; i < N; ++i)
+          obs_multi(c, s->pos + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt + (size_t)b * N * 2, N, i,
+                    obs + ((size_t)b * N + i) * 10);
+    }
+  }
+  return 0;
+}
+
+int uavo_observe(const uavca_config* c, const uavo_state* s, double* obs) {
+  const int N = c->num_agents;
+  for (int b = 0; b < c->num_envs; ++b) {
+    if (c->kind == UAVCA_KIND_SINGLE)
+      obs_single(c, s->pos + (size_t)b * 2, s->vel + (size_t)b * 2, s->tgt + (size_t)b * 2, s->steps[b] == 0, obs + (size_t)b * 4);
+    else
+      for (int i = 0; i < N; ++i)
+        obs_multi(c, s->pos + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt + (size_t)b * N * 2, N, i,
+                  obs + ((size_t)b * N + i) * 10);
+  }
+  return 0;
+}
+
+int uavo_step_multi(const uavca_config* c, uavo_state* s, const uavo_state* pool, int pool_envs, const float* action,
+                    int action_mode, int evaluate, double* obs, double* reward, uint8_t* done, double* final_obs,
+                    uint8_t* reset_mask, int nthreads) {
+  const int N = c->num_agents, B = c->num_envs;
+  step_ctx ctx = {c, s, action, action_mode, evaluate, obs, reward, done, 0, final_obs};
+  parallel_for(step_multi_body, &ctx, B, nthreads);
+  /* auto-reset pass is serial because it folds into the shared totals */
+  for (int b = 0; b < B; ++b) {
+    int rs = want_reset(c, done + (size_t)b * N, N, s->steps[b]);
+    if (reset_mask) reset_mask[b] = (uint8_t)rs;
+    if (rs) {
+      reset_env_multi(c, s, pool, pool_envs, b);
+      for (int i = 0; i < N; ++i)
+        obs_multi(c, s->pos + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt + (size_t)b * N * 2, N, i,
+                  obs + ((size_t)b * N + i) * 10);
+    }
+  }
+  return 0;
+}
+
+int uavo_step_single(const uavca_config* c, uavo_state* s, const uavo_state* pool, int pool_envs, const float* action,
+                     int action_mode, double* obs, double* reward, uint8_t* done, float* distance, double* final_obs,
+                     uint8_t* reset_mask, int nthreads) {
+  const int B = c->num_envs;
+  step_ctx ctx = {c, s, action, action_mode, 0, obs, reward, done, distance, final_obs};
+  parallel_for(step_single_body, &ctx, B, nthreads);
+  for (int b = 0; b < B; ++b) {
+    int rs = want_reset(c, done + b, 1, s->steps[b]);
+    if (reset_mask) reset_mask[b] = (uint8_t)rs;
+    if (rs) {
+      reset_env_single(c, s, pool, pool_envs, b);
+      obs_single(c, s->pos + (size_t)b * 2, s->vel + (size_t)b * 2, s->tgt + (size_t)b * 2, 1, obs + (size_t)b * 4);
+    }
+  }
+  return 0;
+}
+
+int uavo_map_action(const uavca_config* c, const float* in, int action_mode, float* out) {
+  const size_t M = (size_t)c->num_envs * c->num_agents;
+  for (size_t m = 0; m < M; ++m) map_action(c, action_mode, in[2 * m], in[2 * m + 1], out + 2 * m, out + 2 * m + 1);
+  return 0;
+}
+
+int uavo_max_threads(void) {
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n < 1 ? 1 : (n > 64 ? 64 : (int)n);
+}
