@@ -1,0 +1,260 @@
+"""Batched, device-resident versions of the reference worlds.
+
+`BatchedMultiUAVWorld2D` / `BatchedUAVWorld2D` keep the reference's reset()/step() contract
+(multi_uav_world_2d.py:116,177; uav_world_2d.py:119,137) over B independent environments held in one
+structure-of-arrays state blob in HBM.  All inputs and outputs are CUDA tensors; the step is one kernel launch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _capi, ops
+from ._capi import (ACTION_CARTESIAN, ACTION_POLAR, ACTION_SCALED, KIND_MULTI, KIND_SINGLE, RESET_ON_ALL_DONE,  # noqa: F401
+                    RESET_ON_ANY_DONE, RESET_ON_DONE0, SOURCE_PHILOX, SOURCE_POOL)
+
+_ACTION_MODES = {"cartesian": ACTION_CARTESIAN, "polar": ACTION_POLAR, "scaled": ACTION_SCALED,
+                 ACTION_CARTESIAN: ACTION_CARTESIAN, ACTION_POLAR: ACTION_POLAR, ACTION_SCALED: ACTION_SCALED}
+
+_FIELD_DTYPES = dict(pos=(torch.float32, 2), vel=(torch.float64, 2), tgt=(torch.float32, 2), init=(torch.float32, 0),
+                     prev=(torch.float32, 0), flags=(torch.uint8, 0))
+_ENV_FIELDS = dict(steps=torch.int32, reach=torch.int32, coll=torch.int32, episode=torch.int32)
+
+
+class Box:
+    """Record standing in for gym.spaces.Box (low/high/shape/dtype/sample), so callers that read
+    `env.action_space.high` or `observation_space.shape[0]` (test_sac_multi.py:39-40,77) keep working without gym."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape)
+        self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
+        self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
+
+    def sample(self):
+        return np.random.uniform(self.low, self.high, size=self.shape).astype(self.dtype)
+
+    def __repr__(self):
+        return f"Box({self.low}, {self.high}, {self.shape}, {self.dtype})"
+
+
+class StateBlob:
+    """One SoA state blob (uint8 CUDA tensor) with typed tensor views of its fields (zero-copy)."""
+
+    def __init__(self, layout: _capi.Layout, num_envs: int, num_agents: int, device: torch.device):
+        self.B, self.N = num_envs, num_agents
+        self.layout = layout
+        self.blob = torch.zeros(layout.total_bytes, dtype=torch.uint8, device=device)
+        M = num_envs * num_agents
+        for name, (dt, inner) in _FIELD_DTYPES.items():
+            nbytes = M * max(inner, 1) * torch.empty((), dtype=dt).element_size()
+            off = getattr(layout, name)
+            shape = (num_envs, num_agents, inner) if inner else (num_envs, num_agents)
+            setattr(self, name, self.blob[off:off + nbytes].view(dt).view(shape))
+        for name, dt in _ENV_FIELDS.items():
+            off = getattr(layout, name)
+            setattr(self, name, self.blob[off:off + num_envs * 4].view(dt))
+        self.stats = self.blob[layout.stats:layout.stats + 64].view(torch.int64)
+        self.init.fill_(1.0)
+        self.prev.fill_(1.0)
+
+    FIELDS = ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode")
+
+    def load_arrays(self, **arrays) -> None:
+        """Overwrite fields from host arrays / tensors of the matching shape (parity runs, checkpoints)."""
+        for k, v in arrays.items():
+            dst = getattr(self, k)
+            src = torch.as_tensor(np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v)
+            if k == "episode" and src.dtype != torch.int32:
+                src = src.to(torch.int64).to(torch.int32)
+            dst.copy_(src.to(dst.dtype).reshape(dst.shape), non_blocking=False)
+
+    def to_host(self) -> dict:
+        out = {k: getattr(self, k).cpu().numpy() for k in self.FIELDS}
+        out["stats"] = self.stats.cpu().numpy()
+        return out
+
+
+class _BatchedBase:
+    kind: int = KIND_MULTI
+
+    def __init__(self, num_envs: int, num_agents: int, cfg: _capi.Config, device=None):
+        if not torch.cuda.is_available():
+            raise _capi.UavcaError("gym_uav_collision_avoidance_b200 needs a CUDA device (B200, sm_100a); "
+                                   "there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise _capi.UavcaError("device must be a CUDA device")
+        self._lib = _capi.load()
+        self.cfg = cfg
+        self.num_envs, self.num_agents = num_envs, num_agents
+        self.obs_dim = _capi.OBS_DIM[cfg.kind]
+        h = C.c_void_p()
+        _capi.check(self._lib.uavca_create(C.byref(cfg), self.device.index or 0, C.byref(h)), "uavca_create")
+        self._h = h.value
+        lay = _capi.Layout()
+        _capi.check(self._lib.uavca_state_layout(self._h, C.byref(lay)), "uavca_state_layout")
+        self.state = StateBlob(lay, num_envs, num_agents, self.device)
+        self._pool: Optional[StateBlob] = None
+        B, N, D = num_envs, num_agents, self.obs_dim
+        self.obs = torch.zeros((B, N, D), dtype=torch.float32, device=self.device)
+        self.reward = torch.zeros((B, N), dtype=torch.float32, device=self.device)
+        self.done = torch.zeros((B, N), dtype=torch.uint8, device=self.device)
+        self.final_obs: Optional[torch.Tensor] = None
+        self.reset_mask = torch.zeros(B, dtype=torch.uint8, device=self.device)
+        self._stats = torch.zeros(8, dtype=torch.int64, device=self.device)
+
+    # -- lifetime -----------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.uavca_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reset pool (host-supplied reset states) -----------------------------------------------------------------
+    def make_pool(self, pool_envs: int) -> StateBlob:
+        lay = _capi.Layout()
+        _capi.check(self._lib.uavca_pool_layout(self._h, pool_envs, C.byref(lay)), "uavca_pool_layout")
+        pool = StateBlob(lay, pool_envs, self.num_agents, self.device)
+        self._pool = pool
+        _capi.check(self._lib.uavca_set_reset_pool(self._h, pool.blob.data_ptr(), pool_envs), "uavca_set_reset_pool")
+        return pool
+
+    # -- gym-shaped API --------------------------------------------------------------------------------------------
+    def enable_final_obs(self, on: bool = True):
+        """Also emit the step's own next-observation before any auto-reset (what a replay buffer stores)."""
+        self.final_obs = torch.zeros_like(self.obs) if on else None
+
+    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        ops.reset(self._h, self.state.blob, mask, self.obs)
+        return self.obs
+
+    def observe(self) -> torch.Tensor:
+        ops.observe(self._h, self.state.blob, self.obs)
+        return self.obs
+
+    def map_action(self, action: torch.Tensor, action_mode="polar") -> torch.Tensor:
+        out = torch.empty_like(action)
+        ops.map_action(self._h, action.contiguous(), _ACTION_MODES[action_mode], out)
+        return out
+
+    def stats(self) -> dict:
+        """Totals over finished episodes plus the counters of the episodes in flight."""
+        ops.stats(self._h, self.state.blob, self._stats)
+        v = self._stats.cpu().tolist()
+        return dict(episodes=v[0], reach=v[1], collisions=v[2], steps=v[3], live_reach=v[4], live_collisions=v[5],
+                    live_steps=v[6], num_envs=v[7])
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.uavca_launch_count(self._h))
+
+    def _check_action(self, action: torch.Tensor) -> torch.Tensor:
+        B, N = self.num_envs, self.num_agents
+        if action.device != self.device or action.dtype != torch.float32:
+            action = action.to(device=self.device, dtype=torch.float32)
+        if action.numel() != B * N * 2:
+            raise ValueError(f"action must hold {B}x{N}x2 values, got shape {tuple(action.shape)}")
+        return action.contiguous()
+
+    def step_host(self, action: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor,
+                  action_mode="cartesian", evaluate: bool = False):
+        """End-to-end step with HOST tensors (pinned for speed): H2D actions, step, D2H obs/reward/done."""
+        for t in (action, obs, reward, done):
+            if t.is_cuda or not t.is_contiguous():
+                raise ValueError("step_host takes contiguous CPU tensors")
+        _capi.check(self._lib.uavca_step_host(self._h, self.state.blob.data_ptr(), action.data_ptr(),
+                                              _ACTION_MODES[action_mode], int(evaluate), obs.data_ptr(),
+                                              reward.data_ptr(), done.data_ptr()), "uavca_step_host")
+        return obs, reward, done
+
+
+class BatchedMultiUAVWorld2D(_BatchedBase):
+    """B x MultiUAVWorld2D (multi_uav_world_2d.py:10).  Constructor kwargs follow the reference (:13)."""
+
+    kind = KIND_MULTI
+
+    def __init__(self, num_envs: int, x_size=50.0, y_size=50.0, max_speed=10.0, max_acceleration=5.0, num_agents=4,
+                 collider_radius=1.0, d_sense=15, *, device=None, seed=0, reset_mode=0, max_episode_steps=0,
+                 reset_source=SOURCE_PHILOX, circular=False, env_index_base=0, hard_collision_radius=0.5):
+        cfg = _capi.default_config(KIND_MULTI)
+        cfg.num_envs, cfg.num_agents = num_envs, num_agents
+        cfg.x_size, cfg.y_size, cfg.max_speed, cfg.max_acceleration = x_size, y_size, max_speed, max_acceleration
+        cfg.collider_radius, cfg.d_sense, cfg.hard_collision_radius = collider_radius, d_sense, hard_collision_radius
+        cfg.seed, cfg.reset_mode, cfg.max_episode_steps = seed, reset_mode, max_episode_steps
+        cfg.reset_source, cfg.circular, cfg.env_index_base = reset_source, int(circular), env_index_base
+        # np.linalg.norm(env.action_space.high) with a float32 `high` (test_sac_multi.py:77)
+        cfg.polar_scale = float(np.linalg.norm(np.full(2, max_speed, dtype=np.float32)))
+        super().__init__(num_envs, num_agents, cfg, device)
+        # attributes the reference exposes (multi_uav_world_2d.py:14-47; `max_acceleratoin` sic)
+        self.x_size, self.y_size = x_size, y_size
+        self.map_diagonal_size = np.linalg.norm([x_size, y_size])
+        self.min_location = np.array([-x_size / 2.0, -y_size / 2.0])
+        self.max_location = np.array([x_size / 2.0, y_size / 2.0])
+        self.max_speed = np.array([max_speed, max_speed])
+        self.min_speed = -self.max_speed
+        self.max_acceleratoin = np.array([max_acceleration, max_acceleration])
+        self.min_acceleratoin = -self.max_acceleratoin
+        self.tau, self.collider_radius, self.d_sense = 0.02, collider_radius, d_sense
+        self.observation_space = Box(np.array([0, -1, 0, -1, 0, -1, -1, 0, -1, 1]), np.ones(10), (10,))  # :44-45 (sic)
+        self.action_space = Box(-max_speed, max_speed, (2,))  # :47
+
+    def step(self, action: torch.Tensor, evaluate: bool = False, action_mode="cartesian"):
+        """action [B,N,2] float32 CUDA -> (obs [B,N,10], reward [B,N], done [B,N] uint8, info)."""
+        action = self._check_action(action)
+        ops.step_multi(self._h, self.state.blob, action, _ACTION_MODES[action_mode], bool(evaluate), self.obs,
+                       self.reward, self.done, self.final_obs, self.reset_mask)
+        info = {"distance": 0, "reset_mask": self.reset_mask}  # multi_uav_world_2d.py:111-114
+        if self.final_obs is not None:
+            info["final_obs"] = self.final_obs
+        return self.obs, self.reward, self.done, info
+
+
+class BatchedUAVWorld2D(_BatchedBase):
+    """B x UAVWorld2D (uav_world_2d.py:11).  Constructor kwargs follow the reference (:14)."""
+
+    kind = KIND_SINGLE
+
+    def __init__(self, num_envs: int, x_size=100.0, y_size=100.0, agent_num=4, max_speed=12.0, max_acceleration=5.0, *,
+                 device=None, seed=0, reset_mode=0, max_episode_steps=0, reset_source=SOURCE_PHILOX, env_index_base=0,
+                 float32_first_step=False):
+        cfg = _capi.default_config(KIND_SINGLE)
+        cfg.num_envs, cfg.num_agents = num_envs, 1
+        cfg.x_size, cfg.y_size, cfg.max_speed, cfg.max_acceleration = x_size, y_size, max_speed, max_acceleration
+        cfg.seed, cfg.reset_mode, cfg.max_episode_steps = seed, reset_mode, max_episode_steps
+        cfg.reset_source, cfg.env_index_base = reset_source, env_index_base
+        cfg.single_f32_first_step = int(float32_first_step)
+        cfg.polar_scale = float(np.float32(max_speed))  # env.action_space.high[0] (test_sac.py:77)
+        super().__init__(num_envs, 1, cfg, device)
+        self.x_size, self.y_size = x_size, y_size
+        self.map_diagonal_size = np.linalg.norm([x_size, y_size])
+        self.min_location = np.array([-x_size / 2.0, -y_size / 2.0])
+        self.max_location = np.array([x_size / 2.0, y_size / 2.0])
+        self.max_speed = np.array([max_speed, max_speed])
+        self.min_speed = -self.max_speed
+        self.max_acceleratoin = np.array([max_acceleration, max_acceleration])
+        self.min_acceleratoin = -self.max_acceleratoin
+        self.tau = 0.02
+        self.observation_space = Box(np.array([0., -1., 0., -1.]), np.ones(4), (4,))  # uav_world_2d.py:55
+        self.action_space = Box(-max_speed, max_speed, (2,))  # :64
+        self.distance = torch.zeros(num_envs, dtype=torch.float32, device=self.device)
+
+    def step(self, action: torch.Tensor, action_mode="cartesian"):
+        """action [B,2] float32 CUDA -> (obs [B,1,4], reward [B,1], done [B,1] uint8, info)."""
+        action = self._check_action(action)
+        ops.step_single(self._h, self.state.blob, action, _ACTION_MODES[action_mode], self.obs, self.reward, self.done,
+                        self.distance, self.final_obs, self.reset_mask)
+        info = {"distance": self.distance, "reset_mask": self.reset_mask}  # uav_world_2d.py:114-117
+        if self.final_obs is not None:
+            info["final_obs"] = self.final_obs
+        return self.obs, self.reward, self.done, info

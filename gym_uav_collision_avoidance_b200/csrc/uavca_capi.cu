@@ -1,0 +1,442 @@
+// uavca_capi.cu — the C-ABI of include/uavca.h: handles, derived constants, state layout, launch plumbing.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "uavca_host.h"
+
+using namespace uavca;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& msg) {
+  g_error = msg;
+  return code;
+}
+int fail_cuda(const char* what, cudaError_t e) {
+  return fail(-2, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
+}
+
+constexpr size_t kAlign = 256;
+size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+void compute_layout(int B, int N, uavca_layout* L) {
+  const size_t M = (size_t)B * (size_t)N;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
+  L->stats = take(8 * sizeof(uint64_t));
+  L->pos = take(M * 2 * sizeof(float));
+  L->vel = take(M * 2 * sizeof(double));
+  L->tgt = take(M * 2 * sizeof(float));
+  L->init = take(M * sizeof(float));
+  L->prev = take(M * sizeof(float));
+  L->flags = take(M);
+  L->steps = take((size_t)B * sizeof(int32_t));
+  L->reach = take((size_t)B * sizeof(int32_t));
+  L->coll = take((size_t)B * sizeof(int32_t));
+  L->episode = take((size_t)B * sizeof(uint32_t));
+  L->total_bytes = off;
+}
+
+StateView view_of(void* blob, const uavca_layout& L) {
+  StateView v{};
+  if (!blob) return v;
+  char* p = static_cast<char*>(blob);
+  v.stats = reinterpret_cast<unsigned long long*>(p + L.stats);
+  v.pos = reinterpret_cast<float2*>(p + L.pos);
+  v.vel = reinterpret_cast<double2*>(p + L.vel);
+  v.tgt = reinterpret_cast<float2*>(p + L.tgt);
+  v.init = reinterpret_cast<float*>(p + L.init);
+  v.prev = reinterpret_cast<float*>(p + L.prev);
+  v.flags = reinterpret_cast<uint8_t*>(p + L.flags);
+  v.steps = reinterpret_cast<int*>(p + L.steps);
+  v.reach = reinterpret_cast<int*>(p + L.reach);
+  v.coll = reinterpret_cast<int*>(p + L.coll);
+  v.episode = reinterpret_cast<unsigned*>(p + L.episode);
+  return v;
+}
+
+// Shift a view to the sub-range of envs starting at env0 (stats stay shared).
+StateView offset_view(const StateView& v, long long env0, int N) {
+  StateView o = v;
+  const long long m0 = env0 * N;
+  o.pos += m0; o.vel += m0; o.tgt += m0; o.init += m0; o.prev += m0; o.flags += m0;
+  o.steps += env0; o.reach += env0; o.coll += env0; o.episode += env0;
+  return o;
+}
+
+// np.linalg.norm of a float64 2-vector as the reference's BLAS forms it (second product fused).
+double n64(double x, double y) { return std::sqrt(std::fma(y, y, x * x)); }
+
+Consts derive_consts(const uavca_config& g) {
+  Consts c{};
+  c.tau = g.tau;
+  c.inv_tau = 1.0 / g.tau;
+  c.amax = g.max_acceleration;
+  c.vmax = g.max_speed;
+  // least x >= 0 with fl(x / tau) >= amax (division is monotone, so the clip is decided by comparing x)
+  {
+    volatile double tau = g.tau;
+    double x = g.max_acceleration * g.tau;
+    for (int k = 0; k < 64 && x > 0 && std::nextafter(x, 0.0) / tau >= g.max_acceleration; ++k) x = std::nextafter(x, 0.0);
+    for (int k = 0; k < 64 && x / tau < g.max_acceleration; ++k) x = std::nextafter(x, INFINITY);
+    c.clip_x = x;
+  }
+  c.vm2 = n64(g.max_speed, g.max_speed);
+  c.inv_vm2 = 1.0 / c.vm2;
+  c.lox = -g.x_size / 2.0; c.hix = g.x_size / 2.0;
+  c.loy = -g.y_size / 2.0; c.hiy = g.y_size / 2.0;
+  // least s with sqrt(s) >= reach_speed:  ||v|| < reach_speed  <=>  (vx*vx + vy*vy) < s
+  {
+    double s = g.reach_speed * g.reach_speed;
+    for (int k = 0; k < 64 && s > 0 && std::sqrt(std::nextafter(s, 0.0)) >= g.reach_speed; ++k) s = std::nextafter(s, 0.0);
+    for (int k = 0; k < 64 && std::sqrt(s) < g.reach_speed; ++k) s = std::nextafter(s, INFINITY);
+    c.reach_speed_sq = s;
+  }
+  c.two_r = (float)(2.0 * g.collider_radius);
+  c.two_h = (float)(2.0 * g.hard_collision_radius);
+  c.dsense = (float)g.d_sense;
+  c.reach_dist = (float)g.reach_distance;
+  const double diag = n64(g.x_size, g.y_size);
+  c.inv_diag = (float)(1.0 / diag);
+  c.inv_vm2_f = (float)(1.0 / c.vm2);
+  c.inv_vmax_f = (float)(1.0 / g.max_speed);
+  c.inv_pi = (float)(1.0 / 3.141592653589793);
+  c.polar_scale = (float)g.polar_scale;
+  c.vmax_f = (float)g.max_speed;
+  c.tau_f = (float)g.tau;
+  c.reset_mode = g.reset_mode;
+  c.max_steps = g.max_episode_steps;
+  c.reset_source = g.reset_source;
+  c.circular = g.circular;
+  c.single_f32_first_step = g.single_f32_first_step;
+  c.seed_lo = (unsigned)(g.seed & 0xffffffffull);
+  c.seed_hi = (unsigned)(g.seed >> 32);
+  c.env_base = g.env_index_base;
+  return c;
+}
+
+}  // namespace
+
+struct uavca_handle {
+  uavca_config cfg;
+  Consts consts;
+  uavca_layout layout;
+  int device;
+  const void* pool_blob = nullptr;
+  int pool_envs = 0;
+  uavca_layout pool_layout{};
+  float4* ring = nullptr;  // circular-reset table (owned)
+  long long launches = 0;
+  // end-to-end (host buffer) path, created lazily
+  static constexpr int kHostStreams = 3;
+  cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
+  float* d_action = nullptr;
+  float* d_obs = nullptr;
+  float* d_reward = nullptr;
+  uint8_t* d_done = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+KernelArgs make_args(const uavca_handle* h, void* state) {
+  KernelArgs a{};
+  a.c = h->consts;
+  a.s = view_of(state, h->layout);
+  a.pool = view_of(const_cast<void*>(h->pool_blob), h->pool_layout);
+  a.pool_envs = h->pool_envs;
+  a.ring = h->ring;
+  a.B = h->cfg.num_envs;
+  a.N = h->cfg.num_agents;
+  return a;
+}
+
+int check_handle(const uavca_handle* h) { return h ? 0 : fail(-1, "null handle"); }
+
+int validate_config(const uavca_config& g) {
+  if (g.kind != UAVCA_KIND_MULTI && g.kind != UAVCA_KIND_SINGLE) return fail(-1, "config.kind must be UAVCA_KIND_MULTI or UAVCA_KIND_SINGLE");
+  if (g.num_envs <= 0) return fail(-1, "config.num_envs must be positive");
+  if (g.num_agents < 1 || g.num_agents > UAVCA_MAX_AGENTS) return fail(-1, "config.num_agents must be in 1..32");
+  if (g.kind == UAVCA_KIND_SINGLE && g.num_agents != 1) return fail(-1, "the single-UAV world has num_agents == 1");
+  if (!(g.tau > 0) || !(g.max_speed > 0) || !(g.max_acceleration > 0)) return fail(-1, "tau, max_speed and max_acceleration must be positive");
+  if (!(g.x_size > 0) || !(g.y_size > 0)) return fail(-1, "x_size and y_size must be positive");
+  if (g.reset_source != UAVCA_SOURCE_PHILOX && g.reset_source != UAVCA_SOURCE_POOL) return fail(-1, "config.reset_source invalid");
+  if (g.max_episode_steps < 0) return fail(-1, "config.max_episode_steps must be >= 0");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* uavca_last_error(void) { return g_error.c_str(); }
+int uavca_version(void) { return UAVCA_VERSION; }
+
+int uavca_default_config(int kind, uavca_config* cfg) {
+  if (!cfg) return fail(-1, "null config");
+  std::memset(cfg, 0, sizeof(*cfg));
+  cfg->kind = kind;
+  cfg->num_envs = 1;
+  cfg->tau = 0.02;
+  cfg->max_acceleration = 5.0;
+  cfg->collider_radius = 1.0;
+  cfg->hard_collision_radius = 0.5;
+  cfg->d_sense = 15.0;
+  cfg->reach_distance = 0.5;
+  cfg->reach_speed = 0.2;
+  if (kind == UAVCA_KIND_SINGLE) {  // uav_world_2d.py:14
+    cfg->num_agents = 1;
+    cfg->x_size = 100.0; cfg->y_size = 100.0; cfg->max_speed = 12.0;
+    cfg->polar_scale = 12.0;  // action_space.high[0] (test_sac.py:77)
+  } else if (kind == UAVCA_KIND_MULTI) {  // multi_uav_world_2d.py:13
+    cfg->num_agents = 4;
+    cfg->x_size = 50.0; cfg->y_size = 50.0; cfg->max_speed = 10.0;
+    cfg->polar_scale = (double)std::sqrt(200.0f);  // float32 norm of action_space.high (test_sac_multi.py:77)
+  } else {
+    return fail(-1, "unknown world kind");
+  }
+  return 0;
+}
+
+int uavca_create(const uavca_config* cfg, int device, uavca_handle** out) {
+  if (!cfg || !out) return fail(-1, "null argument");
+  *out = nullptr;
+  if (int rc = validate_config(*cfg)) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    return fail(-3, std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= ndev) return fail(-1, "device index out of range");
+  uavca_handle* h = new (std::nothrow) uavca_handle();
+  if (!h) return fail(-4, "out of host memory");
+  h->cfg = *cfg;
+  h->consts = derive_consts(*cfg);
+  h->device = device;
+  compute_layout(cfg->num_envs, cfg->num_agents, &h->layout);
+  if (cfg->kind == UAVCA_KIND_MULTI && cfg->circular) {
+    // multi_uav_world_2d.py:157-163, computed with the host libm and rounded to the float32 state
+    DeviceGuard g(device);
+    const int N = cfg->num_agents;
+    std::vector<float4> ring(N);
+    const double pi = 3.141592653589793;
+    for (int i = 0; i < N; ++i) {
+      double th = 2 * i * pi / N;
+      ring[i] = make_float4((float)(20.0 * std::cos(th)), (float)(20.0 * std::sin(th)), (float)(23.0 * std::cos(th + pi)),
+                            (float)(23.0 * std::sin(th + pi)));
+    }
+    e = cudaMalloc(&h->ring, sizeof(float4) * N);
+    if (e == cudaSuccess) e = cudaMemcpy(h->ring, ring.data(), sizeof(float4) * N, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete h; return fail_cuda("circular reset table", e); }
+  }
+  *out = h;
+  return 0;
+}
+
+int uavca_destroy(uavca_handle* h) {
+  if (!h) return 0;
+  DeviceGuard g(h->device);
+  if (h->ring) cudaFree(h->ring);
+  for (auto& s : h->hs) if (s) cudaStreamDestroy(s);
+  if (h->d_action) cudaFree(h->d_action);
+  if (h->d_obs) cudaFree(h->d_obs);
+  if (h->d_reward) cudaFree(h->d_reward);
+  if (h->d_done) cudaFree(h->d_done);
+  delete h;
+  return 0;
+}
+
+int uavca_get_config(const uavca_handle* h, uavca_config* out) {
+  if (int rc = check_handle(h)) return rc;
+  if (!out) return fail(-1, "null argument");
+  *out = h->cfg;
+  return 0;
+}
+
+int uavca_state_layout(const uavca_handle* h, uavca_layout* out) {
+  if (int rc = check_handle(h)) return rc;
+  if (!out) return fail(-1, "null argument");
+  *out = h->layout;
+  return 0;
+}
+
+int uavca_pool_layout(const uavca_handle* h, int32_t pool_envs, uavca_layout* out) {
+  if (int rc = check_handle(h)) return rc;
+  if (!out || pool_envs <= 0) return fail(-1, "bad pool_envs / null argument");
+  compute_layout(pool_envs, h->cfg.num_agents, out);
+  return 0;
+}
+
+int uavca_set_reset_pool(uavca_handle* h, const void* pool_state, int32_t pool_envs) {
+  if (int rc = check_handle(h)) return rc;
+  if (pool_state == nullptr || pool_envs <= 0) {
+    h->pool_blob = nullptr; h->pool_envs = 0;
+    return 0;
+  }
+  h->pool_blob = pool_state;
+  h->pool_envs = pool_envs;
+  compute_layout(pool_envs, h->cfg.num_agents, &h->pool_layout);
+  return 0;
+}
+
+int uavca_reset(uavca_handle* h, void* state, const uint8_t* mask, float* obs, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!state) return fail(-1, "null state");
+  if (h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
+  DeviceGuard g(h->device);
+  KernelArgs a = make_args(h, state);
+  a.io.obs = obs;
+  cudaError_t e = h->cfg.kind == UAVCA_KIND_SINGLE ? launch_reset_single(a, mask, (cudaStream_t)stream)
+                                                   : launch_reset_multi(a, mask, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_reset", e);
+  h->launches += 1;
+  return 0;
+}
+
+int uavca_observe(uavca_handle* h, const void* state, float* obs, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!state || !obs) return fail(-1, "null argument");
+  DeviceGuard g(h->device);
+  KernelArgs a = make_args(h, const_cast<void*>(state));
+  a.io.obs = obs;
+  cudaError_t e = h->cfg.kind == UAVCA_KIND_SINGLE ? launch_observe_single(a, (cudaStream_t)stream)
+                                                   : launch_observe_multi(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_observe", e);
+  h->launches += 1;
+  return 0;
+}
+
+int uavca_step_multi(uavca_handle* h, void* state, const float* action, int action_mode, int evaluate, float* obs,
+                     float* reward, uint8_t* done, float* final_obs, uint8_t* reset_mask, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.kind != UAVCA_KIND_MULTI) return fail(-1, "uavca_step_multi on a single-UAV handle");
+  if (!state || !action || !obs || !reward || !done) return fail(-1, "null argument");
+  if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
+  if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
+  DeviceGuard g(h->device);
+  KernelArgs a = make_args(h, state);
+  a.io.action = reinterpret_cast<const float2*>(action);
+  a.io.obs = obs; a.io.reward = reward; a.io.done = done; a.io.final_obs = final_obs; a.io.reset_mask = reset_mask;
+  a.io.action_mode = action_mode; a.io.evaluate = evaluate;
+  cudaError_t e = launch_step_multi(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_step_multi", e);
+  h->launches += 1;
+  return 0;
+}
+
+int uavca_step_single(uavca_handle* h, void* state, const float* action, int action_mode, float* obs, float* reward,
+                      uint8_t* done, float* distance, float* final_obs, uint8_t* reset_mask, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.kind != UAVCA_KIND_SINGLE) return fail(-1, "uavca_step_single on a multi-UAV handle");
+  if (!state || !action || !obs || !reward || !done) return fail(-1, "null argument");
+  if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
+  if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
+  DeviceGuard g(h->device);
+  KernelArgs a = make_args(h, state);
+  a.io.action = reinterpret_cast<const float2*>(action);
+  a.io.obs = obs; a.io.reward = reward; a.io.done = done; a.io.final_obs = final_obs; a.io.reset_mask = reset_mask;
+  a.io.distance = distance; a.io.action_mode = action_mode;
+  cudaError_t e = launch_step_single(a, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_step_single", e);
+  h->launches += 1;
+  return 0;
+}
+
+int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* out, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!in || !out) return fail(-1, "null argument");
+  if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_map_action(h->consts, in, out, (long long)h->cfg.num_envs * h->cfg.num_agents, action_mode,
+                                    (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_map_action", e);
+  h->launches += 1;
+  return 0;
+}
+
+int uavca_stats(uavca_handle* h, const void* state, int64_t* out8, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!state || !out8) return fail(-1, "null argument");
+  DeviceGuard g(h->device);
+  StateView s = view_of(const_cast<void*>(state), h->layout);
+  cudaError_t e = launch_stats(s, h->cfg.num_envs, reinterpret_cast<long long*>(out8), (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_stats", e);
+  h->launches += 1;
+  return 0;
+}
+
+int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int action_mode, int evaluate,
+                    float* host_obs, float* host_reward, uint8_t* host_done) {
+  if (int rc = check_handle(h)) return rc;
+  if (!state || !host_action || !host_obs || !host_reward || !host_done) return fail(-1, "null argument");
+  if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
+  if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
+  DeviceGuard g(h->device);
+  const int B = h->cfg.num_envs, N = h->cfg.num_agents;
+  const int D = h->cfg.kind == UAVCA_KIND_SINGLE ? UAVCA_OBS_DIM_SINGLE : UAVCA_OBS_DIM_MULTI;
+  const size_t M = (size_t)B * N;
+  cudaError_t e = cudaSuccess;
+  if (!h->d_action) {
+    for (auto& s : h->hs) {
+      e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+      if (e != cudaSuccess) return fail_cuda("stream create", e);
+    }
+    if ((e = cudaMalloc(&h->d_action, M * 2 * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_obs, M * D * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_reward, M * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
+    if ((e = cudaMalloc(&h->d_done, M)) != cudaSuccess) return fail_cuda("cudaMalloc", e);
+  }
+  // the caller's earlier work on `state` (any stream) must be visible before the internal streams touch it
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail_cuda("device synchronize", e);
+  // chunk the env range so that H2D of chunk k+1, the step of chunk k and D2H of chunk k-1 overlap
+  int chunks = 8;
+  long long per = ((long long)B + chunks - 1) / chunks;
+  per = (per + 63) / 64 * 64;  // keeps every chunk's rows 16-byte aligned for any N
+  if (per <= 0) per = 64;
+  for (long long env0 = 0, k = 0; env0 < B; env0 += per, ++k) {
+    const long long nb = (env0 + per <= B) ? per : (B - env0);
+    const size_t m0 = (size_t)env0 * N, mc = (size_t)nb * N;
+    cudaStream_t st = h->hs[k % uavca_handle::kHostStreams];
+    if ((e = cudaMemcpyAsync(h->d_action + m0 * 2, host_action + m0 * 2, mc * 2 * sizeof(float), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+      return fail_cuda("H2D action", e);
+    KernelArgs a = make_args(h, state);
+    a.s = offset_view(a.s, env0, N);
+    a.c.env_base += env0;
+    a.B = (int)nb;
+    a.io.action = reinterpret_cast<const float2*>(h->d_action + m0 * 2);
+    a.io.obs = h->d_obs + m0 * D; a.io.reward = h->d_reward + m0; a.io.done = h->d_done + m0;
+    a.io.action_mode = action_mode; a.io.evaluate = evaluate;
+    e = h->cfg.kind == UAVCA_KIND_SINGLE ? launch_step_single(a, st) : launch_step_multi(a, st);
+    if (e != cudaSuccess) return fail_cuda("uavca_step_host launch", e);
+    h->launches += 1;
+    if ((e = cudaMemcpyAsync(host_obs + m0 * D, h->d_obs + m0 * D, mc * D * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+      return fail_cuda("D2H obs", e);
+    if ((e = cudaMemcpyAsync(host_reward + m0, h->d_reward + m0, mc * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+      return fail_cuda("D2H reward", e);
+    if ((e = cudaMemcpyAsync(host_done + m0, h->d_done + m0, mc, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+      return fail_cuda("D2H done", e);
+  }
+  for (auto& s : h->hs)
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return fail_cuda("stream synchronize", e);
+  return 0;
+}
+
+int64_t uavca_launch_count(const uavca_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+// uavca_device.cuh — device-side building blocks of the batched env step (sm_100a).
+//
+// Numerics contract: everything that feeds a comparison in the reference — velocity (float64),
+// position (float32, one rounding of a float64 sum), float32 distances formed as sqrt(x*x + y*y) without
+// fusion — is reproduced with explicit round-to-nearest intrinsics so that nvcc's FMA contraction cannot
+// change a bit.  Quantities that are outputs only (reward, observation features) are computed to well inside
+// the 1e-5 relative tolerance with cheaper single-precision transcendental code.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/uavca.h"
+
+namespace uavca {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned kMaxResetAttempts = 4096u;  // the reference would loop forever in an over-crowded box
+
+enum : int { kStreamPos = 0, kStreamTgt = 1, kStreamVel = 2 };
+
+// Constants derived once on the host from uavca_config (capi.cu: derive_consts).
+struct Consts {
+  // float64 kinematics (uav_agent.py:26-29)
+  double tau, inv_tau, amax, vmax;
+  double clip_x;        // least x >= 0 with fl(x / tau) >= amax: beyond it the acceleration clip decides
+  double vm2, inv_vm2;  // ||(vmax, vmax)|| as np.linalg.norm computes it, and its reciprocal
+  double lox, hix, loy, hiy;  // box (float64 compare, multi_uav_world_2d.py:213,224)
+  double reach_speed_sq;      // least s with sqrt(s) >= reach_speed: ||v|| < reach_speed  <=>  s < this
+  // float32 thresholds (python scalars are weak against float32 norms under NumPy 2)
+  float two_r, two_h, dsense, reach_dist;
+  float inv_diag, inv_vm2_f, inv_vmax_f, inv_pi;
+  float polar_scale, vmax_f, tau_f;
+  // episode control
+  int reset_mode, max_steps, reset_source, circular, single_f32_first_step;
+  unsigned seed_lo, seed_hi;
+  long long env_base;
+};
+
+// Structure-of-arrays state of one shard (pointers into the caller's blob).
+struct StateView {
+  float2* pos;
+  double2* vel;
+  float2* tgt;
+  float* init;
+  float* prev;
+  uint8_t* flags;
+  int* steps;
+  int* reach;
+  int* coll;
+  unsigned* episode;
+  unsigned long long* stats;
+};
+
+struct StepIO {
+  const float2* action;
+  float* obs;
+  float* reward;
+  uint8_t* done;
+  float* final_obs;     // nullable
+  uint8_t* reset_mask;  // nullable
+  float* distance;      // nullable (single world)
+  int action_mode;
+  int evaluate;
+};
+
+struct KernelArgs {
+  Consts c;
+  StateView s;
+  StateView pool;  // reset pool (pos == nullptr when absent)
+  int pool_envs;
+  const float4* ring;  // circular reset table [N]: (pos.x, pos.y, tgt.x, tgt.y), nullable
+  StepIO io;
+  int B, N;
+};
+
+// ---- exact float32 / float64 primitives ------------------------------------------------------------------
+
+// squared float32 norm the way np.linalg.norm forms it: products and sum rounded separately (never fused)
+__device__ __forceinline__ float sq32(float dx, float dy) {
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+__device__ __forceinline__ float n32(float dx, float dy) { return __fsqrt_rn(sq32(dx, dy)); }
+
+// squared float64 norm as the ddot kernel forms it: second product fused
+__device__ __forceinline__ double sq64(double x, double y) { return fma(y, y, __dmul_rn(x, x)); }
+
+__device__ __forceinline__ double clipd(double v, double lo, double hi) {
+  // np.clip: NaN propagates (both comparisons are false)
+  v = (v < lo) ? lo : v;
+  v = (v > hi) ? hi : v;
+  return v;
+}
+
+// Correctly rounded x / tau from the reciprocal and two FMA residual corrections (Markstein): after the first
+// correction the quotient is faithful, after the second it is the round-to-nearest quotient.  Bit-identical
+// to IEEE division for every finite x in the unclipped range; 5 DP instructions instead of ~25.
+__device__ __forceinline__ double div_tau(double x, const Consts& c) {
+  double q0 = __dmul_rn(x, c.inv_tau);
+  double r0 = fma(-q0, c.tau, x);
+  double q1 = fma(r0, c.inv_tau, q0);
+  double r1 = fma(-q1, c.tau, x);
+  return fma(r1, c.inv_tau, q1);
+}
+
+// dv = clip((a - v) / tau, -amax, amax)            (uav_agent.py:26)
+__device__ __forceinline__ double accel(double a, double v, const Consts& c) {
+  double x = __dsub_rn(a, v);
+  double q = div_tau(x, c);
+  // |x| >= clip_x  <=>  |fl(x/tau)| >= amax: the clip decides and the quotient (possibly inf/NaN for huge x) is unused
+  q = (x >= c.clip_x) ? c.amax : q;
+  q = (x <= -c.clip_x) ? -c.amax : q;
+  return q;
+}
+
+// One UAV kinematic update: v = clip(v + dv*tau, +-vmax); p = float32(float64(p) + v*tau)   (uav_agent.py:27-29)
+__device__ __forceinline__ void integrate(double ax, double ay, double& vx, double& vy, float& px, float& py,
+                                          const Consts& c) {
+  double dvx = accel(ax, vx, c), dvy = accel(ay, vy, c);
+  vx = clipd(__dadd_rn(vx, __dmul_rn(dvx, c.tau)), -c.vmax, c.vmax);
+  vy = clipd(__dadd_rn(vy, __dmul_rn(dvy, c.tau)), -c.vmax, c.vmax);
+  px = __double2float_rn(__dadd_rn((double)px, __dmul_rn(vx, c.tau)));
+  py = __double2float_rn(__dadd_rn((double)py, __dmul_rn(vy, c.tau)));
+}
+
+// wrap(atan2(dy,dx) - atan2(hy,hx)) as ONE atan2f of the float64 cross/dot products of the two directions
+// (relative error ~2 ulp float32 even for tiny angles; atan2(0,0)=0 makes a zero heading point along +x).
+__device__ __forceinline__ float rel_angle(double dx, double dy, double hx, double hy) {
+  const bool hzero = (hx == 0.0) & (hy == 0.0);
+  const bool dzero = (dx == 0.0) & (dy == 0.0);
+  hx = hzero ? 1.0 : hx;
+  dx = dzero ? 1.0 : dx;
+  double cr = fma(hx, dy, -(hy * dx));
+  double dt = fma(hx, dx, hy * dy);
+  return atan2f((float)cr, (float)dt);
+}
+
+// Caller-side action mapping (test_sac_multi.py:77-80; test_pytorch_multi.py:80).
+__device__ __forceinline__ float2 map_action(float2 a, int mode, const Consts& c) {
+  if (mode == UAVCA_ACTION_POLAR) {
+    float v = __fmul_rn(__fadd_rn(__fmul_rn(a.x, 0.5f), 0.5f), c.polar_scale);
+    float th = __fmul_rn(a.y, 3.14159274101257324f);
+    float sn, cs;
+    sincosf(th, &sn, &cs);
+    return make_float2(__fmul_rn(v, cs), __fmul_rn(v, sn));
+  }
+  if (mode == UAVCA_ACTION_SCALED) return make_float2(__fmul_rn(a.x, c.vmax_f), __fmul_rn(a.y, c.vmax_f));
+  return a;
+}
+
+// ---- Philox4x32-10 -------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                               uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
+  return __dmul_rn(__dadd_rn(__dmul_rn((double)(a >> 5), 67108864.0), (double)(b >> 6)), 1.0 / 9007199254740992.0);
+}
+
+// float32(np.random.uniform(lo, hi)) per component: lo + (hi-lo)*u, two roundings, then the float32 cast
+__device__ __forceinline__ float2 draw_pair(const Consts& c, long long env_global, uint32_t episode, int stream,
+                                            int uav, uint32_t attempt, double lox, double hix, double loy,
+                                            double hiy) {
+  uint4 r = philox4x32_10((uint32_t)env_global, episode, ((uint32_t)stream << 16) | (uint32_t)uav, attempt, c.seed_lo,
+                          c.seed_hi);
+  double ux = u53(r.x, r.y), uy = u53(r.z, r.w);
+  float x = __double2float_rn(__dadd_rn(lox, __dmul_rn(__dsub_rn(hix, lox), ux)));
+  float y = __double2float_rn(__dadd_rn(loy, __dmul_rn(__dsub_rn(hiy, loy), uy)));
+  return make_float2(x, y);
+}
+
+// ---- streaming loads / stores ----------------------------------------------------------------------------------
+// State and I/O are touched exactly once per step: keep them out of L1 (no reuse) but let L2 write-back merge.
+
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) {
+  return __ldcs(p);
+}
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, T v) {
+  __stcs(p, v);
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(kFull, v, src); }
+
+}  // namespace uavca

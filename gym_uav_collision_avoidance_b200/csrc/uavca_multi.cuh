@@ -1,0 +1,241 @@
+// uavca_multi.cuh — warp-cooperative pieces of the multi-UAV world (MultiUAVWorld2D) shared by the step,
+// reset and observe kernels.
+//
+// Thread mapping: one lane per UAV, the N lanes of an env are adjacent in one warp, floor(32/N) envs per warp.
+// The flat UAV index of lane l in (global) warp w is  w * lanes_used + l, so every per-UAV array is read and
+// written as one contiguous, coalesced run per warp.  Neighbour data never touches memory: lanes exchange
+// positions and velocities with __shfl_sync.
+#pragma once
+
+#include "uavca_device.cuh"
+
+namespace uavca {
+
+struct Lane {
+  int N;           // UAVs per env
+  int lanes_used;  // floor(32/N) * N
+  int lane;
+  int i;            // UAV index inside its env
+  int base;         // first lane of this lane's env
+  unsigned envmask; // N low bits
+  long long env;    // env index inside the shard
+  long long m;      // flat UAV index env*N + i
+  long long warp_m0;  // flat UAV index of lane 0 of this warp
+  int valid_lanes;  // lanes of this warp that map to real UAVs (a prefix)
+  bool valid;
+};
+
+template <int NT>
+__device__ __forceinline__ Lane make_lane(int B, int Nrt) {
+  Lane L;
+  L.N = NT > 0 ? NT : Nrt;
+  const int epw = 32 / L.N;
+  L.lanes_used = epw * L.N;
+  L.lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int e_local = L.lane / L.N;
+  L.i = L.lane - e_local * L.N;
+  L.base = e_local * L.N;
+  L.envmask = L.N >= 32 ? 0xffffffffu : ((1u << L.N) - 1u);
+  L.env = warp_global * epw + e_local;
+  L.warp_m0 = warp_global * L.lanes_used;
+  long long left = ((long long)B - warp_global * epw) * L.N;
+  L.valid_lanes = left <= 0 ? 0 : (left < L.lanes_used ? (int)left : L.lanes_used);
+  L.valid = L.lane < L.valid_lanes;
+  L.m = L.warp_m0 + L.lane;
+  if (!L.valid) { L.base = L.lane; L.i = 0; L.envmask = 1u; }  // idle lanes only ever talk to themselves
+  return L;
+}
+
+struct Uav {
+  float px, py, tx, ty, init, prev;
+  double vx, vy;
+  unsigned flags;
+};
+
+__device__ __forceinline__ Uav load_uav(const StateView& s, const Lane& L) {
+  Uav u;
+  if (L.valid) {
+    float2 p = ld_stream(s.pos + L.m);
+    double2 v = ld_stream(s.vel + L.m);
+    float2 t = ld_stream(s.tgt + L.m);
+    u.init = ld_stream(s.init + L.m);
+    u.prev = ld_stream(s.prev + L.m);
+    u.flags = ld_stream(s.flags + L.m);
+    u.px = p.x; u.py = p.y; u.vx = v.x; u.vy = v.y; u.tx = t.x; u.ty = t.y;
+  } else {
+    u.px = u.py = u.tx = u.ty = 0.f; u.init = u.prev = 1.f; u.vx = u.vy = 0.0; u.flags = 0u;
+  }
+  return u;
+}
+
+__device__ __forceinline__ void store_uav(const StateView& s, const Lane& L, const Uav& u, bool with_target) {
+  if (!L.valid) return;
+  st_stream(s.pos + L.m, make_float2(u.px, u.py));
+  st_stream(s.vel + L.m, make_double2(u.vx, u.vy));
+  st_stream(s.prev + L.m, u.prev);
+  st_stream(s.flags + L.m, (uint8_t)u.flags);
+  if (with_target) {
+    st_stream(s.tgt + L.m, make_float2(u.tx, u.ty));
+    st_stream(s.init + L.m, u.init);
+  }
+}
+
+// Two nearest other UAVs of the env, ordered by (squared float32 distance, index).
+struct Top2 {
+  float s1, s2;
+  int j1, j2;
+};
+
+__device__ __forceinline__ void top2_insert(Top2& t, float s, int j) {
+  if (s < t.s1) { t.s2 = t.s1; t.j2 = t.j1; t.s1 = s; t.j1 = j; }
+  else if (s < t.s2) { t.s2 = s; t.j2 = j; }
+}
+
+template <int NT>
+__device__ __forceinline__ Top2 top2_scan(const Lane& L, float px, float py) {
+  Top2 t{__int_as_float(0x7f800000), __int_as_float(0x7f800000), -1, -1};
+  const int N = NT > 0 ? NT : L.N;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    float qx = __shfl_sync(kFull, px, L.base + j), qy = __shfl_sync(kFull, py, L.base + j);
+    float s = sq32(__fsub_rn(qx, px), __fsub_rn(qy, py));
+    if (j != L.i) top2_insert(t, s, j);
+  }
+  return t;
+}
+
+// MultiUAVWorld2D._get_obs (multi_uav_world_2d.py:60-109) for this lane's UAV.  All lanes of the warp must call.
+__device__ __forceinline__ void obs_multi(const Consts& c, const Lane& L, const Uav& u, const Top2& t, float o[10]) {
+  o[0] = sqrtf((float)sq64(u.vx, u.vy)) * c.inv_vm2_f;                 // :62
+  o[1] = atan2f((float)u.vy, (float)u.vx) * c.inv_pi;                  // :63-64
+  const float tdx = __fsub_rn(u.tx, u.px), tdy = __fsub_rn(u.ty, u.py);
+  o[2] = n32(tdx, tdy) * c.inv_diag;                                   // :67-68
+  o[3] = rel_angle((double)tdx, (double)tdy, u.vx, u.vy) * c.inv_pi;   // :69-72
+  const float d1 = __fsqrt_rn(t.s1), d2 = __fsqrt_rn(t.s2);
+  const bool have1 = (t.j1 >= 0) & (d1 < c.dsense);                    // uav_agent.py:52 strict <
+  const bool have2 = have1 & (t.j2 >= 0) & (d2 < c.dsense);
+  const int src1 = L.base + (t.j1 < 0 ? 0 : t.j1), src2 = L.base + (t.j2 < 0 ? 0 : t.j2);
+  const float n1x = __shfl_sync(kFull, u.px, src1), n1y = __shfl_sync(kFull, u.py, src1);
+  const float n2x = __shfl_sync(kFull, u.px, src2), n2y = __shfl_sync(kFull, u.py, src2);
+  const double n1vx = shfl_d(u.vx, src1), n1vy = shfl_d(u.vy, src1);
+  const double n2vx = shfl_d(u.vx, src2), n2vy = shfl_d(u.vy, src2);
+  const float b1 = rel_angle((double)__fsub_rn(n1x, u.px), (double)__fsub_rn(n1y, u.py), u.vx, u.vy) * c.inv_pi;
+  const float h1 = rel_angle(n1vx, n1vy, u.vx, u.vy) * c.inv_pi;
+  const float b2 = rel_angle((double)__fsub_rn(n2x, u.px), (double)__fsub_rn(n2y, u.py), u.vx, u.vy) * c.inv_pi;
+  const float h2 = rel_angle(n2vx, n2vy, u.vx, u.vy) * c.inv_pi;
+  o[4] = have1 ? __fdiv_rn(d1, c.dsense) : 1.0f;                       // :77
+  o[5] = have1 ? b1 : 1.0f;                                            // :78-81 (no neighbour: bearing pi)
+  o[6] = have1 ? h1 : 0.0f;                                            // :82-85
+  o[7] = have2 ? __fdiv_rn(d2, c.dsense) : 1.0f;                       // :87
+  o[8] = have2 ? b2 : 1.0f;                                            // :88-91
+  o[9] = have2 ? h2 : 0.0f;                                            // :92-95
+}
+
+// Write the warp's observation rows as one contiguous run of 16-byte stores (staged through shared memory;
+// a per-thread row is 40 bytes, which would otherwise scatter 8-byte stores 40 bytes apart).
+__device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const Lane& L, const float o[10]) {
+  float2* st2 = reinterpret_cast<float2*>(stage) + L.lane * 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) st2[k] = make_float2(o[2 * k], o[2 * k + 1]);
+  __syncwarp();
+  float* g = gobs + L.warp_m0 * 10;
+  const int n2 = L.valid_lanes * 5;  // float2 elements to write
+  if ((L.lanes_used & 1) == 0) {     // every warp's run starts on a 16-byte boundary
+    const int n4 = n2 >> 1;
+    const float4* s4 = reinterpret_cast<const float4*>(stage);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    for (int k = L.lane; k < n4; k += 32) st_stream(g4 + k, s4[k]);
+    if ((n2 & 1) && L.lane == 0) st_stream(reinterpret_cast<float2*>(g) + (n2 - 1), reinterpret_cast<const float2*>(stage)[n2 - 1]);
+  } else {
+    const float2* s2 = reinterpret_cast<const float2*>(stage);
+    float2* g2 = reinterpret_cast<float2*>(g);
+    for (int k = L.lane; k < n2; k += 32) st_stream(g2 + k, s2[k]);
+  }
+  __syncwarp();
+}
+
+// Start a new episode for the envs of this warp whose lanes pass do_reset (env-uniform).  Restates
+// MultiUAVWorld2D.reset (multi_uav_world_2d.py:116-168): sequential rejection sampling — UAV i is re-drawn until it
+// is farther than 2r from every UAV j<i, targets likewise plus farther than 2r from the UAV's own start.  The
+// sequential dependency is kept (UAV `cur` is settled only after 0..cur-1), but each test runs across the lanes of
+// the env at once.  All lanes of the warp must call.  `episode` is this env's episode counter BEFORE the reset.
+__device__ __forceinline__ void reset_multi(const KernelArgs& a, const Lane& L, bool do_reset, unsigned episode, Uav& u) {
+  const Consts& c = a.c;
+  const long long env_global = c.env_base + L.env;
+  if (c.reset_source == UAVCA_SOURCE_POOL && a.pool.pos != nullptr) {
+    if (do_reset) {
+      const long long p = (env_global + (long long)episode) % a.pool_envs;
+      const long long pm = p * L.N + L.i;
+      float2 pp = a.pool.pos[pm], pt = a.pool.tgt[pm];
+      double2 pv = a.pool.vel[pm];
+      u.px = pp.x; u.py = pp.y; u.tx = pt.x; u.ty = pt.y; u.vx = pv.x; u.vy = pv.y;
+      u.init = a.pool.init[pm]; u.prev = a.pool.prev[pm]; u.flags = a.pool.flags[pm];
+    }
+    return;
+  }
+  const int N = L.N;
+  // ---- start positions (:126-137)
+  unsigned attempt = 0;
+  float2 cand = make_float2(0.f, 0.f);
+  if (do_reset) cand = draw_pair(c, env_global, episode, kStreamPos, L.i, 0u, c.lox, c.hix, c.loy, c.hiy);
+  int cur = do_reset ? 1 : N;
+  while (__any_sync(kFull, cur < N)) {
+    const bool active = cur < N;
+    const int src = L.base + (active ? cur : 0);
+    const float qx = __shfl_sync(kFull, cand.x, src), qy = __shfl_sync(kFull, cand.y, src);
+    const unsigned att = __shfl_sync(kFull, attempt, src);
+    const bool conflict = active && (L.i < cur) && (n32(__fsub_rn(cand.x, qx), __fsub_rn(cand.y, qy)) <= c.two_r);
+    const unsigned bal = __ballot_sync(kFull, conflict);
+    const bool env_conflict = ((bal >> L.base) & L.envmask) != 0u;
+    if (active) {
+      if (env_conflict && att + 1u < kMaxResetAttempts) {
+        if (L.i == cur) {
+          ++attempt;
+          cand = draw_pair(c, env_global, episode, kStreamPos, L.i, attempt, c.lox, c.hix, c.loy, c.hiy);
+        }
+      } else {
+        ++cur;
+      }
+    }
+  }
+  // ---- targets (:140-153)
+  float2 tg = make_float2(0.f, 0.f);
+  attempt = 0;
+  if (do_reset) tg = draw_pair(c, env_global, episode, kStreamTgt, L.i, 0u, c.lox, c.hix, c.loy, c.hiy);
+  cur = do_reset ? 0 : N;
+  while (__any_sync(kFull, cur < N)) {
+    const bool active = cur < N;
+    const int src = L.base + (active ? cur : 0);
+    const float qx = __shfl_sync(kFull, tg.x, src), qy = __shfl_sync(kFull, tg.y, src);
+    const unsigned att = __shfl_sync(kFull, attempt, src);
+    bool conflict = false;
+    if (active && L.i < cur) conflict = n32(__fsub_rn(tg.x, qx), __fsub_rn(tg.y, qy)) <= c.two_r;
+    if (active && L.i == cur) conflict = n32(__fsub_rn(tg.x, cand.x), __fsub_rn(tg.y, cand.y)) <= c.two_r;
+    const unsigned bal = __ballot_sync(kFull, conflict);
+    const bool env_conflict = ((bal >> L.base) & L.envmask) != 0u;
+    if (active) {
+      if (env_conflict && att + 1u < kMaxResetAttempts) {
+        if (L.i == cur) {
+          ++attempt;
+          tg = draw_pair(c, env_global, episode, kStreamTgt, L.i, attempt, c.lox, c.hix, c.loy, c.hiy);
+        }
+      } else {
+        ++cur;
+      }
+    }
+  }
+  if (do_reset) {
+    if (c.circular && a.ring != nullptr) {  // :157-163 (host-computed ring, rounded to float32)
+      float4 r = a.ring[L.i];
+      cand = make_float2(r.x, r.y);
+      tg = make_float2(r.z, r.w);
+    }
+    u.px = cand.x; u.py = cand.y; u.tx = tg.x; u.ty = tg.y;
+    u.vx = 0.0; u.vy = 0.0; u.flags = 0u;                              // :118-123
+    u.init = n32(__fsub_rn(u.tx, u.px), __fsub_rn(u.ty, u.py));        // :154
+    u.prev = u.init;                                                   // :155
+  }
+}
+
+}  // namespace uavca

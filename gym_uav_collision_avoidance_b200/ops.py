@@ -1,0 +1,83 @@
+"""PyTorch custom ops over the C-ABI (include/uavca.h).
+
+Each op hands `tensor.data_ptr()` of CUDA tensors and torch's current CUDA stream to the shim; nothing is
+copied and nothing runs on the CPU.  Outputs are written into caller-provided tensors (``mutates_args``) so the
+observation / reward / done buffers are handed zero-copy to the policy and the replay buffer, and so the ops
+can be captured in CUDA graphs.  The handle travels as an integer (the `uavca_handle*`).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _capi
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _capi.UavcaError("uavca ops take CUDA tensors only (there is no CPU fallback)")
+        if t is not None and not t.is_contiguous():
+            raise _capi.UavcaError("uavca ops take contiguous tensors")
+
+
+@torch.library.custom_op("uavca::step_multi", mutates_args=("state", "obs", "reward", "done", "final_obs", "reset_mask"))
+def step_multi(handle: int, state: torch.Tensor, action: torch.Tensor, action_mode: int, evaluate: bool,
+               obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, final_obs: Optional[torch.Tensor],
+               reset_mask: Optional[torch.Tensor]) -> None:
+    """MultiUAVWorld2D.step for B envs x N UAVs (multi_uav_world_2d.py:177-241)."""
+    _need_cuda(state, action, obs, reward, done, final_obs, reset_mask)
+    _capi.check(_capi.load().uavca_step_multi(handle, state.data_ptr(), action.data_ptr(), action_mode, int(evaluate),
+                                              obs.data_ptr(), reward.data_ptr(), done.data_ptr(), _ptr(final_obs),
+                                              _ptr(reset_mask), _stream(state)), "uavca_step_multi")
+
+
+@torch.library.custom_op("uavca::step_single",
+                         mutates_args=("state", "obs", "reward", "done", "distance", "final_obs", "reset_mask"))
+def step_single(handle: int, state: torch.Tensor, action: torch.Tensor, action_mode: int, obs: torch.Tensor,
+                reward: torch.Tensor, done: torch.Tensor, distance: Optional[torch.Tensor],
+                final_obs: Optional[torch.Tensor], reset_mask: Optional[torch.Tensor]) -> None:
+    """UAVWorld2D.step for B envs (uav_world_2d.py:137-173)."""
+    _need_cuda(state, action, obs, reward, done, distance, final_obs, reset_mask)
+    _capi.check(_capi.load().uavca_step_single(handle, state.data_ptr(), action.data_ptr(), action_mode, obs.data_ptr(),
+                                               reward.data_ptr(), done.data_ptr(), _ptr(distance), _ptr(final_obs),
+                                               _ptr(reset_mask), _stream(state)), "uavca_step_single")
+
+
+@torch.library.custom_op("uavca::reset", mutates_args=("state", "obs"))
+def reset(handle: int, state: torch.Tensor, mask: Optional[torch.Tensor], obs: torch.Tensor) -> None:
+    """reset() of all (mask=None) or the masked envs (multi_uav_world_2d.py:116-175, uav_world_2d.py:119-135)."""
+    _need_cuda(state, mask, obs)
+    _capi.check(_capi.load().uavca_reset(handle, state.data_ptr(), _ptr(mask), obs.data_ptr(), _stream(state)),
+                "uavca_reset")
+
+
+@torch.library.custom_op("uavca::observe", mutates_args=("obs",))
+def observe(handle: int, state: torch.Tensor, obs: torch.Tensor) -> None:
+    """_get_obs() of the current state (multi_uav_world_2d.py:60-109, uav_world_2d.py:77-112)."""
+    _need_cuda(state, obs)
+    _capi.check(_capi.load().uavca_observe(handle, state.data_ptr(), obs.data_ptr(), _stream(state)), "uavca_observe")
+
+
+@torch.library.custom_op("uavca::map_action", mutates_args=("out",))
+def map_action(handle: int, action: torch.Tensor, action_mode: int, out: torch.Tensor) -> None:
+    """Caller-side action mapping (test_sac_multi.py:77-80, test_pytorch_multi.py:80)."""
+    _need_cuda(action, out)
+    _capi.check(_capi.load().uavca_map_action(handle, action.data_ptr(), action_mode, out.data_ptr(), _stream(action)),
+                "uavca_map_action")
+
+
+@torch.library.custom_op("uavca::stats", mutates_args=("out8",))
+def stats(handle: int, state: torch.Tensor, out8: torch.Tensor) -> None:
+    """Episode statistics (env.steps / target_reach_count / collision_count, multi_uav_world_2d.py:166-168)."""
+    _need_cuda(state, out8)
+    _capi.check(_capi.load().uavca_stats(handle, state.data_ptr(), out8.data_ptr(), _stream(state)), "uavca_stats")

@@ -437,7 +437,7 @@ static void step_env_single(const uavca_config* c, uavo_state* s, int b, const f
   r = r - (float)(0.1 * fabs(dth));                                    /* :157 python float is weak -> float32 */
   const int oob = !((double)pos[0] >= lox && (double)pos[0] <= hix && (double)pos[1] >= loy && (double)pos[1] <= hiy);
   int d;
-  if (dist < (float)c->reach_distance) { d = 1; r = r + 1000.0f; }     /* :159-161 */
+  if (dist < (float)c->reach_distance) { d = 1; r = r + 1000.0f; s->reach[b] += 1; } /* :159-161 (+ our success counter) */
   else if (oob) d = 1;                                                 /* :162-163 */
   else d = 0;
   obs_single(c, pos, vel, tgt, 0, obs);                                /* :168 */

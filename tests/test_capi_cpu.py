@@ -1,0 +1,90 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/uavca.h declares; configuration and
+layout logic (no kernel launches); the product fails loudly without a GPU and never touches the oracle."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from gym_uav_collision_avoidance_b200 import _capi, build
+
+    build.build()
+    return _capi
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "uavca.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(uavca_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound(capi):
+    lib = capi.load()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/uavca.h but not exported by libuavca.so"
+        assert n in capi.SYMBOLS, f"{n} has no ctypes prototype in _capi.SYMBOLS"
+    assert sorted(capi.SYMBOLS) == names
+    assert lib.uavca_version() == 100
+
+
+def test_default_configs_follow_the_reference_constructors(capi):
+    m = capi.default_config(capi.KIND_MULTI)  # multi_uav_world_2d.py:13,26,8
+    assert (m.x_size, m.y_size, m.max_speed, m.max_acceleration, m.num_agents) == (50.0, 50.0, 10.0, 5.0, 4)
+    assert (m.collider_radius, m.d_sense, m.tau, m.hard_collision_radius) == (1.0, 15.0, 0.02, 0.5)
+    assert abs(m.polar_scale - 200 ** 0.5) < 1e-6
+    s = capi.default_config(capi.KIND_SINGLE)  # uav_world_2d.py:14,26
+    assert (s.x_size, s.y_size, s.max_speed, s.max_acceleration, s.num_agents, s.tau) == (100.0, 100.0, 12.0, 5.0, 1, 0.02)
+
+
+def test_config_struct_matches_the_oracle_mirror(capi):
+    from oracle import oracle as O
+
+    assert C.sizeof(capi.Config) == C.sizeof(O.Config)
+    assert [f[0] for f in capi.Config._fields_] == [f[0] for f in O.Config._fields_]
+    for (n1, t1), (n2, t2) in zip(capi.Config._fields_, O.Config._fields_):
+        assert getattr(capi.Config, n1).offset == getattr(O.Config, n2).offset
+
+
+def test_create_fails_loudly_without_a_gpu(capi):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    cfg = capi.default_config(capi.KIND_MULTI)
+    h = C.c_void_p()
+    rc = capi.load().uavca_create(C.byref(cfg), 0, C.byref(h))
+    assert rc != 0 and "no CPU fallback" in capi.last_error()
+    import gym_uav_collision_avoidance_b200 as G
+
+    with pytest.raises(G.UavcaError):
+        G.BatchedMultiUAVWorld2D(8, num_agents=4)
+
+
+def test_bad_configs_are_rejected_before_touching_the_device(capi):
+    lib = capi.load()
+    for field, value in (("num_agents", 33), ("num_agents", 0), ("num_envs", 0), ("tau", 0.0), ("kind", 7)):
+        cfg = capi.default_config(capi.KIND_MULTI)
+        setattr(cfg, field, value)
+        h = C.c_void_p()
+        assert lib.uavca_create(C.byref(cfg), 0, C.byref(h)) == -1, field
+        assert capi.last_error()
+    cfg = capi.default_config(capi.KIND_SINGLE)
+    cfg.num_agents = 2
+    h = C.c_void_p()
+    assert lib.uavca_create(C.byref(cfg), 0, C.byref(h)) == -1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gym_uav_collision_avoidance_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"

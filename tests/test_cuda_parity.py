@@ -1,0 +1,413 @@
+"""GPU: the CUDA path (through the C-ABI / torch custom ops) against the oracle and the reference's golden vectors.
+
+Bar (BASELINE.json north_star): done / collision / reset flags, counters and env indexing bit-exact; positions
+(float32) and velocities (float64) bit-exact as well (they feed the flags); rewards and observations within
+1e-5 relative (+1e-6 absolute floor for values that cancel to ~0), angle features compared on the circle.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+from _golden import Case, golden_names, obs_close
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _b200():
+    import gym_uav_collision_avoidance_b200 as G
+
+    return G
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b) <= rtol * np.abs(b) + atol
+
+
+def make_env(cfg: O.Config, **kw):
+    G = _b200()
+    common = dict(seed=int(cfg.seed), reset_mode=cfg.reset_mode, max_episode_steps=cfg.max_episode_steps,
+                  reset_source=cfg.reset_source, env_index_base=int(cfg.env_index_base))
+    common.update(kw)
+    if cfg.kind == O.KIND_SINGLE:
+        return G.BatchedUAVWorld2D(cfg.num_envs, x_size=cfg.x_size, y_size=cfg.y_size, max_speed=cfg.max_speed,
+                                   max_acceleration=cfg.max_acceleration,
+                                   float32_first_step=bool(cfg.single_f32_first_step), **common)
+    return G.BatchedMultiUAVWorld2D(cfg.num_envs, x_size=cfg.x_size, y_size=cfg.y_size, max_speed=cfg.max_speed,
+                                    max_acceleration=cfg.max_acceleration, num_agents=cfg.num_agents,
+                                    collider_radius=cfg.collider_radius, d_sense=cfg.d_sense,
+                                    circular=bool(cfg.circular), **common)
+
+
+def load_state(blob, st: O.State):
+    blob.load_arrays(pos=st.pos, vel=st.vel, tgt=st.tgt, init=st.init, prev=st.prev, flags=st.flags, steps=st.steps,
+                     reach=st.reach, coll=st.coll, episode=st.episode.astype(np.int64))
+
+
+def assert_state_equal(env, st: O.State, where=""):
+    h = env.state.to_host()
+    for f in ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll"):
+        assert np.array_equal(h[f], getattr(st, f)), f"state field {f} differs {where}"
+    assert np.array_equal(h["episode"].astype(np.uint32), st.episode), f"episode counter differs {where}"
+
+
+def assert_outputs(env, out, where="", obs_ref=None):
+    obs_ref = out["obs"] if obs_ref is None else obs_ref
+    assert np.array_equal(env.done.cpu().numpy(), out["done"]), f"done flags differ {where}"
+    assert np.array_equal(env.reset_mask.cpu().numpy(), out["reset_mask"]), f"reset mask differs {where}"
+    rew = env.reward.cpu().numpy()
+    ok = close(rew, out["reward"])
+    assert ok.all(), f"reward outside tolerance {where}: {rew[~ok][:4]} vs {out['reward'][~ok][:4]}"
+    obs = env.obs.cpu().numpy()
+    ok = obs_close(obs, obs_ref, RTOL, ATOL)
+    assert ok.all(), f"obs outside tolerance {where}: idx {np.argwhere(~ok)[:4].tolist()} {obs[~ok][:4]} vs {obs_ref[~ok][:4]}"
+
+
+# ---- golden vectors produced by the literal reference ----------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_reference_golden(name):
+    case = Case(name)
+    cfg = case.config()
+    env = make_env(cfg)
+    env.enable_final_obs()
+    load_state(env.state, case.init_state())
+    pool_host = case.pool_state()
+    load_state(env.make_pool(pool_host.B), pool_host)
+    z = case.z
+    obs0 = env.observe().cpu().numpy()
+    assert obs_close(obs0, z["obs0"], RTOL, ATOL).all()
+    for t in range(case.T):
+        a = torch.from_numpy(z["action"][t]).cuda()
+        if case.kind == "single":
+            env.step(a)
+        else:
+            env.step(a, evaluate=case.evaluate)
+        w = f"({name}, step {t})"
+        assert np.array_equal(env.done.cpu().numpy(), z["done"][t]), f"done flags differ {w}"
+        assert np.array_equal(env.reset_mask.cpu().numpy(), z["reset_mask"][t]), f"reset mask differs {w}"
+        h = env.state.to_host()
+        assert np.array_equal(h["pos"], z["pos"][t]), f"positions differ {w}"
+        assert np.array_equal(h["vel"], z["vel"][t]), f"velocities differ {w}"
+        assert np.array_equal(h["prev"], z["prev"][t]), f"prev_distance differs {w}"
+        assert np.array_equal(h["steps"], z["steps"][t]), f"env.steps differs {w}"
+        if case.kind == "multi":
+            assert np.array_equal(h["flags"], z["flags"][t]), f"parked/collided latches differ {w}"
+            assert np.array_equal(h["reach"], z["reach"][t]), f"target_reach_count differs {w}"
+            assert np.array_equal(h["coll"], z["coll"][t]), f"collision_count differs {w}"
+        else:
+            assert np.array_equal(env.distance.cpu().numpy(), z["distance"][t]), f"info distance differs {w}"
+        assert close(env.reward.cpu().numpy(), z["reward"][t]).all(), f"reward {w}"
+        assert obs_close(env.obs.cpu().numpy(), z["obs"][t], RTOL, ATOL).all(), f"obs {w}"
+        assert obs_close(env.final_obs.cpu().numpy(), case.final_obs(t), RTOL, ATOL).all(), f"final obs {w}"
+
+
+# ---- rollouts against the oracle, with Philox auto-reset on both sides ----------------------------------------
+
+
+def rollout_vs_oracle(cfg: O.Config, steps, seed, evaluate=False, crowd=None, nthreads=8, check_every=1):
+    """Device and oracle start from the same Philox reset and see the same actions; compare every step."""
+    env = make_env(cfg)
+    orc = O.Oracle(cfg, nthreads=nthreads)
+    obs_dev = env.reset().cpu().numpy()
+    obs_orc = orc.reset()
+    assert_state_equal(env, orc.state, "after reset")
+    assert obs_close(obs_dev, obs_orc, RTOL, ATOL).all()
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    B, N = cfg.num_envs, cfg.num_agents
+    amax = float(cfg.max_speed)
+    events = dict(done=0, resets=0)
+    for t in range(steps):
+        a = (torch.rand((B, N, 2), generator=gen, device="cuda") * 2 - 1) * amax
+        if crowd is not None:  # pull UAVs towards the origin so that they meet
+            a = (a * 0.3 - env.state.pos * crowd).clamp(-amax, amax).contiguous()
+        if cfg.kind == O.KIND_SINGLE:
+            env.step(a)
+        else:
+            env.step(a, evaluate=evaluate)
+        out = orc.step(a.cpu().numpy(), evaluate=evaluate)
+        events["done"] += int(out["done"].sum())
+        events["resets"] += int(out["reset_mask"].sum())
+        if t % check_every == 0 or t == steps - 1:
+            assert_outputs(env, out, f"(step {t})")
+            assert_state_equal(env, orc.state, f"(step {t})")
+    st = env.stats()
+    assert st["episodes"] == int(orc.state.stats[0]) and st["reach"] == int(orc.state.stats[1])
+    assert st["collisions"] == int(orc.state.stats[2]) and st["steps"] == int(orc.state.stats[3])
+    assert st["live_steps"] == int(orc.state.steps.sum())
+    return events, orc
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 10, 13, 16, 17, 24, 31, 32])
+def test_multi_rollout_all_agent_counts(n):
+    """Every N in 1..32 maps to a different lane layout (specialised or generic kernel, ragged last warp)."""
+    B = 257  # not a multiple of any envs-per-warp: exercises the tail
+    cfg = O.multi_config(B, n, reset_mode=O.RESET_ON_DONE0, max_episode_steps=40, seed=1000 + n, x_size=24.0, y_size=24.0)
+    ev, _ = rollout_vs_oracle(cfg, steps=120, seed=n, crowd=0.4)
+    assert ev["resets"] > 0
+
+
+def test_multi_rollout_crowded_collisions_and_reaches():
+    cfg = O.multi_config(2048, 8, reset_mode=O.RESET_ON_ALL_DONE, max_episode_steps=300, seed=77, x_size=16.0, y_size=16.0)
+    ev, orc = rollout_vs_oracle(cfg, steps=400, seed=3, crowd=1.2)
+    assert int(orc.state.stats[2]) + int(orc.state.coll.sum()) > 100, "scenario should produce hard collisions"
+
+
+def test_multi_rollout_evaluate_mode():
+    cfg = O.multi_config(1024, 5, reset_mode=O.RESET_ON_ALL_DONE, max_episode_steps=200, seed=5)
+    rollout_vs_oracle(cfg, steps=250, seed=4, evaluate=True)
+
+
+def test_multi_c3_1000_step_rollout_subset():
+    """BASELINE config 3 (N=8, B=65,536) for 1,000 steps on the GPU; the oracle follows a contiguous 1,024-env
+    window (envs are independent and the Philox streams are keyed by the global env index)."""
+    G = _b200()
+    B, N, W, START = 65536, 8, 1024, 30000
+    kw = dict(reset_mode=O.RESET_ON_DONE0, max_episode_steps=1500, seed=0x5EED)
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=N, **kw)
+    cfg = O.multi_config(W, N, env_index_base=START, **kw)
+    orc = O.Oracle(cfg, nthreads=8)
+    env.reset()
+    orc.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    sl = slice(START, START + W)
+    mism = 0
+    for t in range(1000):
+        a = (torch.rand((B, N, 2), generator=gen, device="cuda") * 20 - 10)
+        obs, rew, done, info = env.step(a)
+        out = orc.step(a[sl].cpu().numpy())
+        assert np.array_equal(done[sl].cpu().numpy(), out["done"]), f"done flags differ at step {t}"
+        assert np.array_equal(info["reset_mask"][sl].cpu().numpy(), out["reset_mask"]), f"reset mask differs at step {t}"
+        if t % 10 == 0 or t == 999:
+            assert np.array_equal(env.state.pos[sl].cpu().numpy(), orc.state.pos), f"positions differ at step {t}"
+            assert np.array_equal(env.state.vel[sl].cpu().numpy(), orc.state.vel), f"velocities differ at step {t}"
+            mism += int((~close(rew[sl].cpu().numpy(), out["reward"])).sum())
+            mism += int((~obs_close(obs[sl].cpu().numpy(), out["obs"], RTOL, ATOL)).sum())
+    assert mism == 0
+    assert int(orc.state.stats[0]) > 100, "the window should have gone through many episodes"
+
+
+def test_multi_c3_full_batch_short():
+    """All 65,536 envs of config 3 against the oracle for 30 steps."""
+    cfg = O.multi_config(65536, 8, reset_mode=O.RESET_ON_DONE0, max_episode_steps=20, seed=9)
+    rollout_vs_oracle(cfg, steps=30, seed=11, check_every=5)
+
+
+def test_multi_n32_rollout():
+    cfg = O.multi_config(4096, 32, reset_mode=O.RESET_ON_DONE0, max_episode_steps=100, seed=32)
+    rollout_vs_oracle(cfg, steps=150, seed=6, check_every=3)
+
+
+@pytest.mark.parametrize("f32", [0, 1])
+def test_single_rollout(f32):
+    cfg = O.single_config(65536, reset_mode=O.RESET_ON_ANY_DONE, max_episode_steps=500, seed=21 + f32,
+                          single_f32_first_step=f32)
+    ev, _ = rollout_vs_oracle(cfg, steps=300, seed=8 + f32, check_every=10)
+    assert ev["resets"] > 100
+
+
+def test_single_1000_step_rollout():
+    """BASELINE config 2 (single UAV, B=65,536) for 1,000 steps; oracle follows a 4,096-env window."""
+    G = _b200()
+    B, W, START = 65536, 4096, 12345
+    kw = dict(reset_mode=O.RESET_ON_ANY_DONE, seed=77)
+    env = G.BatchedUAVWorld2D(B, **kw)
+    orc = O.Oracle(O.single_config(W, env_index_base=START, **kw), nthreads=8)
+    env.reset()
+    orc.reset()
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    sl = slice(START, START + W)
+    for t in range(1000):
+        a = torch.rand((B, 1, 2), generator=gen, device="cuda") * 24 - 12
+        obs, rew, done, info = env.step(a)
+        out = orc.step(a[sl].cpu().numpy())
+        assert np.array_equal(done[sl].cpu().numpy(), out["done"]), f"done flags differ at step {t}"
+        if t % 10 == 0 or t == 999:
+            assert np.array_equal(env.state.pos[sl].cpu().numpy(), orc.state.pos)
+            assert np.array_equal(env.state.vel[sl].cpu().numpy(), orc.state.vel)
+            assert close(rew[sl].cpu().numpy(), out["reward"]).all()
+            assert obs_close(obs[sl].cpu().numpy(), out["obs"], RTOL, ATOL).all()
+            assert np.array_equal(info["distance"][sl].cpu().numpy(), out["distance"])
+
+
+# ---- reset ------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("n", [1, 6, 8, 32])
+def test_reset_constraints_and_philox_parity(n):
+    """Device reset == oracle reset (same Philox stream) bit-for-bit, and the reference's separation constraints
+    (multi_uav_world_2d.py:126-153) hold."""
+    B = 1000
+    cfg = O.multi_config(B, n, seed=4242, x_size=20.0, y_size=20.0)
+    env = make_env(cfg)
+    orc = O.Oracle(cfg)
+    obs = env.reset().cpu().numpy()
+    obs_o = orc.reset()
+    assert_state_equal(env, orc.state, "after reset")
+    assert obs_close(obs, obs_o, RTOL, ATOL).all()
+    pos, tgt = env.state.pos.cpu().numpy(), env.state.tgt.cpu().numpy()
+    assert (np.abs(pos) <= 10).all() and (np.abs(tgt) <= 10).all()
+    d_own = np.linalg.norm(tgt - pos, axis=-1)
+    assert (d_own > 2.0).all()
+    if n > 1:
+        iu = np.triu_indices(n, 1)
+        dp = np.linalg.norm(pos[:, :, None] - pos[:, None, :], axis=-1)[:, iu[0], iu[1]]
+        dt = np.linalg.norm(tgt[:, :, None] - tgt[:, None, :], axis=-1)[:, iu[0], iu[1]]
+        assert (dp > 2.0).all() and (dt > 2.0).all()
+    # masked reset: only the chosen envs change, and their episode counter advances
+    before = env.state.to_host()
+    mask = np.zeros(B, np.uint8)
+    mask[::3] = 1
+    env.reset(torch.from_numpy(mask))
+    orc.reset(mask)
+    assert_state_equal(env, orc.state, "after masked reset")
+    after = env.state.to_host()
+    assert np.array_equal(after["pos"][mask == 0], before["pos"][mask == 0])
+    assert (after["episode"][mask == 1] == 2).all() and (after["episode"][mask == 0] == 1).all()
+
+
+def test_reset_is_uniform_over_the_box():
+    G = _b200()
+    env = G.BatchedMultiUAVWorld2D(200000, num_agents=1, seed=3)
+    env.reset()
+    pos = env.state.pos.cpu().numpy().reshape(-1, 2)
+    assert abs(pos.mean()) < 0.1 and abs(pos.std() - 50 / np.sqrt(12)) < 0.1
+    hist, _ = np.histogram(pos[:, 0], bins=10, range=(-25, 25))
+    assert (np.abs(hist / len(pos) - 0.1) < 0.005).all()
+
+
+def test_circular_reset():
+    cfg = O.multi_config(64, 6, circular=1, seed=1)
+    env = make_env(cfg)
+    orc = O.Oracle(cfg)
+    obs = env.reset().cpu().numpy()
+    obs_o = orc.reset()
+    assert_state_equal(env, orc.state, "after circular reset")
+    assert obs_close(obs, obs_o, RTOL, ATOL).all()
+    assert np.allclose(np.linalg.norm(env.state.pos.cpu().numpy(), axis=-1), 20.0, atol=1e-5)
+
+
+# ---- sharding, action modes, host path, graphs -----------------------------------------------------------------
+
+
+def test_shard_invariance():
+    """Env b behaves identically whichever shard it lands in (Philox keyed by the global env index)."""
+    G = _b200()
+    B, N, steps = 512, 8, 60
+    kw = dict(num_agents=N, seed=31, reset_mode=O.RESET_ON_DONE0, max_episode_steps=25)
+    full = G.BatchedMultiUAVWorld2D(B, **kw)
+    shards = [G.BatchedMultiUAVWorld2D(B // 4, env_index_base=k * (B // 4), **kw) for k in range(4)]
+    full.reset()
+    for s in shards:
+        s.reset()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(steps):
+        a = torch.rand((B, N, 2), generator=gen, device="cuda") * 20 - 10
+        full.step(a)
+        for k, s in enumerate(shards):
+            s.step(a[k * (B // 4):(k + 1) * (B // 4)].contiguous())
+    for k, s in enumerate(shards):
+        sl = slice(k * (B // 4), (k + 1) * (B // 4))
+        assert torch.equal(s.state.pos, full.state.pos[sl]) and torch.equal(s.state.vel, full.state.vel[sl])
+        assert torch.equal(s.obs, full.obs[sl]) and torch.equal(s.done, full.done[sl])
+        assert torch.equal(s.state.episode, full.state.episode[sl])
+
+
+@pytest.mark.parametrize("mode", ["polar", "scaled"])
+def test_action_modes(mode):
+    """Fused mapping == map_action kernel followed by a cartesian step (bit-exact); mapping ~= the callers' NumPy
+    formula (test_sac_multi.py:77-80, test_pytorch_multi.py:80)."""
+    G = _b200()
+    B, N = 300, 5
+    e1 = G.BatchedMultiUAVWorld2D(B, num_agents=N, seed=2)
+    e2 = G.BatchedMultiUAVWorld2D(B, num_agents=N, seed=2)
+    e1.reset()
+    e2.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(20):
+        a = torch.rand((B, N, 2), generator=gen, device="cuda") * 2 - 1
+        mapped = e2.map_action(a, mode)
+        e1.step(a, action_mode=mode)
+        e2.step(mapped)
+        assert torch.equal(e1.state.pos, e2.state.pos) and torch.equal(e1.obs, e2.obs)
+        an = a.cpu().numpy()
+        if mode == "polar":
+            v = (an[..., 0] / 2 + 0.5) * np.float32(np.linalg.norm(e1.action_space.high))
+            th = an[..., 1] * np.float32(np.pi)
+            ref = np.stack([v * np.cos(th.astype(np.float64)), v * np.sin(th.astype(np.float64))], -1)
+        else:
+            ref = an * e1.action_space.high
+        orc = O.Oracle(O.multi_config(B, N))
+        assert np.allclose(mapped.cpu().numpy(), ref, rtol=1e-5, atol=2e-6)
+        assert np.allclose(orc.map_action(an, O.ACTION_POLAR if mode == "polar" else O.ACTION_SCALED), ref, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("kind", ["multi", "single"])
+def test_step_host_matches_device_step(kind):
+    G = _b200()
+    B = 5000
+    if kind == "multi":
+        mk = lambda: G.BatchedMultiUAVWorld2D(B, num_agents=7, seed=8, reset_mode=O.RESET_ON_DONE0, max_episode_steps=30)  # noqa: E731
+        N, D = 7, 10
+    else:
+        mk = lambda: G.BatchedUAVWorld2D(B, seed=8, reset_mode=O.RESET_ON_ANY_DONE, max_episode_steps=30)  # noqa: E731
+        N, D = 1, 4
+    e1, e2 = mk(), mk()
+    e1.reset()
+    e2.reset()
+    act = torch.empty((B, N, 2), dtype=torch.float32).pin_memory()
+    obs = torch.empty((B, N, D), dtype=torch.float32).pin_memory()
+    rew = torch.empty((B, N), dtype=torch.float32).pin_memory()
+    done = torch.empty((B, N), dtype=torch.uint8).pin_memory()
+    g = torch.Generator().manual_seed(0)
+    for _ in range(50):
+        act.copy_(torch.rand((B, N, 2), generator=g) * 20 - 10)
+        e1.step(act.cuda())
+        torch.cuda.synchronize()
+        e2.step_host(act, obs, rew, done)
+        assert torch.equal(obs, e1.obs.cpu()) and torch.equal(rew, e1.reward.cpu()) and torch.equal(done, e1.done.cpu())
+    assert torch.equal(e1.state.blob, e2.state.blob)
+
+
+def test_step_in_cuda_graph():
+    """The custom op captures into a CUDA graph (how bench.py and rollouts replay it)."""
+    G = _b200()
+    B, N = 4096, 8
+    kw = dict(num_agents=N, seed=4, reset_mode=O.RESET_ON_DONE0, max_episode_steps=50)
+    eager, graphed = G.BatchedMultiUAVWorld2D(B, **kw), G.BatchedMultiUAVWorld2D(B, **kw)
+    eager.reset()
+    graphed.reset()
+    a = torch.zeros((B, N, 2), device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        graphed.step(a)  # warm-up outside capture
+    torch.cuda.synchronize()
+    graphed.state.blob.copy_(eager.state.blob)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        graphed.step(a)
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    for _ in range(80):
+        a.copy_(torch.rand((B, N, 2), generator=gen, device="cuda") * 20 - 10)
+        g.replay()
+        eager.step(a)
+    torch.cuda.synchronize()
+    assert torch.equal(eager.state.blob, graphed.state.blob) and torch.equal(eager.obs, graphed.obs)
+
+
+def test_errors_are_loud():
+    G = _b200()
+    with pytest.raises(G.UavcaError):
+        G.BatchedMultiUAVWorld2D(16, num_agents=33)
+    env = G.BatchedMultiUAVWorld2D(16, num_agents=4)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((16, 3, 2), device="cuda"))
+    env2 = G.BatchedMultiUAVWorld2D(16, num_agents=4, reset_mode=1, reset_source=G.SOURCE_POOL)
+    with pytest.raises(G.UavcaError):
+        env2.step(torch.zeros((16, 4, 2), device="cuda"))
