@@ -99,10 +99,33 @@ Consts derive_consts(const uavca_config& g) {
     for (int k = 0; k < 64 && std::sqrt(s) < g.reach_speed; ++k) s = std::nextafter(s, INFINITY);
     c.reach_speed_sq = s;
   }
+  // float32 thresholds moved to squared-distance space (sqrtf is correctly rounded and monotone)
+  auto le_sq = [](float thr) {  // greatest s with sqrtf(s) <= thr
+    float s = thr * thr;
+    for (int k = 0; k < 64 && std::sqrt(s) > thr; ++k) s = std::nextafter(s, 0.0f);
+    for (int k = 0; k < 64 && std::sqrt(std::nextafter(s, INFINITY)) <= thr; ++k) s = std::nextafter(s, INFINITY);
+    return s;
+  };
+  auto lt_sq = [](float thr) {  // least s with sqrtf(s) >= thr  (d < thr  <=>  s < this)
+    float s = thr * thr;
+    for (int k = 0; k < 64 && std::sqrt(s) < thr; ++k) s = std::nextafter(s, INFINITY);
+    for (int k = 0; k < 64 && s > 0 && std::sqrt(std::nextafter(s, 0.0f)) >= thr; ++k) s = std::nextafter(s, 0.0f);
+    return s;
+  };
+  auto ceil_f = [](double v) { float f = (float)v; return ((double)f < v) ? std::nextafter(f, INFINITY) : f; };
+  auto floor_f = [](double v) { float f = (float)v; return ((double)f > v) ? std::nextafter(f, -INFINITY) : f; };
   c.two_r = (float)(2.0 * g.collider_radius);
   c.two_h = (float)(2.0 * g.hard_collision_radius);
   c.dsense = (float)g.d_sense;
   c.reach_dist = (float)g.reach_distance;
+  c.s_two_r_le = le_sq(c.two_r);
+  c.s_two_h_le = le_sq(c.two_h);
+  c.s_dsense_lt = lt_sq(c.dsense);
+  c.lox_f = ceil_f(c.lox); c.hix_f = floor_f(c.hix);
+  c.loy_f = ceil_f(c.loy); c.hiy_f = floor_f(c.hiy);
+  c.vm2_floor_f = floor_f(c.vm2);
+  c.vm2_f = (float)c.vm2;
+  c.inv_dsense = (float)(1.0 / g.d_sense);
   const double diag = n64(g.x_size, g.y_size);
   c.inv_diag = (float)(1.0 / diag);
   c.inv_vm2_f = (float)(1.0 / c.vm2);

@@ -16,6 +16,7 @@ namespace uavca {
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kMinBlocksPerSM = 4;  // step kernel: <= 64 registers per thread -> 32 resident warps per SM
 constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned kMaxResetAttempts = 4096u;  // the reference would loop forever in an over-crowded box
 
@@ -31,6 +32,13 @@ struct Consts {
   double reach_speed_sq;      // least s with sqrt(s) >= reach_speed: ||v|| < reach_speed  <=>  s < this
   // float32 thresholds (python scalars are weak against float32 norms under NumPy 2)
   float two_r, two_h, dsense, reach_dist;
+  // the same thresholds in squared-distance space (sqrt is monotone, so the flags stay bit-exact without a sqrt):
+  //   d <= 2r  <=>  s <= s_two_r_le ;  d <= 2h  <=>  s <= s_two_h_le ;  d < d_sense  <=>  s < s_dsense_lt
+  float s_two_r_le, s_two_h_le, s_dsense_lt;
+  // box as float32 bounds with identical compare results: float64(p) >= lo  <=>  p >= lox_f, ...
+  float lox_f, hix_f, loy_f, hiy_f;
+  float vm2_floor_f;  // greatest float32 <= vm2: float64(init) <= vm2  <=>  init <= vm2_floor_f
+  float vm2_f, inv_dsense;
   float inv_diag, inv_vm2_f, inv_vmax_f, inv_pi;
   float polar_scale, vmax_f, tau_f;
   // episode control
@@ -125,7 +133,44 @@ __device__ __forceinline__ void integrate(double ax, double ay, double& vx, doub
   py = __double2float_rn(__dadd_rn((double)py, __dmul_rn(vy, c.tau)));
 }
 
-// wrap(atan2(dy,dx) - atan2(hy,hx)) as ONE atan2f of the float64 cross/dot products of the two directions
+// atan2 for finite inputs, branch-free: octant reduction, one approximate division and a degree-8 minimax
+// polynomial in t^2 (fit in this repo; max relative error 1.2e-7 evaluated in float32, ~4e-7 with the division).
+// Relative accuracy holds down to tiny angles (P(0) = 1 exactly).  atan2(0, 0) = 0 as in libm.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  float t = __fdividef(mn, mx);
+  t = (mx == 0.0f) ? 0.0f : t;
+  const float s = t * t;
+  float p = 0.0029206890612840652f;
+  p = fmaf(p, s, -0.016367916017770767f);
+  p = fmaf(p, s, 0.04321184381842613f);
+  p = fmaf(p, s, -0.07552213221788406f);
+  p = fmaf(p, s, 0.10666003823280334f);
+  p = fmaf(p, s, -0.14211055636405945f);
+  p = fmaf(p, s, 0.19993773102760315f);
+  p = fmaf(p, s, -0.33333152532577515f);
+  p = fmaf(p, s, 1.0f);
+  float r = t * p;
+  r = (ay > ax) ? (1.57079637050628662f - r) : r;
+  r = (x < 0.0f) ? (3.14159274101257324f - r) : r;
+  return copysignf(r, y);
+}
+
+// difference of two angles given in units of pi, wrapped to [-1, 1]
+__device__ __forceinline__ float wrap_units(float d) {
+  d = (d > 1.0f) ? d - 2.0f : d;
+  d = (d < -1.0f) ? d + 2.0f : d;
+  return d;
+}
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// wrap(atan2(dy,dx) - atan2(hy,hx)) as ONE atan2 of the float64 cross/dot products of the two directions
 // (relative error ~2 ulp float32 even for tiny angles; atan2(0,0)=0 makes a zero heading point along +x).
 __device__ __forceinline__ float rel_angle(double dx, double dy, double hx, double hy) {
   const bool hzero = (hx == 0.0) & (hy == 0.0);
@@ -134,7 +179,7 @@ __device__ __forceinline__ float rel_angle(double dx, double dy, double hx, doub
   dx = dzero ? 1.0 : dx;
   double cr = fma(hx, dy, -(hy * dx));
   double dt = fma(hx, dx, hy * dy);
-  return atan2f((float)cr, (float)dt);
+  return fast_atan2((float)cr, (float)dt);
 }
 
 // Caller-side action mapping (test_sac_multi.py:77-80; test_pytorch_multi.py:80).

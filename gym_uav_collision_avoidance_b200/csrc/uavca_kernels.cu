@@ -18,12 +18,11 @@ namespace uavca {
 // ================================================================================================================
 
 template <int NT>
-__global__ void __launch_bounds__(kThreads) step_multi_kernel(const __grid_constant__ KernelArgs a) {
-  __shared__ __align__(16) float stage_all[kWarpsPerBlock][32 * 10];
-  float* stage = stage_all[threadIdx.x >> 5];
+__global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_kernel(const __grid_constant__ KernelArgs a) {
+  __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
+  const WarpScratch ws = warp_scratch(smem);
   const Consts& c = a.c;
   const Lane L = make_lane<NT>(a.B, a.N);
-  const int N = NT > 0 ? NT : L.N;
 
   Uav u = load_uav(a.s, L);
   float2 act = make_float2(0.f, 0.f);
@@ -40,70 +39,51 @@ __global__ void __launch_bounds__(kThreads) step_multi_kernel(const __grid_const
     integrate((double)act.x, (double)act.y, vx, vy, px, py, c);
     if (!parked) { u.vx = vx; u.vy = vy; u.px = px; u.py = py; }
   }
-  const float tdx = __fsub_rn(u.tx, u.px), tdy = __fsub_rn(u.ty, u.py);
-  const float dist = parked ? 0.f : n32(tdx, tdy);
+  const Own w = own_features(c, u);  // heading, heading error to the target, distance, |v|^2 (multi_uav_world_2d.py:184-186)
+  ws.pp[L.lane] = make_float4(u.px, u.py, ox, oy);
+  ws.th[L.lane] = w.th_u;
+  __syncwarp();
+
+  const float dist = parked ? 0.f : w.dist;
   const float prev_d = parked ? 0.f : u.prev;
-  const float dth = rel_angle((double)tdx, (double)tdy, u.vx, u.vy);  // multi_uav_world_2d.py:184-186
 
-  // ---- reward shaping (:188-195), float64 accumulate
-  double r;
+  // ---- reward shaping (:188-195).  Output only: float32 arithmetic, well inside the 1e-5 tolerance.
+  float r;
   {
-    const double initd = (double)u.init;
-    double rc = (double)__frcp_rn(u.init);
-    rc = fma(fma(-initd, rc, 1.0), rc, rc);            // 1/init to ~1e-14
-    double m = (initd <= c.vm2) ? 1.0 : c.vm2 * rc;    // min(vm2/init, 1)
-    r = -0.01 * m;
-    r += 50.0 * ((double)__fsub_rn(prev_d, dist) * c.inv_vm2);
-    const float q = __fdiv_rn(dist, __fmul_rn(1.5f, u.init));
-    const float f = (r > 0.0) ? __fsub_rn(1.0f, q) : __fadd_rn(1.0f, q);
-    r *= (double)f;
-    r -= 0.01 * (double)fabsf(dth);
+    const float m = (u.init <= c.vm2_floor_f) ? 1.0f : __fdividef(c.vm2_f, u.init);  // min(vm2/init, 1)
+    r = fmaf(50.0f * c.inv_vm2_f, __fsub_rn(prev_d, dist), -0.01f * m);
+    const float q = __fdividef(dist, 1.5f * u.init);
+    r *= (r > 0.0f) ? (1.0f - q) : (1.0f + q);
+    r = fmaf(-0.01f * 3.14159274101257324f, fabsf(w.dth_u), r);
   }
 
-  // ---- one sweep over the env's UAVs serves both pairwise passes:
-  //   pass A (:198-210): nearest neighbour with j<i at the NEW position and j>i at the OLD one (the reference moves
-  //                      and tests UAVs one after the other);
-  //   pass B (:75):      the two nearest neighbours with every UAV at its NEW position (observation).
-  const float inf = __int_as_float(0x7f800000);
-  float smin = inf;
-  Top2 t{inf, inf, -1, -1};
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const int src = L.base + j;
-    const float njx = __shfl_sync(kFull, u.px, src), njy = __shfl_sync(kFull, u.py, src);
-    const float ojx = __shfl_sync(kFull, ox, src), ojy = __shfl_sync(kFull, oy, src);
-    const float sn = sq32(__fsub_rn(njx, u.px), __fsub_rn(njy, u.py));
-    const float so = sq32(__fsub_rn(ojx, u.px), __fsub_rn(ojy, u.py));
-    const float sa = (j < L.i) ? sn : so;
-    if (j != L.i) {
-      if (sa < smin) smin = sa;
-      top2_insert(t, sn, j);
-    }
-  }
+  // ---- both pairwise passes in one sweep over the env's UAVs
+  float smin;
+  Top2 t;
+  pair_scan<NT>(ws, L, u.px, u.py, smin, t);
 
-  // ---- collisions (:199-210)
-  const float dmin = __fsqrt_rn(smin);
-  const bool in_range = dmin < c.dsense;
-  const bool collision = in_range & (dmin <= c.two_r);
-  if (collision) r = -2.0;
-  const bool hard = in_range & (dmin <= c.two_h) & !parked & ((u.flags & UAVCA_FLAG_COLLIDED) == 0u);
+  // ---- collisions (:199-210), decided in squared-distance space
+  const bool in_range = smin < c.s_dsense_lt;
+  const bool collision = in_range & (smin <= c.s_two_r_le);
+  r = collision ? -2.0f : r;
+  const bool hard = in_range & (smin <= c.s_two_h_le) & !parked & ((u.flags & UAVCA_FLAG_COLLIDED) == 0u);
   if (hard) u.flags |= UAVCA_FLAG_COLLIDED;
 
   // ---- done logic (:213-227)
-  const double vsq = sq64(u.vx, u.vy);
-  const bool slow = vsq < c.reach_speed_sq;
-  const bool inside = ((double)u.px >= c.lox) & ((double)u.px <= c.hix) & ((double)u.py >= c.loy) & ((double)u.py <= c.hiy);
+  const bool slow = w.vsq < c.reach_speed_sq;
+  const bool inside = (u.px >= c.lox_f) & (u.px <= c.hix_f) & (u.py >= c.loy_f) & (u.py <= c.hiy_f);
   const bool reached = (dist < c.reach_dist) & !collision & slow;
   const bool newly_reached = reached & !parked;
   bool done = reached | (!inside & (a.io.evaluate == 0));
   if (reached) {  // UAVAgent.finish (uav_agent.py:38-42)
     u.flags |= UAVCA_FLAG_PARKED;
-    const double nv = sqrt(vsq);
+    const double nv = sqrt(w.vsq);
     double fx = __dmul_rn(__ddiv_rn(u.vx, nv), 0.001), fy = __dmul_rn(__ddiv_rn(u.vy, nv), 0.001);
     if ((fx != fx) | (fy != fy)) { fx = 0.0; fy = 0.0; }
     u.vx = fx; u.vy = fy;
-    r += 10.0;
+    r += 10.0f;
   }
+  const double vsq_obs = reached ? sq64(u.vx, u.vy) : w.vsq;
   u.prev = dist;  // :229
   if (!L.valid) done = false;
 
@@ -123,18 +103,18 @@ __global__ void __launch_bounds__(kThreads) step_multi_kernel(const __grid_const
   rs &= L.valid;
 
   if (L.valid) {
-    st_stream(a.io.reward + L.m, (float)r);
+    st_stream(a.io.reward + L.m, r);
     st_stream(a.io.done + L.m, (uint8_t)done);
   }
   if (leader && a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
 
-  // ---- observation (:233-235)
+  // ---- observation (:233-235): every UAV at its new position
   float o[10];
-  obs_multi(c, L, u, t, o);
+  obs_multi(c, ws, L, u.px, u.py, w.th_u, w.dth_u, w.dist, vsq_obs, t, o);
 
   if (__any_sync(kFull, rs)) {
     // at least one env of this warp starts a new episode in place
-    if (a.io.final_obs) store_obs_rows(stage, a.io.final_obs, L, o);
+    if (a.io.final_obs) store_obs_rows(ws.stage, a.io.final_obs, L, o);
     unsigned episode = 0;
     if (leader) episode = a.s.episode[L.env];
     episode = __shfl_sync(kFull, episode, L.base);
@@ -156,15 +136,14 @@ __global__ void __launch_bounds__(kThreads) step_multi_kernel(const __grid_const
     }
     Uav nu = u;
     reset_multi(a, L, rs, episode, nu);
-    const Top2 nt = top2_scan<NT>(L, nu.px, nu.py);
     float no[10];
-    obs_multi(c, L, nu, nt, no);
+    observe_state<NT>(c, ws, L, nu, no);
     if (rs) {
       u = nu;
 #pragma unroll
       for (int k = 0; k < 10; ++k) o[k] = no[k];
     }
-    store_obs_rows(stage, a.io.obs, L, o);
+    store_obs_rows(ws.stage, a.io.obs, L, o);
     store_uav(a.s, L, u, rs);
   } else {
     if (leader) {
@@ -172,16 +151,16 @@ __global__ void __launch_bounds__(kThreads) step_multi_kernel(const __grid_const
       if (reach_inc) a.s.reach[L.env] += reach_inc;  // :221
       if (coll_inc) a.s.coll[L.env] += coll_inc;     // :209
     }
-    store_obs_rows(stage, a.io.obs, L, o);
-    if (a.io.final_obs) store_obs_rows(stage, a.io.final_obs, L, o);
+    store_obs_rows(ws.stage, a.io.obs, L, o);
+    if (a.io.final_obs) store_obs_rows(ws.stage, a.io.final_obs, L, o);
     store_uav(a.s, L, u, false);
   }
 }
 
 template <int NT>
 __global__ void __launch_bounds__(kThreads) reset_multi_kernel(const __grid_constant__ KernelArgs a, const uint8_t* mask) {
-  __shared__ __align__(16) float stage_all[kWarpsPerBlock][32 * 10];
-  float* stage = stage_all[threadIdx.x >> 5];
+  __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
+  const WarpScratch ws = warp_scratch(smem);
   const Lane L = make_lane<NT>(a.B, a.N);
   Uav u = load_uav(a.s, L);
   const bool rs = L.valid && (mask == nullptr || mask[L.env] != 0);
@@ -200,12 +179,11 @@ __global__ void __launch_bounds__(kThreads) reset_multi_kernel(const __grid_cons
     a.s.episode[L.env] = episode + 1u;
   }
   reset_multi(a, L, rs, episode, u);
-  const Top2 t = top2_scan<NT>(L, u.px, u.py);
   float o[10];
-  obs_multi(a.c, L, u, t, o);
+  observe_state<NT>(a.c, ws, L, u, o);
   if (a.io.obs) {
     if (mask == nullptr) {
-      store_obs_rows(stage, a.io.obs, L, o);
+      store_obs_rows(ws.stage, a.io.obs, L, o);
     } else if (rs) {  // rows of other envs stay untouched
 #pragma unroll
       for (int k = 0; k < 10; ++k) a.io.obs[L.m * 10 + k] = o[k];
@@ -216,14 +194,13 @@ __global__ void __launch_bounds__(kThreads) reset_multi_kernel(const __grid_cons
 
 template <int NT>
 __global__ void __launch_bounds__(kThreads) observe_multi_kernel(const __grid_constant__ KernelArgs a) {
-  __shared__ __align__(16) float stage_all[kWarpsPerBlock][32 * 10];
-  float* stage = stage_all[threadIdx.x >> 5];
+  __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
+  const WarpScratch ws = warp_scratch(smem);
   const Lane L = make_lane<NT>(a.B, a.N);
   const Uav u = load_uav(a.s, L);
-  const Top2 t = top2_scan<NT>(L, u.px, u.py);
   float o[10];
-  obs_multi(a.c, L, u, t, o);
-  store_obs_rows(stage, a.io.obs, L, o);
+  observe_state<NT>(a.c, ws, L, u, o);
+  store_obs_rows(ws.stage, a.io.obs, L, o);
 }
 
 // ================================================================================================================
@@ -238,9 +215,9 @@ struct SingleEnv {
 
 __device__ __forceinline__ void obs_single(const Consts& c, const SingleEnv& e, bool vel_is_f32, float o[4]) {
   // UAVWorld2D._get_obs (uav_world_2d.py:88-97)
-  const float speed = vel_is_f32 ? n32((float)e.vx, (float)e.vy) : sqrtf((float)sq64(e.vx, e.vy));
+  const float speed = vel_is_f32 ? n32((float)e.vx, (float)e.vy) : sqrt_approx((float)sq64(e.vx, e.vy));
   o[0] = speed * c.inv_vmax_f;
-  o[1] = atan2f((float)e.vy, (float)e.vx) * c.inv_pi;
+  o[1] = fast_atan2((float)e.vy, (float)e.vx) * c.inv_pi;
   const float tdx = __fsub_rn(e.tx, e.px), tdy = __fsub_rn(e.ty, e.py);
   o[2] = n32(tdx, tdy) * c.inv_diag;
   o[3] = rel_angle((double)tdx, (double)tdy, e.vx, e.vy) * c.inv_pi;
@@ -324,7 +301,7 @@ __global__ void __launch_bounds__(kThreads) step_single_kernel(const __grid_cons
   float r = __fsub_rn(0.0f, __fdiv_rn(1.0f, e.init));
   r = __fadd_rn(r, __fmul_rn(10.0f, __fsub_rn(e.prev, dist)));
   r = __fsub_rn(r, (float)(0.1 * (double)fabsf(dth)));
-  const bool inside = ((double)e.px >= c.lox) & ((double)e.px <= c.hix) & ((double)e.py >= c.loy) & ((double)e.py <= c.hiy);
+  const bool inside = (e.px >= c.lox_f) & (e.px <= c.hix_f) & (e.py >= c.loy_f) & (e.py <= c.hiy_f);
   const bool reached = dist < c.reach_dist;                                       // :159
   if (reached) r = __fadd_rn(r, 1000.0f);                                         // :161
   const bool done = reached | !inside;                                            // :159-166

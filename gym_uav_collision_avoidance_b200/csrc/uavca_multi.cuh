@@ -4,7 +4,7 @@
 // Thread mapping: one lane per UAV, the N lanes of an env are adjacent in one warp, floor(32/N) envs per warp.
 // The flat UAV index of lane l in (global) warp w is  w * lanes_used + l, so every per-UAV array is read and
 // written as one contiguous, coalesced run per warp.  Neighbour data never touches memory: lanes exchange
-// positions and velocities with __shfl_sync.
+// positions and headings through a per-warp shared-memory scratch (broadcast loads).
 #pragma once
 
 #include "uavca_device.cuh"
@@ -81,60 +81,120 @@ __device__ __forceinline__ void store_uav(const StateView& s, const Lane& L, con
   }
 }
 
+// Per-warp shared-memory scratch.  Neighbour data never goes to global memory: every lane publishes its position
+// (new and old) and heading once, and the pair loops read them back with 16-byte broadcast loads.
+struct WarpScratch {
+  float4* pp;    // [32] (new.x, new.y, old.x, old.y) per lane
+  float* th;     // [32] heading / pi per lane
+  float* stage;  // [320] observation rows of the warp
+};
+constexpr int kScratchFloats = 32 * 4 + 32 + 32 * 10;
+
+__device__ __forceinline__ WarpScratch warp_scratch(float* block_smem) {
+  float* w = block_smem + (threadIdx.x >> 5) * kScratchFloats;
+  return WarpScratch{reinterpret_cast<float4*>(w), w + 128, w + 160};
+}
+
 // Two nearest other UAVs of the env, ordered by (squared float32 distance, index).
 struct Top2 {
   float s1, s2;
   int j1, j2;
 };
 
+// branch-free insertion; visiting j in ascending order keeps the lower index first among equal distances
 __device__ __forceinline__ void top2_insert(Top2& t, float s, int j) {
-  if (s < t.s1) { t.s2 = t.s1; t.j2 = t.j1; t.s1 = s; t.j1 = j; }
-  else if (s < t.s2) { t.s2 = s; t.j2 = j; }
+  const bool p1 = s < t.s1, p2 = s < t.s2;
+  t.j2 = p1 ? t.j1 : (p2 ? j : t.j2);
+  t.s2 = p1 ? t.s1 : (p2 ? s : t.s2);
+  t.j1 = p1 ? j : t.j1;
+  t.s1 = p1 ? s : t.s1;
 }
 
+// One sweep over the env's UAVs serving both pairwise passes of MultiUAVWorld2D.step:
+//   pass A (multi_uav_world_2d.py:198-210): nearest neighbour with j<i at the NEW position and j>i at the OLD one
+//                                           (the reference moves and tests the UAVs one after the other);
+//   pass B (:75 via _get_obs):              the two nearest neighbours with every UAV at its NEW position.
+// For reset/observe the old and new positions coincide and smin is simply unused.
 template <int NT>
-__device__ __forceinline__ Top2 top2_scan(const Lane& L, float px, float py) {
-  Top2 t{__int_as_float(0x7f800000), __int_as_float(0x7f800000), -1, -1};
+__device__ __forceinline__ void pair_scan(const WarpScratch& ws, const Lane& L, float px, float py, float& smin, Top2& t) {
+  const float inf = __int_as_float(0x7f800000);
+  smin = inf;
+  t = Top2{inf, inf, -1, -1};
   const int N = NT > 0 ? NT : L.N;
+  const float4* row = ws.pp + L.base;
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    float qx = __shfl_sync(kFull, px, L.base + j), qy = __shfl_sync(kFull, py, L.base + j);
-    float s = sq32(__fsub_rn(qx, px), __fsub_rn(qy, py));
-    if (j != L.i) top2_insert(t, s, j);
+    const float4 q = row[j];
+    float sn = sq32(__fsub_rn(q.x, px), __fsub_rn(q.y, py));
+    const float so = sq32(__fsub_rn(q.z, px), __fsub_rn(q.w, py));
+    float sa = (j < L.i) ? sn : so;
+    sa = (j == L.i) ? inf : sa;
+    sn = (j == L.i) ? inf : sn;
+    smin = fminf(smin, sa);
+    top2_insert(t, sn, j);
   }
-  return t;
 }
 
-// MultiUAVWorld2D._get_obs (multi_uav_world_2d.py:60-109) for this lane's UAV.  All lanes of the warp must call.
-__device__ __forceinline__ void obs_multi(const Consts& c, const Lane& L, const Uav& u, const Top2& t, float o[10]) {
-  o[0] = sqrtf((float)sq64(u.vx, u.vy)) * c.inv_vm2_f;                 // :62
-  o[1] = atan2f((float)u.vy, (float)u.vx) * c.inv_pi;                  // :63-64
+// MultiUAVWorld2D._get_obs (multi_uav_world_2d.py:60-109) for this lane's UAV.
+//   th_u    own heading atan2(v.y, v.x) / pi                                   (:63-64)
+//   dth_u   wrap(bearing to target - heading) / pi                             (:69-72)
+//   dist    float32 distance to the target                                      (:67)
+//   vsq     |v|^2 in float64
+// Neighbour bearings/headings are differences of float32 angles (absolute error ~2e-7 of a half-turn).
+__device__ __forceinline__ void obs_multi(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
+                                          float th_u, float dth_u, float dist, double vsq, const Top2& t, float o[10]) {
+  o[0] = sqrt_approx((float)vsq) * c.inv_vm2_f;  // :62
+  o[1] = th_u;
+  o[2] = dist * c.inv_diag;                      // :67-68
+  o[3] = dth_u;
+  const bool have1 = (t.j1 >= 0) & (t.s1 < c.s_dsense_lt);  // uav_agent.py:52 strict <
+  const bool have2 = have1 & (t.j2 >= 0) & (t.s2 < c.s_dsense_lt);
+  const int k1 = L.base + (t.j1 < 0 ? 0 : t.j1), k2 = L.base + (t.j2 < 0 ? 0 : t.j2);
+  const float4 q1 = ws.pp[k1], q2 = ws.pp[k2];
+  const float h1 = ws.th[k1], h2 = ws.th[k2];
+  const float b1 = fast_atan2(__fsub_rn(q1.y, py), __fsub_rn(q1.x, px)) * c.inv_pi;
+  const float b2 = fast_atan2(__fsub_rn(q2.y, py), __fsub_rn(q2.x, px)) * c.inv_pi;
+  o[4] = have1 ? sqrt_approx(t.s1) * c.inv_dsense : 1.0f;  // :77
+  o[5] = have1 ? wrap_units(b1 - th_u) : 1.0f;             // :78-81 (no neighbour: bearing pi)
+  o[6] = have1 ? wrap_units(h1 - th_u) : 0.0f;             // :82-85
+  o[7] = have2 ? sqrt_approx(t.s2) * c.inv_dsense : 1.0f;  // :87
+  o[8] = have2 ? wrap_units(b2 - th_u) : 1.0f;             // :88-91
+  o[9] = have2 ? wrap_units(h2 - th_u) : 0.0f;             // :92-95
+}
+
+// Everything the observation needs from a UAV's own state.
+struct Own {
+  float th_u, dth_u, dist;
+  double vsq;
+};
+__device__ __forceinline__ Own own_features(const Consts& c, const Uav& u) {
+  Own w;
   const float tdx = __fsub_rn(u.tx, u.px), tdy = __fsub_rn(u.ty, u.py);
-  o[2] = n32(tdx, tdy) * c.inv_diag;                                   // :67-68
-  o[3] = rel_angle((double)tdx, (double)tdy, u.vx, u.vy) * c.inv_pi;   // :69-72
-  const float d1 = __fsqrt_rn(t.s1), d2 = __fsqrt_rn(t.s2);
-  const bool have1 = (t.j1 >= 0) & (d1 < c.dsense);                    // uav_agent.py:52 strict <
-  const bool have2 = have1 & (t.j2 >= 0) & (d2 < c.dsense);
-  const int src1 = L.base + (t.j1 < 0 ? 0 : t.j1), src2 = L.base + (t.j2 < 0 ? 0 : t.j2);
-  const float n1x = __shfl_sync(kFull, u.px, src1), n1y = __shfl_sync(kFull, u.py, src1);
-  const float n2x = __shfl_sync(kFull, u.px, src2), n2y = __shfl_sync(kFull, u.py, src2);
-  const double n1vx = shfl_d(u.vx, src1), n1vy = shfl_d(u.vy, src1);
-  const double n2vx = shfl_d(u.vx, src2), n2vy = shfl_d(u.vy, src2);
-  const float b1 = rel_angle((double)__fsub_rn(n1x, u.px), (double)__fsub_rn(n1y, u.py), u.vx, u.vy) * c.inv_pi;
-  const float h1 = rel_angle(n1vx, n1vy, u.vx, u.vy) * c.inv_pi;
-  const float b2 = rel_angle((double)__fsub_rn(n2x, u.px), (double)__fsub_rn(n2y, u.py), u.vx, u.vy) * c.inv_pi;
-  const float h2 = rel_angle(n2vx, n2vy, u.vx, u.vy) * c.inv_pi;
-  o[4] = have1 ? __fdiv_rn(d1, c.dsense) : 1.0f;                       // :77
-  o[5] = have1 ? b1 : 1.0f;                                            // :78-81 (no neighbour: bearing pi)
-  o[6] = have1 ? h1 : 0.0f;                                            // :82-85
-  o[7] = have2 ? __fdiv_rn(d2, c.dsense) : 1.0f;                       // :87
-  o[8] = have2 ? b2 : 1.0f;                                            // :88-91
-  o[9] = have2 ? h2 : 0.0f;                                            // :92-95
+  w.dist = n32(tdx, tdy);
+  w.vsq = sq64(u.vx, u.vy);
+  w.th_u = fast_atan2((float)u.vy, (float)u.vx) * c.inv_pi;
+  w.dth_u = rel_angle((double)tdx, (double)tdy, u.vx, u.vy) * c.inv_pi;
+  return w;
+}
+
+// Observation of a state at rest (reset / observe kernels): publish, scan, build.  All lanes must call.
+template <int NT>
+__device__ __forceinline__ void observe_state(const Consts& c, const WarpScratch& ws, const Lane& L, const Uav& u, float o[10]) {
+  const Own w = own_features(c, u);
+  __syncwarp();
+  ws.pp[L.lane] = make_float4(u.px, u.py, u.px, u.py);
+  ws.th[L.lane] = w.th_u;
+  __syncwarp();
+  float smin;
+  Top2 t;
+  pair_scan<NT>(ws, L, u.px, u.py, smin, t);
+  obs_multi(c, ws, L, u.px, u.py, w.th_u, w.dth_u, w.dist, w.vsq, t, o);
 }
 
 // Write the warp's observation rows as one contiguous run of 16-byte stores (staged through shared memory;
 // a per-thread row is 40 bytes, which would otherwise scatter 8-byte stores 40 bytes apart).
 __device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const Lane& L, const float o[10]) {
+  __syncwarp();
   float2* st2 = reinterpret_cast<float2*>(stage) + L.lane * 5;
 #pragma unroll
   for (int k = 0; k < 5; ++k) st2[k] = make_float2(o[2 * k], o[2 * k + 1]);
@@ -142,17 +202,24 @@ __device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const 
   float* g = gobs + L.warp_m0 * 10;
   const int n2 = L.valid_lanes * 5;  // float2 elements to write
   if ((L.lanes_used & 1) == 0) {     // every warp's run starts on a 16-byte boundary
-    const int n4 = n2 >> 1;
+    const int n4 = n2 >> 1;          // <= 80
     const float4* s4 = reinterpret_cast<const float4*>(stage);
     float4* g4 = reinterpret_cast<float4*>(g);
-    for (int k = L.lane; k < n4; k += 32) st_stream(g4 + k, s4[k]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int k = L.lane + 32 * r;
+      if (k < n4) st_stream(g4 + k, s4[k]);
+    }
     if ((n2 & 1) && L.lane == 0) st_stream(reinterpret_cast<float2*>(g) + (n2 - 1), reinterpret_cast<const float2*>(stage)[n2 - 1]);
   } else {
     const float2* s2 = reinterpret_cast<const float2*>(stage);
     float2* g2 = reinterpret_cast<float2*>(g);
-    for (int k = L.lane; k < n2; k += 32) st_stream(g2 + k, s2[k]);
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int k = L.lane + 32 * r;
+      if (k < n2) st_stream(g2 + k, s2[k]);
+    }
   }
-  __syncwarp();
 }
 
 // Start a new episode for the envs of this warp whose lanes pass do_reset (env-uniform).  Restates
