@@ -87,11 +87,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("UAVCA_LIB", LIB_PATH)  # override: kernel-variant experiments only
+    if not os.path.exists(path):
         raise UavcaError(
-            f"{LIB_PATH} is missing: build the CUDA extension first (python -m gym_uav_collision_avoidance_b200.build "
+            f"{path} is missing: build the CUDA extension first (python -m gym_uav_collision_avoidance_b200.build "
             "or __graft_entry__.build()).  This package has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res

@@ -196,6 +196,7 @@ int validate_config(const uavca_config& g) {
   if (g.kind != UAVCA_KIND_MULTI && g.kind != UAVCA_KIND_SINGLE) return fail(-1, "config.kind must be UAVCA_KIND_MULTI or UAVCA_KIND_SINGLE");
   if (g.num_envs <= 0) return fail(-1, "config.num_envs must be positive");
   if (g.num_agents < 1 || g.num_agents > UAVCA_MAX_AGENTS) return fail(-1, "config.num_agents must be in 1..32");
+  if ((long long)g.num_envs * g.num_agents > 0x7fffffffLL) return fail(-1, "num_envs * num_agents must be below 2^31 per handle (shard across handles)");
   if (g.kind == UAVCA_KIND_SINGLE && g.num_agents != 1) return fail(-1, "the single-UAV world has num_agents == 1");
   if (!(g.tau > 0) || !(g.max_speed > 0) || !(g.max_acceleration > 0)) return fail(-1, "tau, max_speed and max_acceleration must be positive");
   if (!(g.x_size > 0) || !(g.y_size > 0)) return fail(-1, "x_size and y_size must be positive");

@@ -14,9 +14,15 @@
 
 namespace uavca {
 
-constexpr int kWarpsPerBlock = 8;
+#ifndef UAVCA_WPB
+#define UAVCA_WPB 4
+#endif
+#ifndef UAVCA_MINB
+#define UAVCA_MINB 8
+#endif
+constexpr int kWarpsPerBlock = UAVCA_WPB;
 constexpr int kThreads = kWarpsPerBlock * 32;
-constexpr int kMinBlocksPerSM = 4;  // step kernel: <= 64 registers per thread -> 32 resident warps per SM
+constexpr int kMinBlocksPerSM = UAVCA_MINB;  // step kernel: caps registers per thread (8 warps x 4 blocks -> 64 regs, 32 warps/SM)
 constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned kMaxResetAttempts = 4096u;  // the reference would loop forever in an over-crowded box
 
@@ -133,14 +139,13 @@ __device__ __forceinline__ void integrate(double ax, double ay, double& vx, doub
   py = __double2float_rn(__dadd_rn((double)py, __dmul_rn(vy, c.tau)));
 }
 
-// atan2 for finite inputs, branch-free: octant reduction, one approximate division and a degree-8 minimax
+// atan2 for finite inputs whose larger magnitude is 0 or >= ~1e-30, branch-free: octant reduction, one approximate division and a degree-8 minimax
 // polynomial in t^2 (fit in this repo; max relative error 1.2e-7 evaluated in float32, ~4e-7 with the division).
 // Relative accuracy holds down to tiny angles (P(0) = 1 exactly).  atan2(0, 0) = 0 as in libm.
 __device__ __forceinline__ float fast_atan2(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  float t = __fdividef(mn, mx);
-  t = (mx == 0.0f) ? 0.0f : t;
+  const float t = __fdividef(mn, mx + 1e-37f);  // the tiny bias makes atan2(0, 0) = 0 without a select
   const float s = t * t;
   float p = 0.0029206890612840652f;
   p = fmaf(p, s, -0.016367916017770767f);
@@ -157,11 +162,41 @@ __device__ __forceinline__ float fast_atan2(float y, float x) {
   return copysignf(r, y);
 }
 
+// Two atan2 at once: the polynomial runs on Blackwell's packed FP32 pipe (FMUL2/FFMA2, two lanes per instruction);
+// octant reduction and fix-up stay scalar.  Same arithmetic per element as fast_atan2.
+__constant__ float2 kAtanC[9] = {
+    {0.0029206890612840652f, 0.0029206890612840652f}, {-0.016367916017770767f, -0.016367916017770767f},
+    {0.04321184381842613f, 0.04321184381842613f},     {-0.07552213221788406f, -0.07552213221788406f},
+    {0.10666003823280334f, 0.10666003823280334f},     {-0.14211055636405945f, -0.14211055636405945f},
+    {0.19993773102760315f, 0.19993773102760315f},     {-0.33333152532577515f, -0.33333152532577515f},
+    {1.0f, 1.0f}};
+
+__device__ __forceinline__ float2 fast_atan2_pair(float y0, float x0, float y1, float x1) {
+  const float ax0 = fabsf(x0), ay0 = fabsf(y0), ax1 = fabsf(x1), ay1 = fabsf(y1);
+  const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+  const float2 t = make_float2(__fdividef(mn0, mx0 + 1e-37f), __fdividef(mn1, mx1 + 1e-37f));
+  const float2 s = __fmul2_rn(t, t);
+  float2 p = kAtanC[0];
+#pragma unroll
+  for (int k = 1; k < 9; ++k) p = __ffma2_rn(p, s, kAtanC[k]);
+  float2 r = __fmul2_rn(t, p);
+  r.x = (ay0 > ax0) ? (1.57079637050628662f - r.x) : r.x;
+  r.y = (ay1 > ax1) ? (1.57079637050628662f - r.y) : r.y;
+  r.x = (x0 < 0.0f) ? (3.14159274101257324f - r.x) : r.x;
+  r.y = (x1 < 0.0f) ? (3.14159274101257324f - r.y) : r.y;
+  return make_float2(copysignf(r.x, y0), copysignf(r.y, y1));
+}
+
 // difference of two angles given in units of pi, wrapped to [-1, 1]
 __device__ __forceinline__ float wrap_units(float d) {
-  d = (d > 1.0f) ? d - 2.0f : d;
-  d = (d < -1.0f) ? d + 2.0f : d;
-  return d;
+  // d - 2*rint(d/2) with rint done by the 1.5*2^23 magic constant: three FMA-pipe instructions, no compare/select
+  const float k = __fadd_rn(__fmaf_rn(d, 0.5f, 12582912.0f), -12582912.0f);
+  return __fmaf_rn(k, -2.0f, d);
+}
+__device__ __forceinline__ float2 wrap_units2(float2 d) {
+  const float2 m = make_float2(12582912.0f, 12582912.0f);
+  const float2 k = __fadd2_rn(__ffma2_rn(d, make_float2(0.5f, 0.5f), m), make_float2(-12582912.0f, -12582912.0f));
+  return __ffma2_rn(k, make_float2(-2.0f, -2.0f), d);
 }
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -171,15 +206,20 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 // wrap(atan2(dy,dx) - atan2(hy,hx)) as ONE atan2 of the float64 cross/dot products of the two directions
-// (relative error ~2 ulp float32 even for tiny angles; atan2(0,0)=0 makes a zero heading point along +x).
+// (relative error ~4e-7 even for tiny angles).  Callers deal with zero / denormal-tiny vectors.
 __device__ __forceinline__ float rel_angle(double dx, double dy, double hx, double hy) {
-  const bool hzero = (hx == 0.0) & (hy == 0.0);
-  const bool dzero = (dx == 0.0) & (dy == 0.0);
-  hx = hzero ? 1.0 : hx;
-  dx = dzero ? 1.0 : dx;
   double cr = fma(hx, dy, -(hy * dx));
   double dt = fma(hx, dx, hy * dy);
   return fast_atan2((float)cr, (float)dt);
+}
+
+// libm-grade fallback for the rare degenerate inputs (velocity components below ~1e-30 but not both zero, or a
+// UAV sitting exactly on its target): same formulas as the reference, in double.
+static __device__ __noinline__ void angles_slow(double tdx, double tdy, double vx, double vy, float& th_u, float& dth_u) {
+  const double th = atan2(vy, vx);
+  const double d = atan2(tdy, tdx) - th;
+  th_u = (float)(th * 0.3183098861837907);
+  dth_u = (float)(atan2(sin(d), cos(d)) * 0.3183098861837907);
 }
 
 // Caller-side action mapping (test_sac_multi.py:77-80; test_pytorch_multi.py:80).

@@ -23,29 +23,42 @@ __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_kernel(c
   const WarpScratch ws = warp_scratch(smem);
   const Consts& c = a.c;
   const Lane L = make_lane<NT>(a.B, a.N);
+  const bool leader = L.valid & (L.i == 0);
 
+  // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream was
+  // still draining; everything above overlapped with it, nothing below may (it reads memory that kernel wrote).
+  cudaGridDependencySynchronize();
+
+  // every global load of the step is issued here, back to back
   Uav u = load_uav(a.s, L);
   float2 act = make_float2(0.f, 0.f);
   if (L.valid) act = ld_stream(a.io.action + L.m);
+  int steps_new = 0;
+  if (leader) steps_new = ld_stream(a.s.steps + L.env) + 1;  // :238
+  cudaTriggerProgrammaticLaunchCompletion();
   act = map_action(act, a.io.action_mode, c);
 
   const bool parked = (u.flags & UAVCA_FLAG_PARKED) != 0u;
   const float ox = u.px, oy = u.py;  // position before this step
 
   // ---- UAVAgent.step (uav_agent.py:23-36); parked UAVs do not move and report (0, 0)
-  {
+  float dist, prev_d;
+  Own w;
+  if (__any_sync(kFull, parked)) {  // warp-uniform: most warps hold no parked UAV and skip the selects
     double vx = u.vx, vy = u.vy;
     float px = u.px, py = u.py;
     integrate((double)act.x, (double)act.y, vx, vy, px, py, c);
     if (!parked) { u.vx = vx; u.vy = vy; u.px = px; u.py = py; }
+    w = own_features(c, u);  // heading, heading error to the target, distance, |v|^2 (multi_uav_world_2d.py:184-186)
+    dist = parked ? 0.f : w.dist;
+    prev_d = parked ? 0.f : u.prev;
+  } else {
+    integrate((double)act.x, (double)act.y, u.vx, u.vy, u.px, u.py, c);
+    w = own_features(c, u);
+    dist = w.dist;
+    prev_d = u.prev;
   }
-  const Own w = own_features(c, u);  // heading, heading error to the target, distance, |v|^2 (multi_uav_world_2d.py:184-186)
-  ws.pp[L.lane] = make_float4(u.px, u.py, ox, oy);
-  ws.th[L.lane] = w.th_u;
-  __syncwarp();
-
-  const float dist = parked ? 0.f : w.dist;
-  const float prev_d = parked ? 0.f : u.prev;
+  publish(ws, L, u.px, u.py, ox, oy, w.th_u);
 
   // ---- reward shaping (:188-195).  Output only: float32 arithmetic, well inside the 1e-5 tolerance.
   float r;
@@ -91,9 +104,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_kernel(c
   const unsigned done_env = (__ballot_sync(kFull, done) >> L.base) & L.envmask;
   const int reach_inc = __popc((__ballot_sync(kFull, newly_reached & L.valid) >> L.base) & L.envmask);
   const int coll_inc = __popc((__ballot_sync(kFull, hard & L.valid) >> L.base) & L.envmask);
-  int steps_new = 0;
-  const bool leader = L.valid & (L.i == 0);
-  if (leader) steps_new = a.s.steps[L.env] + 1;  // :238
   steps_new = __shfl_sync(kFull, steps_new, L.base);
   bool rs = false;
   if (c.reset_mode & UAVCA_RESET_ON_DONE0) rs |= (done_env & 1u) != 0u;
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(kThreads) reset_multi_kernel(const __grid_cons
       store_obs_rows(ws.stage, a.io.obs, L, o);
     } else if (rs) {  // rows of other envs stay untouched
 #pragma unroll
-      for (int k = 0; k < 10; ++k) a.io.obs[L.m * 10 + k] = o[k];
+      for (int k = 0; k < 10; ++k) a.io.obs[(size_t)L.m * 10 + k] = o[k];
     }
   }
   if (rs) store_uav(a.s, L, u, true);
@@ -410,11 +420,29 @@ static inline int multi_grid(int B, int N) {
     default: { constexpr int NT = 0; CALL; } break;  \
   }
 
+// The step kernel is launched with programmatic stream serialization (PDL): its blocks may become resident while
+// the previous kernel in the stream drains, and wait in cudaGridDependencySynchronize() before touching memory.
+template <int NT>
+static cudaError_t launch_step_multi_n(const KernelArgs& a, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, step_multi_kernel<NT>, a);
+}
+
 cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
   const int grid = multi_grid(a.B, a.N);
-  UAVCA_DISPATCH_N(a.N, (step_multi_kernel<NT><<<grid, kThreads, 0, st>>>(a)));
-  return cudaGetLastError();
+  cudaError_t e = cudaSuccess;
+  UAVCA_DISPATCH_N(a.N, (e = launch_step_multi_n<NT>(a, grid, st)));
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_reset_multi(const KernelArgs& a, const uint8_t* mask, cudaStream_t st) {

@@ -18,9 +18,9 @@ struct Lane {
   int i;            // UAV index inside its env
   int base;         // first lane of this lane's env
   unsigned envmask; // N low bits
-  long long env;    // env index inside the shard
-  long long m;      // flat UAV index env*N + i
-  long long warp_m0;  // flat UAV index of lane 0 of this warp
+  int env;          // env index inside the shard
+  int m;            // flat UAV index env*N + i  (B*N < 2^31 is checked at uavca_create)
+  int warp_m0;      // flat UAV index of lane 0 of this warp
   int valid_lanes;  // lanes of this warp that map to real UAVs (a prefix)
   bool valid;
 };
@@ -32,18 +32,18 @@ __device__ __forceinline__ Lane make_lane(int B, int Nrt) {
   const int epw = 32 / L.N;
   L.lanes_used = epw * L.N;
   L.lane = threadIdx.x & 31;
-  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int e_local = L.lane / L.N;
   L.i = L.lane - e_local * L.N;
   L.base = e_local * L.N;
   L.envmask = L.N >= 32 ? 0xffffffffu : ((1u << L.N) - 1u);
   L.env = warp_global * epw + e_local;
   L.warp_m0 = warp_global * L.lanes_used;
-  long long left = ((long long)B - warp_global * epw) * L.N;
-  L.valid_lanes = left <= 0 ? 0 : (left < L.lanes_used ? (int)left : L.lanes_used);
+  const int left = (B - warp_global * epw) * L.N;  // UAVs from this warp's first env to the end of the shard
+  L.valid_lanes = left <= 0 ? 0 : (left < L.lanes_used ? left : L.lanes_used);
   L.valid = L.lane < L.valid_lanes;
   L.m = L.warp_m0 + L.lane;
-  if (!L.valid) { L.base = L.lane; L.i = 0; L.envmask = 1u; }  // idle lanes only ever talk to themselves
+  if (!L.valid) { L.base = 0; L.i = 0; }  // idle lanes shadow UAV 0 of the warp's first env and never store
   return L;
 }
 
@@ -81,18 +81,33 @@ __device__ __forceinline__ void store_uav(const StateView& s, const Lane& L, con
   }
 }
 
-// Per-warp shared-memory scratch.  Neighbour data never goes to global memory: every lane publishes its position
-// (new and old) and heading once, and the pair loops read them back with 16-byte broadcast loads.
+// Per-warp shared-memory scratch.  Neighbour data never goes to global memory.  Each env owns a DOUBLED ring of
+// 2N slots: slot m < N holds UAV m's (old position, new position), slot N+m holds (new, new) and its heading.
+// Lane i reads slot i+k for k = 1..N-1, i.e. its ring neighbour j = (i+k) mod N, and receives as "a" exactly the
+// position the reference's sequential sweep would see — OLD for j > i (not moved yet), NEW for j < i — and as "n"
+// the NEW position, with no index arithmetic, no compare and no select.  A slot is laid out (a.x, n.x, a.y, n.y)
+// so that both squared distances come out of five packed FP32 instructions (FADD2/FMUL2).
 struct WarpScratch {
-  float4* pp;    // [32] (new.x, new.y, old.x, old.y) per lane
-  float* th;     // [32] heading / pi per lane
+  float4* ring;  // [64] per-env doubled rings, env e at offset 2*e*N
+  float* th;     // [64] heading / pi, doubled the same way
   float* stage;  // [320] observation rows of the warp
 };
-constexpr int kScratchFloats = 32 * 4 + 32 + 32 * 10;
+constexpr int kScratchFloats = 64 * 4 + 64 + 32 * 10;
 
 __device__ __forceinline__ WarpScratch warp_scratch(float* block_smem) {
   float* w = block_smem + (threadIdx.x >> 5) * kScratchFloats;
-  return WarpScratch{reinterpret_cast<float4*>(w), w + 128, w + 160};
+  return WarpScratch{reinterpret_cast<float4*>(w), w + 256, w + 320};
+}
+
+__device__ __forceinline__ void publish(const WarpScratch& ws, const Lane& L, float nx, float ny, float ox, float oy, float th_u) {
+  if (L.valid) {
+    const int slot = 2 * L.base + L.i;
+    ws.ring[slot] = make_float4(ox, nx, oy, ny);
+    ws.ring[slot + L.N] = make_float4(nx, nx, ny, ny);
+    ws.th[slot] = th_u;
+    ws.th[slot + L.N] = th_u;
+  }
+  __syncwarp();
 }
 
 // Two nearest other UAVs of the env, ordered by (squared float32 distance, index).
@@ -101,37 +116,37 @@ struct Top2 {
   int j1, j2;
 };
 
-// branch-free insertion; visiting j in ascending order keeps the lower index first among equal distances
-__device__ __forceinline__ void top2_insert(Top2& t, float s, int j) {
+// branch-free insertion; visiting the ring offsets k in ascending order keeps the nearer ring offset first among
+// exactly equal distances (the reference's own order of exact ties is undefined)
+__device__ __forceinline__ void top2_insert(Top2& t, float s, int k) {
   const bool p1 = s < t.s1, p2 = s < t.s2;
-  t.j2 = p1 ? t.j1 : (p2 ? j : t.j2);
+  t.j2 = p1 ? t.j1 : (p2 ? k : t.j2);
   t.s2 = p1 ? t.s1 : (p2 ? s : t.s2);
-  t.j1 = p1 ? j : t.j1;
+  t.j1 = p1 ? k : t.j1;
   t.s1 = p1 ? s : t.s1;
 }
 
-// One sweep over the env's UAVs serving both pairwise passes of MultiUAVWorld2D.step:
+// One sweep over the env's other UAVs serving both pairwise passes of MultiUAVWorld2D.step:
 //   pass A (multi_uav_world_2d.py:198-210): nearest neighbour with j<i at the NEW position and j>i at the OLD one
 //                                           (the reference moves and tests the UAVs one after the other);
 //   pass B (:75 via _get_obs):              the two nearest neighbours with every UAV at its NEW position.
-// For reset/observe the old and new positions coincide and smin is simply unused.
+// Top2.j1/j2 are ring offsets k (neighbour slot = own slot + k); 0 = none.
 template <int NT>
 __device__ __forceinline__ void pair_scan(const WarpScratch& ws, const Lane& L, float px, float py, float& smin, Top2& t) {
   const float inf = __int_as_float(0x7f800000);
   smin = inf;
-  t = Top2{inf, inf, -1, -1};
+  t = Top2{inf, inf, 0, 0};
   const int N = NT > 0 ? NT : L.N;
-  const float4* row = ws.pp + L.base;
+  const float4* row = ws.ring + 2 * L.base + L.i;
+  const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const float4 q = row[j];
-    float sn = sq32(__fsub_rn(q.x, px), __fsub_rn(q.y, py));
-    const float so = sq32(__fsub_rn(q.z, px), __fsub_rn(q.w, py));
-    float sa = (j < L.i) ? sn : so;
-    sa = (j == L.i) ? inf : sa;
-    sn = (j == L.i) ? inf : sn;
-    smin = fminf(smin, sa);
-    top2_insert(t, sn, j);
+  for (int k = 1; k < N; ++k) {
+    const float4 q = row[k];
+    // (a.x - p.x, n.x - p.x), (a.y - p.y, n.y - p.y); squares and sum rounded separately, exactly as sq32()
+    const float2 dx = __fadd2_rn(make_float2(q.x, q.y), npx), dy = __fadd2_rn(make_float2(q.z, q.w), npy);
+    const float2 s = __fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy));
+    smin = fminf(smin, s.x);
+    top2_insert(t, s.y, k);
   }
 }
 
@@ -147,19 +162,21 @@ __device__ __forceinline__ void obs_multi(const Consts& c, const WarpScratch& ws
   o[1] = th_u;
   o[2] = dist * c.inv_diag;                      // :67-68
   o[3] = dth_u;
-  const bool have1 = (t.j1 >= 0) & (t.s1 < c.s_dsense_lt);  // uav_agent.py:52 strict <
-  const bool have2 = have1 & (t.j2 >= 0) & (t.s2 < c.s_dsense_lt);
-  const int k1 = L.base + (t.j1 < 0 ? 0 : t.j1), k2 = L.base + (t.j2 < 0 ? 0 : t.j2);
-  const float4 q1 = ws.pp[k1], q2 = ws.pp[k2];
-  const float h1 = ws.th[k1], h2 = ws.th[k2];
-  const float b1 = fast_atan2(__fsub_rn(q1.y, py), __fsub_rn(q1.x, px)) * c.inv_pi;
-  const float b2 = fast_atan2(__fsub_rn(q2.y, py), __fsub_rn(q2.x, px)) * c.inv_pi;
+  const bool have1 = t.s1 < c.s_dsense_lt;       // uav_agent.py:52 strict <  (s = +inf when there is no other UAV)
+  const bool have2 = have1 & (t.s2 < c.s_dsense_lt);
+  const int slot = 2 * L.base + L.i;
+  const float4 q1 = ws.ring[slot + t.j1], q2 = ws.ring[slot + t.j2];
+  const float h1 = ws.th[slot + t.j1], h2 = ws.th[slot + t.j2];
+  const float2 b = fast_atan2_pair(__fsub_rn(q1.w, py), __fsub_rn(q1.y, px), __fsub_rn(q2.w, py), __fsub_rn(q2.y, px));
+  const float2 nth = make_float2(-th_u, -th_u);
+  const float2 w1 = wrap_units2(__ffma2_rn(b, make_float2(c.inv_pi, c.inv_pi), nth));  // bearings relative to the heading
+  const float2 w2 = wrap_units2(__fadd2_rn(make_float2(h1, h2), nth));                 // neighbour headings, relative
   o[4] = have1 ? sqrt_approx(t.s1) * c.inv_dsense : 1.0f;  // :77
-  o[5] = have1 ? wrap_units(b1 - th_u) : 1.0f;             // :78-81 (no neighbour: bearing pi)
-  o[6] = have1 ? wrap_units(h1 - th_u) : 0.0f;             // :82-85
+  o[5] = have1 ? w1.x : 1.0f;                              // :78-81 (no neighbour: bearing pi)
+  o[6] = have1 ? w2.x : 0.0f;                              // :82-85
   o[7] = have2 ? sqrt_approx(t.s2) * c.inv_dsense : 1.0f;  // :87
-  o[8] = have2 ? wrap_units(b2 - th_u) : 1.0f;             // :88-91
-  o[9] = have2 ? wrap_units(h2 - th_u) : 0.0f;             // :92-95
+  o[8] = have2 ? w1.y : 1.0f;                              // :88-91
+  o[9] = have2 ? w2.y : 0.0f;                              // :92-95
 }
 
 // Everything the observation needs from a UAV's own state.
@@ -172,8 +189,16 @@ __device__ __forceinline__ Own own_features(const Consts& c, const Uav& u) {
   const float tdx = __fsub_rn(u.tx, u.px), tdy = __fsub_rn(u.ty, u.py);
   w.dist = n32(tdx, tdy);
   w.vsq = sq64(u.vx, u.vy);
-  w.th_u = fast_atan2((float)u.vy, (float)u.vx) * c.inv_pi;
-  w.dth_u = rel_angle((double)tdx, (double)tdy, u.vx, u.vy) * c.inv_pi;
+  const float fvx = (float)u.vx, fvy = (float)u.vy;
+  const bool vzero = (u.vx == 0.0) & (u.vy == 0.0);  // atan2(0, 0) = 0: a zero heading points along +x
+  const double cr = fma(u.vx, (double)tdy, -(u.vy * (double)tdx));
+  const double dt = fma(u.vx, (double)tdx, u.vy * (double)tdy);
+  const float2 ang = fast_atan2_pair(fvy, fvx, vzero ? tdy : (float)cr, vzero ? tdx : (float)dt);
+  w.th_u = ang.x * c.inv_pi;
+  w.dth_u = ang.y * c.inv_pi;
+  // degenerate inputs (never produced by ordinary flight): denormal-tiny velocity or a UAV exactly on its target
+  const bool odd = (!vzero & (fabsf(fvx) + fabsf(fvy) < 1e-30f)) | ((tdx == 0.0f) & (tdy == 0.0f));
+  if (odd) angles_slow((double)tdx, (double)tdy, u.vx, u.vy, w.th_u, w.dth_u);
   return w;
 }
 
@@ -182,9 +207,7 @@ template <int NT>
 __device__ __forceinline__ void observe_state(const Consts& c, const WarpScratch& ws, const Lane& L, const Uav& u, float o[10]) {
   const Own w = own_features(c, u);
   __syncwarp();
-  ws.pp[L.lane] = make_float4(u.px, u.py, u.px, u.py);
-  ws.th[L.lane] = w.th_u;
-  __syncwarp();
+  publish(ws, L, u.px, u.py, u.px, u.py, w.th_u);
   float smin;
   Top2 t;
   pair_scan<NT>(ws, L, u.px, u.py, smin, t);
@@ -199,7 +222,7 @@ __device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const 
 #pragma unroll
   for (int k = 0; k < 5; ++k) st2[k] = make_float2(o[2 * k], o[2 * k + 1]);
   __syncwarp();
-  float* g = gobs + L.warp_m0 * 10;
+  float* g = gobs + (size_t)L.warp_m0 * 10;
   const int n2 = L.valid_lanes * 5;  // float2 elements to write
   if ((L.lanes_used & 1) == 0) {     // every warp's run starts on a 16-byte boundary
     const int n4 = n2 >> 1;          // <= 80

@@ -130,11 +130,11 @@ static void obs_multi(const uavca_config* c, const float* pos, const double* vel
 
   /* uavs_in_range (uav_agent.py:44-64): in-range neighbours ascending by float32 distance.  Exact-distance
    * ties have no defined order in the reference (unstable argsort); we refine the order by (squared
-   * distance, index), which agrees with the reference whenever it is defined. */
+   * distance, ring offset (j - i) mod N), which agrees with the reference whenever it is defined. */
   int j1 = -1, j2 = -1;
   float s1 = INFINITY, s2 = INFINITY;
-  for (int j = 0; j < N; ++j) {
-    if (j == i) continue;
+  for (int k = 1; k < N; ++k) {
+    int j = i + k; if (j >= N) j -= N;
     float s = s32(pos[2 * j] - px, pos[2 * j + 1] - py);
     if (s < s1) { s2 = s1; j2 = j1; s1 = s; j1 = j; }
     else if (s < s2) { s2 = s; j2 = j; }
