@@ -86,7 +86,7 @@ __device__ __forceinline__ void store_uav(const StateView& s, const Lane& L, con
 // Lane i reads slot i+k for k = 1..N-1, i.e. its ring neighbour j = (i+k) mod N, and receives as "a" exactly the
 // position the reference's sequential sweep would see — OLD for j > i (not moved yet), NEW for j < i — and as "n"
 // the NEW position, with no index arithmetic, no compare and no select.  A slot is laid out (a.x, n.x, a.y, n.y)
-// so that both squared distances come out of five packed FP32 instructions (FADD2/FMUL2).
+// so that both squared distances come out of four packed FP32 instructions (FADD2/FMUL2) and two scalar adds.
 struct WarpScratch {
   float4* ring;  // [64] per-env doubled rings, env e at offset 2*e*N
   float* th;     // [64] heading / pi, doubled the same way
@@ -144,7 +144,10 @@ __device__ __forceinline__ void pair_scan(const WarpScratch& ws, const Lane& L, 
     const float4 q = row[k];
     // (a.x - p.x, n.x - p.x), (a.y - p.y, n.y - p.y); squares and sum rounded separately, exactly as sq32()
     const float2 dx = __fadd2_rn(make_float2(q.x, q.y), npx), dy = __fadd2_rn(make_float2(q.z, q.w), npy);
-    const float2 s = __fadd2_rn(__fmul2_rn(dx, dx), __fmul2_rn(dy, dy));
+    // the final sum is two SCALAR adds on purpose: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+    // even though both carry .rn (and even under -fmad=false), which would break the unfused np.linalg.norm order
+    const float2 xx = __fmul2_rn(dx, dx), yy = __fmul2_rn(dy, dy);
+    const float2 s = make_float2(__fadd_rn(xx.x, yy.x), __fadd_rn(xx.y, yy.y));
     smin = fminf(smin, s.x);
     top2_insert(t, s.y, k);
   }

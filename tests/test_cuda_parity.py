@@ -236,6 +236,52 @@ def test_single_1000_step_rollout():
             assert np.array_equal(info["distance"][sl].cpu().numpy(), out["distance"])
 
 
+def _edge_states(B, N, radius, rng, spread_ulps=6):
+    """Stationary UAVs whose pair distances sit within a few float32 ulps of `radius` (zero velocity + zero action
+    keep every position fixed, so the step tests exactly these distances)."""
+    st = O.State(B, N)
+    centre = rng.uniform(-6.0, 6.0, size=(B, 1, 2))
+    phi = rng.uniform(0, 2 * np.pi, size=(B, N))
+    # UAV 0 in the middle, the others on a circle of ~radius around it (their mutual distances are arbitrary)
+    r = radius * (1.0 + rng.integers(-spread_ulps, spread_ulps + 1, size=(B, N)) * 2.0 ** -24)
+    off = np.stack([r * np.cos(phi), r * np.sin(phi)], axis=-1)
+    off[:, 0] = 0.0
+    st.pos[...] = (centre + off).astype(np.float32)
+    st.tgt[...] = (st.pos.astype(np.float64) + rng.uniform(5.0, 7.0, size=(B, N, 2))).astype(np.float32)
+    d = st.tgt - st.pos
+    st.init[...] = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1], dtype=np.float32)
+    st.prev[...] = st.init
+    return st
+
+
+@pytest.mark.parametrize("radius,n", [(2.0, 2), (1.0, 2), (15.0, 2), (2.0, 5), (1.0, 8), (2.0, 32)])
+def test_threshold_edges_are_bit_exact(radius, n):
+    """Soft collision (d <= 2.0), hard collision (d <= 1.0) and sensing range (d < 15) decided on distances within
+    a few ulps of the threshold: the float32 norm must be formed exactly as the reference does (products and sum
+    rounded separately; a fused multiply-add flips ~8 % of these)."""
+    B = 131072 if n <= 8 else 8192
+    cfg = O.multi_config(B, n, x_size=60.0, y_size=60.0, seed=3)
+    rng = np.random.default_rng(int(radius * 10) + n)
+    st = _edge_states(B, n, radius, rng)
+    d01 = st.pos[:, 1] - st.pos[:, 0]
+    s01 = (d01[:, 0] * d01[:, 0] + d01[:, 1] * d01[:, 1]).astype(np.float32)
+    lo, hi = np.float32(radius) ** 2 * np.float32(1 - 2e-6), np.float32(radius) ** 2 * np.float32(1 + 2e-6)
+    assert ((s01 > lo) & (s01 < hi)).all(), "the crafted distances should hug the threshold"
+    env = make_env(cfg)
+    orc = O.Oracle(cfg, nthreads=8)
+    orc.state = st.copy()
+    load_state(env.state, st)
+    zero = torch.zeros((B, n, 2), device="cuda")
+    for t in range(2):  # second step: the collided latch is set, collision_count must not grow again
+        env.step(zero)
+        out = orc.step(zero.cpu().numpy())
+        assert_outputs(env, out, f"(edge {radius}, step {t})")
+        assert_state_equal(env, orc.state, f"(edge {radius}, step {t})")
+    if radius == 2.0 and n == 2:
+        hit = int((out["reward"] == -2.0).sum())
+        assert 0 < hit < B * n, "the edge cases should fall on both sides of the threshold"
+
+
 # ---- reset ------------------------------------------------------------------------------------------------------
 
 
