@@ -2,6 +2,7 @@
 // No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -60,15 +61,6 @@ StateView view_of(void* blob, const uavca_layout& L) {
   v.coll = reinterpret_cast<int*>(p + L.coll);
   v.episode = reinterpret_cast<unsigned*>(p + L.episode);
   return v;
-}
-
-// Shift a view to the sub-range of envs starting at env0 (stats stay shared).
-StateView offset_view(const StateView& v, long long env0, int N) {
-  StateView o = v;
-  const long long m0 = env0 * N;
-  o.pos += m0; o.vel += m0; o.tgt += m0; o.init += m0; o.prev += m0; o.flags += m0;
-  o.steps += env0; o.reach += env0; o.coll += env0; o.episode += env0;
-  return o;
 }
 
 // np.linalg.norm of a float64 2-vector as the reference's BLAS forms it (second product fused).
@@ -157,6 +149,7 @@ struct uavca_handle {
   uavca_layout pool_layout{};
   float4* ring = nullptr;  // circular-reset table (owned)
   long long launches = 0;
+  int path = UAVCA_PATH_AUTO;  // UAVCA_STEP_PATH=lanes in the environment forces the per-lane kernel (A/B measurements)
   // end-to-end (host buffer) path, created lazily
   static constexpr int kHostStreams = 3;
   cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
@@ -254,6 +247,7 @@ int uavca_create(const uavca_config* cfg, int device, uavca_handle** out) {
   h->consts = derive_consts(*cfg);
   h->device = device;
   compute_layout(cfg->num_envs, cfg->num_agents, &h->layout);
+  if (const char* p = std::getenv("UAVCA_STEP_PATH")) h->path = std::strcmp(p, "lanes") == 0 ? UAVCA_PATH_LANES : UAVCA_PATH_AUTO;
   if (cfg->kind == UAVCA_KIND_MULTI && cfg->circular) {
     // multi_uav_world_2d.py:157-163, computed with the host libm and rounded to the float32 state
     DeviceGuard g(device);
@@ -358,9 +352,10 @@ int uavca_step_multi(uavca_handle* h, void* state, const float* action, int acti
   a.io.action = reinterpret_cast<const float2*>(action);
   a.io.obs = obs; a.io.reward = reward; a.io.done = done; a.io.final_obs = final_obs; a.io.reset_mask = reset_mask;
   a.io.action_mode = action_mode; a.io.evaluate = evaluate;
-  cudaError_t e = launch_step_multi(a, (cudaStream_t)stream);
+  int launched = 0;
+  cudaError_t e = launch_step_multi(a, (cudaStream_t)stream, &launched, h->path);
+  h->launches += launched;
   if (e != cudaSuccess) return fail_cuda("uavca_step_multi", e);
-  h->launches += 1;
   return 0;
 }
 
@@ -446,9 +441,10 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
     a.io.action = reinterpret_cast<const float2*>(h->d_action + m0 * 2);
     a.io.obs = h->d_obs + m0 * D; a.io.reward = h->d_reward + m0; a.io.done = h->d_done + m0;
     a.io.action_mode = action_mode; a.io.evaluate = evaluate;
-    e = h->cfg.kind == UAVCA_KIND_SINGLE ? launch_step_single(a, st) : launch_step_multi(a, st);
+    int launched = 1;
+    e = h->cfg.kind == UAVCA_KIND_SINGLE ? launch_step_single(a, st) : launch_step_multi(a, st, &launched, h->path);
+    h->launches += launched;
     if (e != cudaSuccess) return fail_cuda("uavca_step_host launch", e);
-    h->launches += 1;
     if ((e = cudaMemcpyAsync(host_obs + m0 * D, h->d_obs + m0 * D, mc * D * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
       return fail_cuda("D2H obs", e);
     if ((e = cudaMemcpyAsync(host_reward + m0, h->d_reward + m0, mc * sizeof(float), cudaMemcpyDeviceToHost, st)) != cudaSuccess)

@@ -7,7 +7,10 @@
 
 namespace uavca {
 
-cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st);
+// path: which kernel(s) may run the step (UAVCA_PATH_AUTO: TMA bulk kernel for whole tiles + per-lane kernel for the
+// ragged rest; UAVCA_PATH_LANES: per-lane kernel only).  *launched receives the number of kernels launched.
+enum : int { UAVCA_PATH_AUTO = 0, UAVCA_PATH_LANES = 1 };
+cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path);
 cudaError_t launch_reset_multi(const KernelArgs& a, const uint8_t* mask, cudaStream_t st);
 cudaError_t launch_observe_multi(const KernelArgs& a, cudaStream_t st);
 cudaError_t launch_step_single(const KernelArgs& a, cudaStream_t st);
@@ -15,5 +18,14 @@ cudaError_t launch_reset_single(const KernelArgs& a, const uint8_t* mask, cudaSt
 cudaError_t launch_observe_single(const KernelArgs& a, cudaStream_t st);
 cudaError_t launch_map_action(const Consts& c, const float* in, float* out, long long M, int mode, cudaStream_t st);
 cudaError_t launch_stats(const StateView& s, int B, long long* out8, cudaStream_t st);
+
+// Shift a view to the sub-range of envs starting at env0 (stats stay shared).
+inline StateView offset_view(const StateView& v, long long env0, int N) {
+  StateView o = v;
+  const long long m0 = env0 * N;
+  o.pos += m0; o.vel += m0; o.tgt += m0; o.init += m0; o.prev += m0; o.flags += m0;
+  o.steps += env0; o.reach += env0; o.coll += env0; o.episode += env0;
+  return o;
+}
 
 }  // namespace uavca

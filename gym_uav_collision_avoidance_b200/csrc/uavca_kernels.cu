@@ -10,6 +10,7 @@
 // dense contraction anywhere in the step.
 #include "uavca_host.h"
 #include "uavca_multi.cuh"
+#include "uavca_tma.cuh"
 
 namespace uavca {
 
@@ -17,154 +18,45 @@ namespace uavca {
 // Multi-UAV world
 // ================================================================================================================
 
+// I/O policy of step_core for per-lane streaming global accesses (ragged tails, unaligned tensors, any N).
+struct GlobalIO {
+  const KernelArgs& a;
+  const Lane& L;
+  float* stage;  // per-warp staging of the observation rows
+  __device__ __forceinline__ Uav load_uav() const { return uavca::load_uav(a.s, L); }
+  __device__ __forceinline__ float2 load_action() const {
+    return L.valid ? ld_stream(a.io.action + L.m) : make_float2(0.f, 0.f);
+  }
+  __device__ __forceinline__ int load_steps() const { return ld_stream(a.s.steps + L.env); }
+  // Programmatic dependent launch: every input is in registers, the next kernel of the stream may start launching
+  __device__ __forceinline__ void loads_done() const { cudaTriggerProgrammaticLaunchCompletion(); }
+  __device__ __forceinline__ void store_reward_done(float r, bool done) const {
+    if (L.valid) {
+      st_stream(a.io.reward + L.m, r);
+      st_stream(a.io.done + L.m, (uint8_t)done);
+    }
+  }
+  __device__ __forceinline__ bool wants_final() const { return a.io.final_obs != nullptr; }
+  __device__ __forceinline__ void store_obs(const float o[10]) const { store_obs_rows(stage, a.io.obs, L, o); }
+  __device__ __forceinline__ void store_final(const float o[10]) const { store_obs_rows(stage, a.io.final_obs, L, o); }
+  __device__ __forceinline__ void store_state(const Uav& u) const { store_uav(a.s, L, u, false); }
+  __device__ __forceinline__ void store_target(const Uav& u) const {
+    st_stream(a.s.tgt + L.m, make_float2(u.tx, u.ty));
+    st_stream(a.s.init + L.m, u.init);
+  }
+  __device__ __forceinline__ void store_steps(int v) const { a.s.steps[L.env] = v; }
+};
+
 template <int NT>
 __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
   const WarpScratch ws = warp_scratch(smem);
-  const Consts& c = a.c;
   const Lane L = make_lane<NT>(a.B, a.N);
-  const bool leader = L.valid & (L.i == 0);
-
   // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream was
   // still draining; everything above overlapped with it, nothing below may (it reads memory that kernel wrote).
   cudaGridDependencySynchronize();
-
-  // every global load of the step is issued here, back to back
-  Uav u = load_uav(a.s, L);
-  float2 act = make_float2(0.f, 0.f);
-  if (L.valid) act = ld_stream(a.io.action + L.m);
-  int steps_new = 0;
-  if (leader) steps_new = ld_stream(a.s.steps + L.env) + 1;  // :238
-  cudaTriggerProgrammaticLaunchCompletion();
-  act = map_action(act, a.io.action_mode, c);
-
-  const bool parked = (u.flags & UAVCA_FLAG_PARKED) != 0u;
-  const float ox = u.px, oy = u.py;  // position before this step
-
-  // ---- UAVAgent.step (uav_agent.py:23-36); parked UAVs do not move and report (0, 0)
-  float dist, prev_d;
-  Own w;
-  if (__any_sync(kFull, parked)) {  // warp-uniform: most warps hold no parked UAV and skip the selects
-    double vx = u.vx, vy = u.vy;
-    float px = u.px, py = u.py;
-    integrate((double)act.x, (double)act.y, vx, vy, px, py, c);
-    if (!parked) { u.vx = vx; u.vy = vy; u.px = px; u.py = py; }
-    w = own_features(c, u);  // heading, heading error to the target, distance, |v|^2 (multi_uav_world_2d.py:184-186)
-    dist = parked ? 0.f : w.dist;
-    prev_d = parked ? 0.f : u.prev;
-  } else {
-    integrate((double)act.x, (double)act.y, u.vx, u.vy, u.px, u.py, c);
-    w = own_features(c, u);
-    dist = w.dist;
-    prev_d = u.prev;
-  }
-  publish(ws, L, u.px, u.py, ox, oy, w.th_u);
-
-  // ---- reward shaping (:188-195).  Output only: float32 arithmetic, well inside the 1e-5 tolerance.
-  float r;
-  {
-    const float m = (u.init <= c.vm2_floor_f) ? 1.0f : __fdividef(c.vm2_f, u.init);  // min(vm2/init, 1)
-    r = fmaf(50.0f * c.inv_vm2_f, __fsub_rn(prev_d, dist), -0.01f * m);
-    const float q = __fdividef(dist, 1.5f * u.init);
-    r *= (r > 0.0f) ? (1.0f - q) : (1.0f + q);
-    r = fmaf(-0.01f * 3.14159274101257324f, fabsf(w.dth_u), r);
-  }
-
-  // ---- both pairwise passes in one sweep over the env's UAVs
-  float smin;
-  Top2 t;
-  pair_scan<NT>(ws, L, u.px, u.py, smin, t);
-
-  // ---- collisions (:199-210), decided in squared-distance space
-  const bool in_range = smin < c.s_dsense_lt;
-  const bool collision = in_range & (smin <= c.s_two_r_le);
-  r = collision ? -2.0f : r;
-  const bool hard = in_range & (smin <= c.s_two_h_le) & !parked & ((u.flags & UAVCA_FLAG_COLLIDED) == 0u);
-  if (hard) u.flags |= UAVCA_FLAG_COLLIDED;
-
-  // ---- done logic (:213-227)
-  const bool slow = w.vsq < c.reach_speed_sq;
-  const bool inside = (u.px >= c.lox_f) & (u.px <= c.hix_f) & (u.py >= c.loy_f) & (u.py <= c.hiy_f);
-  const bool reached = (dist < c.reach_dist) & !collision & slow;
-  const bool newly_reached = reached & !parked;
-  bool done = reached | (!inside & (a.io.evaluate == 0));
-  if (reached) {  // UAVAgent.finish (uav_agent.py:38-42)
-    u.flags |= UAVCA_FLAG_PARKED;
-    const double nv = sqrt(w.vsq);
-    double fx = __dmul_rn(__ddiv_rn(u.vx, nv), 0.001), fy = __dmul_rn(__ddiv_rn(u.vy, nv), 0.001);
-    if ((fx != fx) | (fy != fy)) { fx = 0.0; fy = 0.0; }
-    u.vx = fx; u.vy = fy;
-    r += 10.0f;
-  }
-  const double vsq_obs = reached ? sq64(u.vx, u.vy) : w.vsq;
-  u.prev = dist;  // :229
-  if (!L.valid) done = false;
-
-  // ---- per-env bookkeeping: counters, reset decision
-  const unsigned done_env = (__ballot_sync(kFull, done) >> L.base) & L.envmask;
-  const int reach_inc = __popc((__ballot_sync(kFull, newly_reached & L.valid) >> L.base) & L.envmask);
-  const int coll_inc = __popc((__ballot_sync(kFull, hard & L.valid) >> L.base) & L.envmask);
-  steps_new = __shfl_sync(kFull, steps_new, L.base);
-  bool rs = false;
-  if (c.reset_mode & UAVCA_RESET_ON_DONE0) rs |= (done_env & 1u) != 0u;
-  if (c.reset_mode & UAVCA_RESET_ON_ALL_DONE) rs |= done_env == L.envmask;
-  if (c.reset_mode & UAVCA_RESET_ON_ANY_DONE) rs |= done_env != 0u;
-  if (c.max_steps > 0) rs |= steps_new >= c.max_steps;
-  rs &= L.valid;
-
-  if (L.valid) {
-    st_stream(a.io.reward + L.m, r);
-    st_stream(a.io.done + L.m, (uint8_t)done);
-  }
-  if (leader && a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
-
-  // ---- observation (:233-235): every UAV at its new position
-  float o[10];
-  obs_multi(c, ws, L, u.px, u.py, w.th_u, w.dth_u, w.dist, vsq_obs, t, o);
-
-  if (__any_sync(kFull, rs)) {
-    // at least one env of this warp starts a new episode in place
-    if (a.io.final_obs) store_obs_rows(ws.stage, a.io.final_obs, L, o);
-    unsigned episode = 0;
-    if (leader) episode = a.s.episode[L.env];
-    episode = __shfl_sync(kFull, episode, L.base);
-    if (leader) {
-      if (rs) {
-        if (episode > 0u) {  // fold the finished episode into the running totals
-          atomicAdd(a.s.stats + 0, 1ull);
-          atomicAdd(a.s.stats + 1, (unsigned long long)(a.s.reach[L.env] + reach_inc));
-          atomicAdd(a.s.stats + 2, (unsigned long long)(a.s.coll[L.env] + coll_inc));
-          atomicAdd(a.s.stats + 3, (unsigned long long)steps_new);
-        }
-        a.s.steps[L.env] = 0; a.s.reach[L.env] = 0; a.s.coll[L.env] = 0;  // :166-168
-        a.s.episode[L.env] = episode + 1u;
-      } else {
-        a.s.steps[L.env] = steps_new;
-        if (reach_inc) a.s.reach[L.env] += reach_inc;
-        if (coll_inc) a.s.coll[L.env] += coll_inc;
-      }
-    }
-    Uav nu = u;
-    reset_multi(a, L, rs, episode, nu);
-    float no[10];
-    observe_state<NT>(c, ws, L, nu, no);
-    if (rs) {
-      u = nu;
-#pragma unroll
-      for (int k = 0; k < 10; ++k) o[k] = no[k];
-    }
-    store_obs_rows(ws.stage, a.io.obs, L, o);
-    store_uav(a.s, L, u, rs);
-  } else {
-    if (leader) {
-      a.s.steps[L.env] = steps_new;
-      if (reach_inc) a.s.reach[L.env] += reach_inc;  // :221
-      if (coll_inc) a.s.coll[L.env] += coll_inc;     // :209
-    }
-    store_obs_rows(ws.stage, a.io.obs, L, o);
-    if (a.io.final_obs) store_obs_rows(ws.stage, a.io.final_obs, L, o);
-    store_uav(a.s, L, u, false);
-  }
+  GlobalIO io{a, L, ws.stage};
+  step_core<NT>(a, ws, L, io);
 }
 
 template <int NT>
@@ -437,12 +329,116 @@ static cudaError_t launch_step_multi_n(const KernelArgs& a, int grid, cudaStream
   return cudaLaunchKernelEx(&cfg, step_multi_kernel<NT>, a);
 }
 
-cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st) {
+// ---- bulk path (uavca_tma.cuh): persistent grid sized to the SM slots the kernel can hold --------------------------
+
+template <typename Kernel>
+static cudaError_t launch_pdl(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t st, const KernelArgs& a,
+                              int num_tiles) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a, num_tiles);
+}
+
+template <int NT, bool FINAL>
+static cudaError_t launch_step_tma_n(const KernelArgs& a, int num_tiles, cudaStream_t st) {
+  using G = TmaGeom<NT, FINAL>;
+  constexpr int kMaxDev = 64;
+  static int slots[kMaxDev] = {0};  // resident CTAs per device for this instantiation (0 = not configured yet)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDev) return cudaErrorInvalidDevice;
+  auto kernel = step_multi_tma_kernel<NT, FINAL>;
+  if (slots[dev] == 0) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, G::THREADS, G::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    slots[dev] = per_sm * sms;
+  }
+  const int grid = num_tiles < slots[dev] ? num_tiles : slots[dev];
+  return launch_pdl(kernel, grid, G::THREADS, G::SMEM_BYTES, st, a, num_tiles);
+}
+
+// envs per tile of the bulk path for this N (0: no bulk path, the per-lane kernel takes everything)
+static int tma_tile_envs(int N) {
+  switch (N) {
+    case 2: return TmaGeom<2, false>::E;
+    case 4: return TmaGeom<4, false>::E;
+    case 5: return TmaGeom<5, false>::E;
+    case 8: return TmaGeom<8, false>::E;
+    case 10: return TmaGeom<10, false>::E;
+    case 16: return TmaGeom<16, false>::E;
+    case 32: return TmaGeom<32, false>::E;
+    default: return 0;
+  }
+}
+
+#define UAVCA_DISPATCH_TMA(N, CALL)                  \
+  switch (N) {                                       \
+    case 2: { constexpr int NT = 2; CALL; } break;   \
+    case 4: { constexpr int NT = 4; CALL; } break;   \
+    case 5: { constexpr int NT = 5; CALL; } break;   \
+    case 8: { constexpr int NT = 8; CALL; } break;   \
+    case 10: { constexpr int NT = 10; CALL; } break; \
+    case 16: { constexpr int NT = 16; CALL; } break; \
+    case 32: { constexpr int NT = 32; CALL; } break; \
+    default: break;                                  \
+  }
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path) {
+  if (launched) *launched = 0;
   if (a.B <= 0) return cudaSuccess;
-  const int grid = multi_grid(a.B, a.N);
   cudaError_t e = cudaSuccess;
-  UAVCA_DISPATCH_N(a.N, (e = launch_step_multi_n<NT>(a, grid, st)));
-  return e != cudaSuccess ? e : cudaGetLastError();
+  // whole tiles go through the bulk (TMA) kernel, the ragged rest through the per-lane kernel
+  int tile_envs = path == UAVCA_PATH_LANES ? 0 : tma_tile_envs(a.N);
+  if (tile_envs && !(aligned16(a.io.action) && aligned16(a.io.obs) && aligned16(a.io.reward) && aligned16(a.io.done) &&
+                     aligned16(a.io.final_obs) && aligned16(a.s.pos) && aligned16(a.s.vel) && aligned16(a.s.tgt) &&
+                     aligned16(a.s.init) && aligned16(a.s.prev) && aligned16(a.s.flags) && aligned16(a.s.steps)))
+    tile_envs = 0;
+  const int tiles = tile_envs ? a.B / tile_envs : 0;
+  const int bulk_envs = tiles * tile_envs;
+  if (tiles > 0) {
+    if (a.io.final_obs) {
+      UAVCA_DISPATCH_TMA(a.N, (e = launch_step_tma_n<NT, true>(a, tiles, st)));
+    } else {
+      UAVCA_DISPATCH_TMA(a.N, (e = launch_step_tma_n<NT, false>(a, tiles, st)));
+    }
+    if (e != cudaSuccess) return e;
+    if (launched) *launched += 1;
+  }
+  if (bulk_envs < a.B) {
+    KernelArgs r = a;
+    const long long m0 = (long long)bulk_envs * a.N;
+    r.s = offset_view(a.s, bulk_envs, a.N);
+    r.c.env_base += bulk_envs;
+    r.B = a.B - bulk_envs;
+    r.io.action += m0;
+    r.io.obs += m0 * UAVCA_OBS_DIM_MULTI;
+    r.io.reward += m0;
+    r.io.done += m0;
+    if (r.io.final_obs) r.io.final_obs += m0 * UAVCA_OBS_DIM_MULTI;
+    if (r.io.reset_mask) r.io.reset_mask += bulk_envs;
+    const int grid = multi_grid(r.B, r.N);
+    UAVCA_DISPATCH_N(r.N, (e = launch_step_multi_n<NT>(r, grid, st)));
+    if (e != cudaSuccess) return e;
+    if (launched) *launched += 1;
+  }
+  return cudaGetLastError();
 }
 
 cudaError_t launch_reset_multi(const KernelArgs& a, const uint8_t* mask, cudaStream_t st) {

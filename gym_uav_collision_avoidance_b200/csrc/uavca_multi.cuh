@@ -331,4 +331,172 @@ __device__ __forceinline__ void reset_multi(const KernelArgs& a, const Lane& L, 
   }
 }
 
+// ================================================================================================================
+// The step itself, independent of where the state and the I/O live.  `IO` is a policy that moves one UAV's data:
+//   GlobalIO (uavca_kernels.cu)  per-lane streaming global loads/stores           (ragged tails, any N, any alignment)
+//   SmemIO   (uavca_tma.cuh)     shared-memory stage filled / drained by TMA bulk copies (the bulk of every batch)
+// Both run exactly this code, so they cannot disagree on semantics.
+//
+//   Uav   load_uav();  float2 load_action();  int load_steps();        (load_steps: env leader lanes only)
+//   void  loads_done();                                                (every input of this warp is in registers)
+//   void  store_reward_done(float r, bool done);
+//   void  store_obs(const float o[10]);   void store_final(const float o[10]);
+//   void  store_state(const Uav&);        pos, vel, prev, flags
+//   void  store_target(const Uav&);       tgt, init (reset lanes only)
+//   void  store_steps(int);               (env leader lanes only)
+//   bool  wants_final();
+// ================================================================================================================
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <int NT, class IO>
+__device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch& ws, const Lane& L, IO& io) {
+  const Consts& c = a.c;
+  const bool leader = L.valid & (L.i == 0);
+
+  Uav u = io.load_uav();
+  float2 act = io.load_action();
+  int steps_new = 0;
+  if (leader) steps_new = io.load_steps() + 1;  // multi_uav_world_2d.py:238
+  io.loads_done();
+  act = map_action(act, a.io.action_mode, c);
+
+  const bool parked = (u.flags & UAVCA_FLAG_PARKED) != 0u;
+  const float ox = u.px, oy = u.py;  // position before this step
+
+  // ---- UAVAgent.step (uav_agent.py:23-36); parked UAVs do not move and report (0, 0)
+  float dist, prev_d;
+  Own w;
+  if (__any_sync(kFull, parked)) {  // warp-uniform: most warps hold no parked UAV and skip the selects
+    double vx = u.vx, vy = u.vy;
+    float px = u.px, py = u.py;
+    integrate((double)act.x, (double)act.y, vx, vy, px, py, c);
+    if (!parked) { u.vx = vx; u.vy = vy; u.px = px; u.py = py; }
+    w = own_features(c, u);  // heading, heading error to the target, distance, |v|^2 (multi_uav_world_2d.py:184-186)
+    dist = parked ? 0.f : w.dist;
+    prev_d = parked ? 0.f : u.prev;
+  } else {
+    integrate((double)act.x, (double)act.y, u.vx, u.vy, u.px, u.py, c);
+    w = own_features(c, u);
+    dist = w.dist;
+    prev_d = u.prev;
+  }
+  publish(ws, L, u.px, u.py, ox, oy, w.th_u);
+
+  // ---- reward shaping (:188-195).  Output only: float32 arithmetic, well inside the 1e-5 tolerance.
+  float r;
+  {
+    const float inv_init = rcp_approx(u.init);
+    const float m = fminf(c.vm2_f * inv_init, 1.0f);  // min(vm2/init, 1)
+    r = fmaf(50.0f * c.inv_vm2_f, __fsub_rn(prev_d, dist), -0.01f * m);
+    const float q = dist * inv_init * (1.0f / 1.5f);
+    r *= (r > 0.0f) ? (1.0f - q) : (1.0f + q);
+    r = fmaf(-0.01f * 3.14159274101257324f, fabsf(w.dth_u), r);
+  }
+
+  // ---- both pairwise passes in one sweep over the env's UAVs
+  float smin;
+  Top2 t;
+  pair_scan<NT>(ws, L, u.px, u.py, smin, t);
+
+  // ---- collisions (:199-210), decided in squared-distance space
+  const bool in_range = smin < c.s_dsense_lt;
+  const bool collision = in_range & (smin <= c.s_two_r_le);
+  r = collision ? -2.0f : r;
+  const bool hard = in_range & (smin <= c.s_two_h_le) & !parked & ((u.flags & UAVCA_FLAG_COLLIDED) == 0u);
+  if (hard) u.flags |= UAVCA_FLAG_COLLIDED;
+
+  // ---- done logic (:213-227)
+  const bool slow = w.vsq < c.reach_speed_sq;
+  const bool inside = (u.px >= c.lox_f) & (u.px <= c.hix_f) & (u.py >= c.loy_f) & (u.py <= c.hiy_f);
+  const bool reached = (dist < c.reach_dist) & !collision & slow;
+  const bool newly_reached = reached & !parked;
+  bool done = reached | (!inside & (a.io.evaluate == 0));
+  double vsq_obs = w.vsq;
+  if (reached) {  // UAVAgent.finish (uav_agent.py:38-42)
+    u.flags |= UAVCA_FLAG_PARKED;
+    const double nv = sqrt(w.vsq);
+    double fx = __dmul_rn(__ddiv_rn(u.vx, nv), 0.001), fy = __dmul_rn(__ddiv_rn(u.vy, nv), 0.001);
+    if ((fx != fx) | (fy != fy)) { fx = 0.0; fy = 0.0; }
+    u.vx = fx; u.vy = fy;
+    r += 10.0f;
+    vsq_obs = sq64(u.vx, u.vy);
+  }
+  u.prev = dist;  // :229
+  if (!L.valid) done = false;
+
+  // ---- per-env bookkeeping: counters, reset decision
+  const unsigned done_env = (__ballot_sync(kFull, done) >> L.base) & L.envmask;
+  const unsigned ev_reach = __ballot_sync(kFull, newly_reached & L.valid);
+  const unsigned ev_coll = __ballot_sync(kFull, hard & L.valid);
+  steps_new = __shfl_sync(kFull, steps_new, L.base);
+  bool rs = false;
+  if (c.reset_mode & UAVCA_RESET_ON_DONE0) rs |= (done_env & 1u) != 0u;
+  if (c.reset_mode & UAVCA_RESET_ON_ALL_DONE) rs |= done_env == L.envmask;
+  if (c.reset_mode & UAVCA_RESET_ON_ANY_DONE) rs |= done_env != 0u;
+  if (c.max_steps > 0) rs |= steps_new >= c.max_steps;
+  rs &= L.valid;
+
+  io.store_reward_done(r, done);
+  if (leader && a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
+
+  // ---- observation (:233-235): every UAV at its new position
+  float o[10];
+  obs_multi(c, ws, L, u.px, u.py, w.th_u, w.dth_u, w.dist, vsq_obs, t, o);
+
+  const bool any_event = (ev_reach | ev_coll) != 0u;  // warp-uniform
+  if (!__any_sync(kFull, rs)) {
+    if (leader) io.store_steps(steps_new);
+    if (any_event && leader) {
+      const int reach_inc = __popc((ev_reach >> L.base) & L.envmask), coll_inc = __popc((ev_coll >> L.base) & L.envmask);
+      if (reach_inc) a.s.reach[L.env] += reach_inc;  // :221
+      if (coll_inc) a.s.coll[L.env] += coll_inc;     // :209
+    }
+    io.store_obs(o);
+    if (io.wants_final()) io.store_final(o);
+    io.store_state(u);
+    return;
+  }
+
+  // ---- at least one env of this warp starts a new episode in place (rare)
+  if (io.wants_final()) io.store_final(o);
+  const int reach_inc = __popc((ev_reach >> L.base) & L.envmask), coll_inc = __popc((ev_coll >> L.base) & L.envmask);
+  unsigned episode = 0;
+  if (leader) episode = a.s.episode[L.env];
+  episode = __shfl_sync(kFull, episode, L.base);
+  if (leader) {
+    if (rs) {
+      if (episode > 0u) {  // fold the finished episode into the running totals
+        atomicAdd(a.s.stats + 0, 1ull);
+        atomicAdd(a.s.stats + 1, (unsigned long long)(a.s.reach[L.env] + reach_inc));
+        atomicAdd(a.s.stats + 2, (unsigned long long)(a.s.coll[L.env] + coll_inc));
+        atomicAdd(a.s.stats + 3, (unsigned long long)steps_new);
+      }
+      io.store_steps(0);
+      a.s.reach[L.env] = 0; a.s.coll[L.env] = 0;  // :166-168
+      a.s.episode[L.env] = episode + 1u;
+    } else {
+      io.store_steps(steps_new);
+      if (reach_inc) a.s.reach[L.env] += reach_inc;
+      if (coll_inc) a.s.coll[L.env] += coll_inc;
+    }
+  }
+  Uav nu = u;
+  reset_multi(a, L, rs, episode, nu);
+  float no[10];
+  observe_state<NT>(c, ws, L, nu, no);
+  if (rs) {
+    u = nu;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) o[k] = no[k];
+  }
+  io.store_obs(o);
+  io.store_state(u);
+  if (rs) io.store_target(u);
+}
+
 }  // namespace uavca
