@@ -87,7 +87,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("UAVCA_LIB", LIB_PATH)  # override: kernel-variant experiments only
+    path = os.environ.get("UAVCA_LIB") or LIB_PATH  # override: kernel-variant experiments only
     if not os.path.exists(path):
         raise UavcaError(
             f"{path} is missing: build the CUDA extension first (python -m gym_uav_collision_avoidance_b200.build "

@@ -113,6 +113,12 @@ Consts derive_consts(const uavca_config& g) {
   c.s_two_r_le = le_sq(c.two_r);
   c.s_two_h_le = le_sq(c.two_h);
   c.s_dsense_lt = lt_sq(c.dsense);
+  {
+    const float below_sense = std::nextafter(c.s_dsense_lt, -INFINITY);  // greatest s with sqrtf(s) < d_sense
+    c.s_coll_le = std::fmin(c.s_two_r_le, below_sense);
+    c.s_hard_le = std::fmin(c.s_two_h_le, below_sense);
+  }
+  c.s_reach_lt = lt_sq(c.reach_dist);
   c.lox_f = ceil_f(c.lox); c.hix_f = floor_f(c.hix);
   c.loy_f = ceil_f(c.loy); c.hiy_f = floor_f(c.hiy);
   c.vm2_floor_f = floor_f(c.vm2);
@@ -128,6 +134,9 @@ Consts derive_consts(const uavca_config& g) {
   c.tau_f = (float)g.tau;
   c.reset_mode = g.reset_mode;
   c.max_steps = g.max_episode_steps;
+  c.rs_any_mask = (g.reset_mode & UAVCA_RESET_ON_ANY_DONE) ? 0xffffffffu : ((g.reset_mode & UAVCA_RESET_ON_DONE0) ? 1u : 0u);
+  c.rs_all_off = (g.reset_mode & UAVCA_RESET_ON_ALL_DONE) ? 0u : 1u;
+  c.steps_limit = g.max_episode_steps > 0 ? g.max_episode_steps : 0x7fffffff;
   c.reset_source = g.reset_source;
   c.circular = g.circular;
   c.single_f32_first_step = g.single_f32_first_step;
@@ -149,7 +158,7 @@ struct uavca_handle {
   uavca_layout pool_layout{};
   float4* ring = nullptr;  // circular-reset table (owned)
   long long launches = 0;
-  int path = UAVCA_PATH_AUTO;  // UAVCA_STEP_PATH=lanes in the environment forces the per-lane kernel (A/B measurements)
+  int path = UAVCA_PATH_LANES;  // UAVCA_STEP_PATH=tma in the environment selects the bulk (TMA) kernel for whole tiles (A/B measurements)
   // end-to-end (host buffer) path, created lazily
   static constexpr int kHostStreams = 3;
   cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
@@ -247,7 +256,7 @@ int uavca_create(const uavca_config* cfg, int device, uavca_handle** out) {
   h->consts = derive_consts(*cfg);
   h->device = device;
   compute_layout(cfg->num_envs, cfg->num_agents, &h->layout);
-  if (const char* p = std::getenv("UAVCA_STEP_PATH")) h->path = std::strcmp(p, "lanes") == 0 ? UAVCA_PATH_LANES : UAVCA_PATH_AUTO;
+  if (const char* p = std::getenv("UAVCA_STEP_PATH")) h->path = std::strcmp(p, "tma") == 0 ? UAVCA_PATH_AUTO : UAVCA_PATH_LANES;
   if (cfg->kind == UAVCA_KIND_MULTI && cfg->circular) {
     // multi_uav_world_2d.py:157-163, computed with the host libm and rounded to the float32 state
     DeviceGuard g(device);

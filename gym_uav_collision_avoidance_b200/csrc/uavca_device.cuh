@@ -41,6 +41,9 @@ struct Consts {
   // the same thresholds in squared-distance space (sqrt is monotone, so the flags stay bit-exact without a sqrt):
   //   d <= 2r  <=>  s <= s_two_r_le ;  d <= 2h  <=>  s <= s_two_h_le ;  d < d_sense  <=>  s < s_dsense_lt
   float s_two_r_le, s_two_h_le, s_dsense_lt;
+  // soft / hard collision of the nearest neighbour, sensing range folded in: d < d_sense and d <= 2r  <=>  s <= s_coll_le
+  float s_coll_le, s_hard_le;
+  float s_reach_lt;  // dist < reach_distance  <=>  s < s_reach_lt
   // box as float32 bounds with identical compare results: float64(p) >= lo  <=>  p >= lox_f, ...
   float lox_f, hix_f, loy_f, hiy_f;
   float vm2_floor_f;  // greatest float32 <= vm2: float64(init) <= vm2  <=>  init <= vm2_floor_f
@@ -49,6 +52,8 @@ struct Consts {
   float polar_scale, vmax_f, tau_f;
   // episode control
   int reset_mode, max_steps, reset_source, circular, single_f32_first_step;
+  unsigned rs_any_mask, rs_all_off;  // reset_mode as masks over an env's done bits (step_core)
+  int steps_limit;                   // max_steps, or INT_MAX when there is no limit
   unsigned seed_lo, seed_hi;
   long long env_base;
 };
@@ -199,10 +204,39 @@ __device__ __forceinline__ float2 wrap_units2(float2 d) {
   return __ffma2_rn(k, make_float2(-2.0f, -2.0f), d);
 }
 
+// Output-only square root / reciprocal (observation features, reward): flush-to-zero MUFU forms, no denormal fix-up.
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// sin and cos of |x| <= ~1e4 (here |x| <= pi): Cody-Waite reduction by pi/2 in three FMA steps and the usual
+// minimax polynomials on [-pi/4, pi/4]; ~1.5 ulp.  Unlike sincosf() there is no huge-argument path, hence no
+// local-memory frame in the kernels that inline it.
+__device__ __forceinline__ void sincos_bounded(float x, float& sn, float& cs) {
+  const float k = rintf(x * 0.636619747f);
+  float r = fmaf(k, -1.57079601e+00f, x);
+  r = fmaf(k, -3.13916473e-07f, r);
+  r = fmaf(k, -5.39030253e-15f, r);
+  const int q = (int)k;
+  const float s = r * r;
+  float ps = fmaf(-1.95152959e-4f, s, 8.33307933e-3f);
+  ps = fmaf(ps, s, -1.66666597e-1f);
+  ps = fmaf(ps * s, r, r);
+  float pc = fmaf(2.44331571e-5f, s, -1.38873036e-3f);
+  pc = fmaf(pc, s, 4.16666418e-2f);
+  pc = fmaf(pc, s, -0.5f);
+  pc = fmaf(pc, s, 1.0f);
+  const bool swap = (q & 1) != 0;
+  float a = swap ? pc : ps, b = swap ? ps : pc;
+  sn = (q & 2) ? -a : a;
+  cs = ((q + 1) & 2) ? -b : b;
 }
 
 // wrap(atan2(dy,dx) - atan2(hy,hx)) as ONE atan2 of the float64 cross/dot products of the two directions
@@ -215,11 +249,10 @@ __device__ __forceinline__ float rel_angle(double dx, double dy, double hx, doub
 
 // libm-grade fallback for the rare degenerate inputs (velocity components below ~1e-30 but not both zero, or a
 // UAV sitting exactly on its target): same formulas as the reference, in double.
-static __device__ __noinline__ void angles_slow(double tdx, double tdy, double vx, double vy, float& th_u, float& dth_u) {
+static __device__ __noinline__ float2 angles_slow(double tdx, double tdy, double vx, double vy) {
   const double th = atan2(vy, vx);
   const double d = atan2(tdy, tdx) - th;
-  th_u = (float)(th * 0.3183098861837907);
-  dth_u = (float)(atan2(sin(d), cos(d)) * 0.3183098861837907);
+  return make_float2((float)(th * 0.3183098861837907), (float)(atan2(sin(d), cos(d)) * 0.3183098861837907));
 }
 
 // Caller-side action mapping (test_sac_multi.py:77-80; test_pytorch_multi.py:80).
@@ -228,7 +261,7 @@ __device__ __forceinline__ float2 map_action(float2 a, int mode, const Consts& c
     float v = __fmul_rn(__fadd_rn(__fmul_rn(a.x, 0.5f), 0.5f), c.polar_scale);
     float th = __fmul_rn(a.y, 3.14159274101257324f);
     float sn, cs;
-    sincosf(th, &sn, &cs);
+    sincos_bounded(th, sn, cs);
     return make_float2(__fmul_rn(v, cs), __fmul_rn(v, sn));
   }
   if (mode == UAVCA_ACTION_SCALED) return make_float2(__fmul_rn(a.x, c.vmax_f), __fmul_rn(a.y, c.vmax_f));

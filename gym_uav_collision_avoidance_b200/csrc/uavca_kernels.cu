@@ -27,7 +27,7 @@ struct GlobalIO {
   __device__ __forceinline__ float2 load_action() const {
     return L.valid ? ld_stream(a.io.action + L.m) : make_float2(0.f, 0.f);
   }
-  __device__ __forceinline__ int load_steps() const { return ld_stream(a.s.steps + L.env); }
+  __device__ __forceinline__ int load_steps() const { return L.valid ? a.s.steps[L.env] : 0; }
   // Programmatic dependent launch: every input is in registers, the next kernel of the stream may start launching
   __device__ __forceinline__ void loads_done() const { cudaTriggerProgrammaticLaunchCompletion(); }
   __device__ __forceinline__ void store_reward_done(float r, bool done) const {
@@ -37,8 +37,15 @@ struct GlobalIO {
     }
   }
   __device__ __forceinline__ bool wants_final() const { return a.io.final_obs != nullptr; }
-  __device__ __forceinline__ void store_obs(const float o[10]) const { store_obs_rows(stage, a.io.obs, L, o); }
-  __device__ __forceinline__ void store_final(const float o[10]) const { store_obs_rows(stage, a.io.final_obs, L, o); }
+  __device__ __forceinline__ void put_own(float2 o01, float2 o23) const { stage_own(stage, L.lane, o01, o23); }
+  __device__ __forceinline__ void put_neighbours(const ObsTail& n) const { stage_neighbours(stage, L.lane, n); }
+  __device__ __forceinline__ void commit(float* g) const {
+    __syncwarp();
+    flush_rows(stage, g, L);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void commit_obs() const { commit(a.io.obs); }
+  __device__ __forceinline__ void commit_final() const { commit(a.io.final_obs); }
   __device__ __forceinline__ void store_state(const Uav& u) const { store_uav(a.s, L, u, false); }
   __device__ __forceinline__ void store_target(const Uav& u) const {
     st_stream(a.s.tgt + L.m, make_float2(u.tx, u.ty));
@@ -51,12 +58,21 @@ template <int NT>
 __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
   const WarpScratch ws = warp_scratch(smem);
-  const Lane L = make_lane<NT>(a.B, a.N);
+  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int N = NT > 0 ? NT : a.N;
+  const bool full = uavs_left(a.B, N, warp_global) >= (32 / N) * N;  // warp-uniform
   // Programmatic dependent launch: this grid may have been scheduled while the previous kernel of the stream was
   // still draining; everything above overlapped with it, nothing below may (it reads memory that kernel wrote).
   cudaGridDependencySynchronize();
-  GlobalIO io{a, L, ws.stage};
-  step_core<NT>(a, ws, L, io);
+  if (full) {  // all warps but the last of a shard: no validity predicates
+    const Lane L = make_lane<NT, true>(a.B, a.N, warp_global);
+    GlobalIO io{a, L, ws.stage};
+    step_core<NT>(a, ws, L, io);
+  } else {
+    const Lane L = make_lane<NT, false>(a.B, a.N, warp_global);
+    GlobalIO io{a, L, ws.stage};
+    step_core<NT>(a, ws, L, io);
+  }
 }
 
 template <int NT>

@@ -25,26 +25,38 @@ struct Lane {
   bool valid;
 };
 
-template <int NT>
-__device__ __forceinline__ Lane make_lane(int B, int Nrt) {
+// UAVs from warp `warp_global`'s first env to the end of the shard (>= lanes_used: the warp is full)
+__device__ __forceinline__ int uavs_left(int B, int N, int warp_global) { return (B - warp_global * (32 / N)) * N; }
+
+// FULL: the caller knows that every env slot of this warp maps to a real env (all warps but the last of a shard);
+// the validity predicates then fold to compile-time constants.
+template <int NT, bool FULL = false>
+__device__ __forceinline__ Lane make_lane(int B, int Nrt, int warp_global) {
   Lane L;
   L.N = NT > 0 ? NT : Nrt;
   const int epw = 32 / L.N;
   L.lanes_used = epw * L.N;
   L.lane = threadIdx.x & 31;
-  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int e_local = L.lane / L.N;
   L.i = L.lane - e_local * L.N;
   L.base = e_local * L.N;
   L.envmask = L.N >= 32 ? 0xffffffffu : ((1u << L.N) - 1u);
   L.env = warp_global * epw + e_local;
   L.warp_m0 = warp_global * L.lanes_used;
-  const int left = (B - warp_global * epw) * L.N;  // UAVs from this warp's first env to the end of the shard
-  L.valid_lanes = left <= 0 ? 0 : (left < L.lanes_used ? left : L.lanes_used);
+  if (FULL) {
+    L.valid_lanes = L.lanes_used;
+  } else {
+    const int left = uavs_left(B, L.N, warp_global);
+    L.valid_lanes = left <= 0 ? 0 : (left < L.lanes_used ? left : L.lanes_used);
+  }
   L.valid = L.lane < L.valid_lanes;
   L.m = L.warp_m0 + L.lane;
   if (!L.valid) { L.base = 0; L.i = 0; }  // idle lanes shadow UAV 0 of the warp's first env and never store
   return L;
+}
+template <int NT>
+__device__ __forceinline__ Lane make_lane(int B, int Nrt) {
+  return make_lane<NT, false>(B, Nrt, blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5));
 }
 
 struct Uav {
@@ -153,18 +165,13 @@ __device__ __forceinline__ void pair_scan(const WarpScratch& ws, const Lane& L, 
   }
 }
 
-// MultiUAVWorld2D._get_obs (multi_uav_world_2d.py:60-109) for this lane's UAV.
-//   th_u    own heading atan2(v.y, v.x) / pi                                   (:63-64)
-//   dth_u   wrap(bearing to target - heading) / pi                             (:69-72)
-//   dist    float32 distance to the target                                      (:67)
-//   vsq     |v|^2 in float64
+// MultiUAVWorld2D._get_obs (multi_uav_world_2d.py:60-109) for this lane's UAV, neighbour half: features 4..9.
 // Neighbour bearings/headings are differences of float32 angles (absolute error ~2e-7 of a half-turn).
-__device__ __forceinline__ void obs_multi(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
-                                          float th_u, float dth_u, float dist, double vsq, const Top2& t, float o[10]) {
-  o[0] = sqrt_approx((float)vsq) * c.inv_vm2_f;  // :62
-  o[1] = th_u;
-  o[2] = dist * c.inv_diag;                      // :67-68
-  o[3] = dth_u;
+struct ObsTail {
+  float2 a, b, c;  // (o4, o5) (o6, o7) (o8, o9)
+};
+__device__ __forceinline__ ObsTail obs_neighbours(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
+                                                  float th_u, const Top2& t) {
   const bool have1 = t.s1 < c.s_dsense_lt;       // uav_agent.py:52 strict <  (s = +inf when there is no other UAV)
   const bool have2 = have1 & (t.s2 < c.s_dsense_lt);
   const int slot = 2 * L.base + L.i;
@@ -174,57 +181,85 @@ __device__ __forceinline__ void obs_multi(const Consts& c, const WarpScratch& ws
   const float2 nth = make_float2(-th_u, -th_u);
   const float2 w1 = wrap_units2(__ffma2_rn(b, make_float2(c.inv_pi, c.inv_pi), nth));  // bearings relative to the heading
   const float2 w2 = wrap_units2(__fadd2_rn(make_float2(h1, h2), nth));                 // neighbour headings, relative
-  o[4] = have1 ? sqrt_approx(t.s1) * c.inv_dsense : 1.0f;  // :77
-  o[5] = have1 ? w1.x : 1.0f;                              // :78-81 (no neighbour: bearing pi)
-  o[6] = have1 ? w2.x : 0.0f;                              // :82-85
-  o[7] = have2 ? sqrt_approx(t.s2) * c.inv_dsense : 1.0f;  // :87
-  o[8] = have2 ? w1.y : 1.0f;                              // :88-91
-  o[9] = have2 ? w2.y : 0.0f;                              // :92-95
+  ObsTail o;
+  o.a.x = have1 ? sqrt_approx(t.s1) * c.inv_dsense : 1.0f;  // :77
+  o.a.y = have1 ? w1.x : 1.0f;                              // :78-81 (no neighbour: bearing pi)
+  o.b.x = have1 ? w2.x : 0.0f;                              // :82-85
+  o.b.y = have2 ? sqrt_approx(t.s2) * c.inv_dsense : 1.0f;  // :87
+  o.c.x = have2 ? w1.y : 1.0f;                              // :88-91
+  o.c.y = have2 ? w2.y : 0.0f;                              // :92-95
+  return o;
 }
 
-// Everything the observation needs from a UAV's own state.
+// Everything the step and the observation need from a UAV's own state.
+//   th_u    own heading atan2(v.y, v.x) / pi                                   (multi_uav_world_2d.py:63-64)
+//   dth_u   wrap(bearing to target - heading) / pi                             (:69-72, :184-186)
+//   dist    float32 distance to the target, ssq its square                      (:67)
+//   vsq     |v|^2 in float64
+// The heading error is ONE atan2 of the cross / dot products of heading and target direction, formed in float32
+// from exactly representable differences: absolute error ~1e-7 rad, relative accuracy kept down to small angles.
 struct Own {
-  float th_u, dth_u, dist;
+  float th_u, dth_u, dist, ssq;
   double vsq;
 };
-__device__ __forceinline__ Own own_features(const Consts& c, const Uav& u) {
+__device__ __forceinline__ Own own_features(const Consts& c, float px, float py, float tx, float ty, double vx, double vy) {
   Own w;
-  const float tdx = __fsub_rn(u.tx, u.px), tdy = __fsub_rn(u.ty, u.py);
-  w.dist = n32(tdx, tdy);
-  w.vsq = sq64(u.vx, u.vy);
-  const float fvx = (float)u.vx, fvy = (float)u.vy;
-  const bool vzero = (u.vx == 0.0) & (u.vy == 0.0);  // atan2(0, 0) = 0: a zero heading points along +x
-  const double cr = fma(u.vx, (double)tdy, -(u.vy * (double)tdx));
-  const double dt = fma(u.vx, (double)tdx, u.vy * (double)tdy);
-  const float2 ang = fast_atan2_pair(fvy, fvx, vzero ? tdy : (float)cr, vzero ? tdx : (float)dt);
+  const float tdx = __fsub_rn(tx, px), tdy = __fsub_rn(ty, py);
+  w.ssq = sq32(tdx, tdy);
+  w.dist = __fsqrt_rn(w.ssq);
+  w.vsq = sq64(vx, vy);
+  const float fvx = (float)vx, fvy = (float)vy;
+  // a velocity of exactly zero is common (the clipped acceleration walks v on a lattice of multiples of amax*tau
+  // that contains 0, and every UAV starts at rest): atan2(0, 0) = 0, i.e. the heading points along +x
+  const bool vzero = (vx == 0.0) & (vy == 0.0);
+  const float hx = vzero ? 1.0f : fvx;
+  const float cr = fmaf(hx, tdy, -(fvy * tdx));
+  const float dt = fmaf(hx, tdx, fvy * tdy);
+  const float2 ang = fast_atan2_pair(fvy, fvx, cr, dt);
   w.th_u = ang.x * c.inv_pi;
   w.dth_u = ang.y * c.inv_pi;
-  // degenerate inputs (never produced by ordinary flight): denormal-tiny velocity or a UAV exactly on its target
-  const bool odd = (!vzero & (fabsf(fvx) + fabsf(fvy) < 1e-30f)) | ((tdx == 0.0f) & (tdy == 0.0f));
-  if (odd) angles_slow((double)tdx, (double)tdy, u.vx, u.vy, w.th_u, w.dth_u);
+  // never seen in ordinary flight: a denormal-tiny non-zero velocity, or a UAV exactly on its target ->
+  // the reference's own formulas in double
+  if ((!vzero & (fabsf(fvx) + fabsf(fvy) < 1e-30f)) | (w.ssq == 0.0f)) {
+    const float2 s = angles_slow((double)tdx, (double)tdy, vx, vy);
+    w.th_u = s.x; w.dth_u = s.y;
+  }
   return w;
+}
+
+__device__ __forceinline__ void obs_own(const Consts& c, const Own& w, double vsq, float2& o01, float2& o23) {
+  o01 = make_float2(sqrt_approx((float)vsq) * c.inv_vm2_f, w.th_u);  // :62-64
+  o23 = make_float2(w.dist * c.inv_diag, w.dth_u);                   // :67-72
 }
 
 // Observation of a state at rest (reset / observe kernels): publish, scan, build.  All lanes must call.
 template <int NT>
 __device__ __forceinline__ void observe_state(const Consts& c, const WarpScratch& ws, const Lane& L, const Uav& u, float o[10]) {
-  const Own w = own_features(c, u);
+  const Own w = own_features(c, u.px, u.py, u.tx, u.ty, u.vx, u.vy);
   __syncwarp();
   publish(ws, L, u.px, u.py, u.px, u.py, w.th_u);
   float smin;
   Top2 t;
   pair_scan<NT>(ws, L, u.px, u.py, smin, t);
-  obs_multi(c, ws, L, u.px, u.py, w.th_u, w.dth_u, w.dist, w.vsq, t, o);
+  float2 o01, o23;
+  obs_own(c, w, w.vsq, o01, o23);
+  const ObsTail n = obs_neighbours(c, ws, L, u.px, u.py, w.th_u, t);
+  o[0] = o01.x; o[1] = o01.y; o[2] = o23.x; o[3] = o23.y;
+  o[4] = n.a.x; o[5] = n.a.y; o[6] = n.b.x; o[7] = n.b.y; o[8] = n.c.x; o[9] = n.c.y;
 }
 
-// Write the warp's observation rows as one contiguous run of 16-byte stores (staged through shared memory;
-// a per-thread row is 40 bytes, which would otherwise scatter 8-byte stores 40 bytes apart).
-__device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const Lane& L, const float o[10]) {
-  __syncwarp();
-  float2* st2 = reinterpret_cast<float2*>(stage) + L.lane * 5;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) st2[k] = make_float2(o[2 * k], o[2 * k + 1]);
-  __syncwarp();
+// The warp's observation rows go out as one contiguous run of 16-byte stores, staged through shared memory (a
+// per-thread row is 40 bytes, which would otherwise scatter 8-byte stores 40 bytes apart).
+__device__ __forceinline__ void stage_own(float* stage, int lane, float2 o01, float2 o23) {
+  float2* row = reinterpret_cast<float2*>(stage) + lane * 5;
+  row[0] = o01; row[1] = o23;
+}
+__device__ __forceinline__ void stage_neighbours(float* stage, int lane, const ObsTail& n) {
+  float2* row = reinterpret_cast<float2*>(stage) + lane * 5;
+  row[2] = n.a; row[3] = n.b; row[4] = n.c;
+}
+// all lanes; the caller has __syncwarp()ed after the last stage_* call
+__device__ __forceinline__ void flush_rows(const float* stage, float* gobs, const Lane& L) {
   float* g = gobs + (size_t)L.warp_m0 * 10;
   const int n2 = L.valid_lanes * 5;  // float2 elements to write
   if ((L.lanes_used & 1) == 0) {     // every warp's run starts on a 16-byte boundary
@@ -246,6 +281,14 @@ __device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const 
       if (k < n2) st_stream(g2 + k, s2[k]);
     }
   }
+}
+__device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const Lane& L, const float o[10]) {
+  __syncwarp();
+  float2* st2 = reinterpret_cast<float2*>(stage) + L.lane * 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) st2[k] = make_float2(o[2 * k], o[2 * k + 1]);
+  __syncwarp();
+  flush_rows(stage, gobs, L);
 }
 
 // Start a new episode for the envs of this warp whose lanes pass do_reset (env-uniform).  Restates
@@ -334,57 +377,52 @@ __device__ __forceinline__ void reset_multi(const KernelArgs& a, const Lane& L, 
 // ================================================================================================================
 // The step itself, independent of where the state and the I/O live.  `IO` is a policy that moves one UAV's data:
 //   GlobalIO (uavca_kernels.cu)  per-lane streaming global loads/stores           (ragged tails, any N, any alignment)
-//   SmemIO   (uavca_tma.cuh)     shared-memory stage filled / drained by TMA bulk copies (the bulk of every batch)
+//   SmemIO   (uavca_tma.cuh)     shared-memory stage filled / drained by TMA bulk copies
 // Both run exactly this code, so they cannot disagree on semantics.
 //
-//   Uav   load_uav();  float2 load_action();  int load_steps();        (load_steps: env leader lanes only)
+//   Uav   load_uav();  float2 load_action();  int load_steps();        (load_steps: every lane, its env's counter)
 //   void  loads_done();                                                (every input of this warp is in registers)
 //   void  store_reward_done(float r, bool done);
-//   void  store_obs(const float o[10]);   void store_final(const float o[10]);
+//   void  put_own(float2 o01, float2 o23);  void put_neighbours(const ObsTail&);     observation row of this lane
+//   void  commit_obs();  void commit_final();                          (all lanes; rows -> obs / final_obs)
 //   void  store_state(const Uav&);        pos, vel, prev, flags
 //   void  store_target(const Uav&);       tgt, init (reset lanes only)
 //   void  store_steps(int);               (env leader lanes only)
 //   bool  wants_final();
 // ================================================================================================================
 
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
+// UAVAgent.finish (uav_agent.py:38-42): park at 1 mm/s along the current heading (NaN -> 0 for a zero velocity)
+static __device__ __noinline__ double2 finish_velocity(double vx, double vy, double vsq) {
+  const double nv = sqrt(vsq);
+  double fx = __dmul_rn(__ddiv_rn(vx, nv), 0.001), fy = __dmul_rn(__ddiv_rn(vy, nv), 0.001);
+  if ((fx != fx) | (fy != fy)) { fx = 0.0; fy = 0.0; }
+  return make_double2(fx, fy);
 }
 
 template <int NT, class IO>
 __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch& ws, const Lane& L, IO& io) {
   const Consts& c = a.c;
-  const bool leader = L.valid & (L.i == 0);
 
   Uav u = io.load_uav();
   float2 act = io.load_action();
-  int steps_new = 0;
-  if (leader) steps_new = io.load_steps() + 1;  // multi_uav_world_2d.py:238
+  const int steps_new = io.load_steps() + 1;  // multi_uav_world_2d.py:238
   io.loads_done();
-  act = map_action(act, a.io.action_mode, c);
+  if (a.io.action_mode != UAVCA_ACTION_CARTESIAN) act = map_action(act, a.io.action_mode, c);
 
   const bool parked = (u.flags & UAVCA_FLAG_PARKED) != 0u;
   const float ox = u.px, oy = u.py;  // position before this step
 
   // ---- UAVAgent.step (uav_agent.py:23-36); parked UAVs do not move and report (0, 0)
-  float dist, prev_d;
-  Own w;
-  if (__any_sync(kFull, parked)) {  // warp-uniform: most warps hold no parked UAV and skip the selects
+  {
     double vx = u.vx, vy = u.vy;
     float px = u.px, py = u.py;
     integrate((double)act.x, (double)act.y, vx, vy, px, py, c);
     if (!parked) { u.vx = vx; u.vy = vy; u.px = px; u.py = py; }
-    w = own_features(c, u);  // heading, heading error to the target, distance, |v|^2 (multi_uav_world_2d.py:184-186)
-    dist = parked ? 0.f : w.dist;
-    prev_d = parked ? 0.f : u.prev;
-  } else {
-    integrate((double)act.x, (double)act.y, u.vx, u.vy, u.px, u.py, c);
-    w = own_features(c, u);
-    dist = w.dist;
-    prev_d = u.prev;
   }
+  // heading, heading error to the target, distance, |v|^2 (multi_uav_world_2d.py:184-186)
+  const Own w = own_features(c, u.px, u.py, u.tx, u.ty, u.vx, u.vy);
+  const float dist = parked ? 0.f : w.dist;
+  const float prev_d = parked ? 0.f : u.prev;
   publish(ws, L, u.px, u.py, ox, oy, w.th_u);
 
   // ---- reward shaping (:188-195).  Output only: float32 arithmetic, well inside the 1e-5 tolerance.
@@ -403,68 +441,67 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
   Top2 t;
   pair_scan<NT>(ws, L, u.px, u.py, smin, t);
 
-  // ---- collisions (:199-210), decided in squared-distance space
-  const bool in_range = smin < c.s_dsense_lt;
-  const bool collision = in_range & (smin <= c.s_two_r_le);
+  // ---- collisions (:199-210), decided in squared-distance space (the thresholds already include "in sensing range")
+  const bool collision = smin <= c.s_coll_le;
   r = collision ? -2.0f : r;
-  const bool hard = in_range & (smin <= c.s_two_h_le) & !parked & ((u.flags & UAVCA_FLAG_COLLIDED) == 0u);
+  const bool hard = (smin <= c.s_hard_le) & ((u.flags & (UAVCA_FLAG_PARKED | UAVCA_FLAG_COLLIDED)) == 0u) & L.valid;
   if (hard) u.flags |= UAVCA_FLAG_COLLIDED;
 
   // ---- done logic (:213-227)
-  const bool slow = w.vsq < c.reach_speed_sq;
   const bool inside = (u.px >= c.lox_f) & (u.px <= c.hix_f) & (u.py >= c.loy_f) & (u.py <= c.hiy_f);
-  const bool reached = (dist < c.reach_dist) & !collision & slow;
-  const bool newly_reached = reached & !parked;
-  bool done = reached | (!inside & (a.io.evaluate == 0));
+  const bool reached = (parked ? true : (w.ssq < c.s_reach_lt)) & !collision & (w.vsq < c.reach_speed_sq);
+  const bool newly_reached = reached & !parked & L.valid;
+  const bool done = (reached | (!inside & (a.io.evaluate == 0))) & L.valid;
   double vsq_obs = w.vsq;
-  if (reached) {  // UAVAgent.finish (uav_agent.py:38-42)
+  if (reached) {
     u.flags |= UAVCA_FLAG_PARKED;
-    const double nv = sqrt(w.vsq);
-    double fx = __dmul_rn(__ddiv_rn(u.vx, nv), 0.001), fy = __dmul_rn(__ddiv_rn(u.vy, nv), 0.001);
-    if ((fx != fx) | (fy != fy)) { fx = 0.0; fy = 0.0; }
-    u.vx = fx; u.vy = fy;
+    const double2 fv = finish_velocity(u.vx, u.vy, w.vsq);
+    u.vx = fv.x; u.vy = fv.y;
     r += 10.0f;
     vsq_obs = sq64(u.vx, u.vy);
   }
   u.prev = dist;  // :229
-  if (!L.valid) done = false;
-
-  // ---- per-env bookkeeping: counters, reset decision
-  const unsigned done_env = (__ballot_sync(kFull, done) >> L.base) & L.envmask;
-  const unsigned ev_reach = __ballot_sync(kFull, newly_reached & L.valid);
-  const unsigned ev_coll = __ballot_sync(kFull, hard & L.valid);
-  steps_new = __shfl_sync(kFull, steps_new, L.base);
-  bool rs = false;
-  if (c.reset_mode & UAVCA_RESET_ON_DONE0) rs |= (done_env & 1u) != 0u;
-  if (c.reset_mode & UAVCA_RESET_ON_ALL_DONE) rs |= done_env == L.envmask;
-  if (c.reset_mode & UAVCA_RESET_ON_ANY_DONE) rs |= done_env != 0u;
-  if (c.max_steps > 0) rs |= steps_new >= c.max_steps;
-  rs &= L.valid;
-
-  io.store_reward_done(r, done);
-  if (leader && a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
 
   // ---- observation (:233-235): every UAV at its new position
-  float o[10];
-  obs_multi(c, ws, L, u.px, u.py, w.th_u, w.dth_u, w.dist, vsq_obs, t, o);
+  {
+    float2 o01, o23;
+    obs_own(c, w, vsq_obs, o01, o23);
+    io.put_own(o01, o23);
+    io.put_neighbours(obs_neighbours(c, ws, L, u.px, u.py, w.th_u, t));
+  }
+  io.store_reward_done(r, done);
 
-  const bool any_event = (ev_reach | ev_coll) != 0u;  // warp-uniform
-  if (!__any_sync(kFull, rs)) {
+  // ---- per-env bookkeeping: reset decision, counters
+  // reset triggers as two masks derived on the host: any done flag under rs_any_mask (bit 0 for dones[0], all
+  // bits for any(dones)); every flag of the env set (rs_all_off = 0) for all(dones); the step limit (INT_MAX = none)
+  const unsigned done_env = __ballot_sync(kFull, done) >> L.base;
+  const bool rs = (((done_env & c.rs_any_mask) != 0u) | ((((done_env & L.envmask) ^ L.envmask) | c.rs_all_off) == 0u) |
+                   (steps_new >= c.steps_limit)) & L.valid;
+  const bool leader = L.valid & (L.i == 0);
+  if (leader && a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
+
+  if (!__any_sync(kFull, rs | newly_reached | hard)) {  // nothing to count, nobody resets: the common case
     if (leader) io.store_steps(steps_new);
-    if (any_event && leader) {
-      const int reach_inc = __popc((ev_reach >> L.base) & L.envmask), coll_inc = __popc((ev_coll >> L.base) & L.envmask);
-      if (reach_inc) a.s.reach[L.env] += reach_inc;  // :221
-      if (coll_inc) a.s.coll[L.env] += coll_inc;     // :209
-    }
-    io.store_obs(o);
-    if (io.wants_final()) io.store_final(o);
+    io.commit_obs();
+    if (io.wants_final()) io.commit_final();
     io.store_state(u);
     return;
   }
 
-  // ---- at least one env of this warp starts a new episode in place (rare)
-  if (io.wants_final()) io.store_final(o);
+  // ---- rare: some env of this warp counts a reach / a hard collision or starts a new episode in place
+  const unsigned ev_reach = __ballot_sync(kFull, newly_reached), ev_coll = __ballot_sync(kFull, hard);
   const int reach_inc = __popc((ev_reach >> L.base) & L.envmask), coll_inc = __popc((ev_coll >> L.base) & L.envmask);
+  if (io.wants_final()) io.commit_final();
+  if (!__any_sync(kFull, rs)) {
+    if (leader) {
+      io.store_steps(steps_new);
+      if (reach_inc) a.s.reach[L.env] += reach_inc;  // :221
+      if (coll_inc) a.s.coll[L.env] += coll_inc;     // :209
+    }
+    io.commit_obs();
+    io.store_state(u);
+    return;
+  }
   unsigned episode = 0;
   if (leader) episode = a.s.episode[L.env];
   episode = __shfl_sync(kFull, episode, L.base);
@@ -491,10 +528,10 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
   observe_state<NT>(c, ws, L, nu, no);
   if (rs) {
     u = nu;
-#pragma unroll
-    for (int k = 0; k < 10; ++k) o[k] = no[k];
+    io.put_own(make_float2(no[0], no[1]), make_float2(no[2], no[3]));
+    io.put_neighbours(ObsTail{make_float2(no[4], no[5]), make_float2(no[6], no[7]), make_float2(no[8], no[9])});
   }
-  io.store_obs(o);
+  io.commit_obs();
   io.store_state(u);
   if (rs) io.store_target(u);
 }

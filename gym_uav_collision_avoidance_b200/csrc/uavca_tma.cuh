@@ -136,17 +136,29 @@ struct SmemIO {
     }
   }
   __device__ __forceinline__ bool wants_final() const { return FINAL; }
-  __device__ __forceinline__ void store_row(int off, const float o[10]) const {
+  bool final_open = FINAL;  // rows also go to the final_obs stage until commit_final()
+  __device__ __forceinline__ void put_own(float2 o01, float2 o23) const {
     if (valid) {
-      float2* row = reinterpret_cast<float2*>(st + off + u * 40);
-#pragma unroll
-      for (int k = 0; k < 5; ++k) row[k] = make_float2(o[2 * k], o[2 * k + 1]);
+      float2* row = reinterpret_cast<float2*>(st + G::OBS + u * 40);
+      row[0] = o01; row[1] = o23;
+      if (FINAL && final_open) {
+        float2* frow = reinterpret_cast<float2*>(st + G::FOBS + u * 40);
+        frow[0] = o01; frow[1] = o23;
+      }
     }
   }
-  __device__ __forceinline__ void store_obs(const float o[10]) const { store_row(G::OBS, o); }
-  __device__ __forceinline__ void store_final(const float o[10]) const {
-    if (FINAL) store_row(G::FOBS, o);
+  __device__ __forceinline__ void put_neighbours(const ObsTail& n) const {
+    if (valid) {
+      float2* row = reinterpret_cast<float2*>(st + G::OBS + u * 40);
+      row[2] = n.a; row[3] = n.b; row[4] = n.c;
+      if (FINAL && final_open) {
+        float2* frow = reinterpret_cast<float2*>(st + G::FOBS + u * 40);
+        frow[2] = n.a; frow[3] = n.b; frow[4] = n.c;
+      }
+    }
   }
+  __device__ __forceinline__ void commit_obs() const {}
+  __device__ __forceinline__ void commit_final() { final_open = false; }
   __device__ __forceinline__ void store_state(const Uav& s) const {  // in place: the stage is drained by TMA stores
     if (valid) {
       at<float2>(G::POS)[u] = make_float2(s.px, s.py);
