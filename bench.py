@@ -221,6 +221,11 @@ def run_ours(args, wl, rank, world, local_rank):
     def one_step(k):
         envs[k % ring].step(actions[(k + k // ring) % n_act])
 
+    # The batches of the ring are independent environments: like a double-buffered env pool they are pipelined over
+    # `S` streams, so that one batch's ramp-up overlaps the previous batch's tail.  A batch always runs on the same
+    # stream (its own steps stay ordered).  S=1 (--streams 1) serialises every launch behind the previous one.
+    S = max(1, min(args.streams, ring))
+
     # warm-up (eager), then capture graphs of GRAPH_STEPS steps and of the remainder
     for k in range(W):
         one_step(k)
@@ -229,16 +234,46 @@ def run_ours(args, wl, rank, world, local_rank):
     q, rem = divmod(K, GRAPH_STEPS)
     stream = torch.cuda.Stream(device=dev)
 
-    def capture(n, k0):
+    def capture(n, k0, n_streams):
+        side = [torch.cuda.Stream(device=dev) for _ in range(n_streams - 1)]
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=stream):
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            for s_ in side:
+                s_.wait_event(fork)
             for k in range(n):
-                one_step(k0 + k)
+                lane = ((k0 + k) % ring) % n_streams
+                with torch.cuda.stream(stream if lane == 0 else side[lane - 1]):
+                    one_step(k0 + k)
+            for s_ in side:
+                join = torch.cuda.Event()
+                join.record(s_)
+                stream.wait_event(join)
         return g
 
-    g_main = capture(GRAPH_STEPS, W) if q > 0 else None
+    # the same steps once more on ONE stream (every launch waits for the previous one): reported beside the headline
+    serial_us = None
+    if S > 1 and q > 0:
+        l0 = sum(e.launch_count for e in envs)
+        g_ser = capture(GRAPH_STEPS, W, 1)
+        g_ser.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(1, min(q, 20))
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(reps):
+                g_ser.replay()
+            e1.record(stream)
+        stream.synchronize()
+        serial_us = e0.elapsed_time(e1) * 1e3 / (reps * GRAPH_STEPS)
+        del g_ser
+        launches_before += sum(e.launch_count for e in envs) - l0
+
+    g_main = capture(GRAPH_STEPS, W, S) if q > 0 else None
     launches_per_graph = sum(e.launch_count for e in envs) - launches_before
-    g_rem = capture(rem, W + GRAPH_STEPS) if rem > 0 else None
+    g_rem = capture(rem, W + GRAPH_STEPS, S) if rem > 0 else None
     launches_rem = sum(e.launch_count for e in envs) - launches_before - launches_per_graph
     if g_main is not None:
         g_main.replay()  # graph warm-up (upload)
@@ -265,12 +300,10 @@ def run_ours(args, wl, rank, world, local_rank):
         if K * 1 < 2000:  # short runs: keep sampling a little so that at least one clock sample lands
             time.sleep(0.03)
     barrier()
-    ms = ev0.elapsed_time(ev1)
+    from gym_uav_collision_avoidance_b200 import sharding
+
+    ms = sharding.max_over_ranks(ev0.elapsed_time(ev1), device=dev)  # device time, slowest rank
     gpu_launches = q * launches_per_graph + launches_rem
-    if dist is not None:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     value = world * units_per_step * K / (ms * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI call (uavca_step_host): pinned host buffers, H2D + step + D2H
@@ -291,22 +324,17 @@ def run_ours(args, wl, rank, world, local_rank):
     for k in range(e2e_steps):
         envs[k % e2e_ring].step_host(h_act[k % 2], h_obs, h_rew, h_done)
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
     e2e_value = world * units_per_step * e2e_steps / e2e_s
     gpu_launches += sum(e.launch_count for e in envs) - launches_e2e0
 
     # episode statistics: the only collective of the path (NCCL all-reduce of 4 counters, outside the timed region)
-    st = torch.zeros(4, dtype=torch.int64, device=dev)
+    local = dict.fromkeys(sharding.STAT_KEYS, 0)
     for e in envs:
         s = e.stats()
-        st += torch.tensor([s["episodes"], s["reach"], s["collisions"], s["steps"]], device=dev)
-    if dist is not None:
-        dist.all_reduce(st)
-    stats = dict(zip(("episodes", "reach", "collisions", "steps"), st.tolist()))
+        for k in sharding.STAT_KEYS:
+            local[k] += s[k]
+    stats = sharding.reduce_stats(local, device=dev)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -333,14 +361,17 @@ def run_ours(args, wl, rank, world, local_rank):
             "config": {"workload": wl["desc"], "envs_per_gpu": B, "uavs_per_env": N, "env_steps_per_s": value / N,
                        "actions": "uniform random cartesian, resident in HBM", "auto_reset": "on-device Philox, dones[0] or 1500 steps",
                        "l2": f"ring of {ring} independent batches ({ring * per_batch / 1e6:.0f} MB > L2) so every launch streams from HBM",
-                       "timing": f"CUDA events around CUDA-graph replays ({GRAPH_STEPS} steps per graph)", "parallelism": f"env-sharded x{world}, no per-step collective"},
+                       "timing": f"CUDA events around CUDA-graph replays ({GRAPH_STEPS} steps per graph)", "parallelism": f"env-sharded x{world}, no per-step collective",
+                       "streams": S, "pipelining": (f"independent batches of the ring pipelined over {S} streams (a batch's own steps stay ordered)" if S > 1 else "none: every launch waits for the previous one"),
+                       "single_stream_us_per_step": serial_us},
             "e2e": {"value": e2e_value, "unit": "UAV env-steps/s", "h2d_bytes_per_step": units_per_step * 8,
                     "d2h_bytes_per_step": units_per_step * (D * 4 + 4 + 1), "steps": e2e_steps,
                     "path": "uavca_step_host: pinned host buffers, chunked H2D/step/D2H pipeline"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_unit": alg,
-                         "units_per_launch": units_per_step, "launch_us": launch_s * 1e6},
+                         "units_per_launch": units_per_step, "launch_us": launch_s * 1e6,
+                         "launch_us_is": "timed region / launches" + (f" ({S} independent launches in flight)" if S > 1 else "")},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
             "episode_stats": stats,
@@ -358,6 +389,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=2, help="streams the independent batches of the ring are pipelined over")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

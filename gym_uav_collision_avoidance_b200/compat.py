@@ -1,0 +1,215 @@
+"""B=1 drop-ins for the reference classes: same constructors, return types and attributes, GPU step underneath.
+
+`MultiUAVWorld2D` / `UAVWorld2D` keep the reference's gym 0.24 contract (multi_uav_world_2d.py:116,177;
+uav_world_2d.py:119,137): `reset()` / `step()` take and return Python lists / NumPy arrays (float64 observations,
+4-tuple `obs, reward, done, info`), `agent_list[i]` exposes `location`, `target_location`, `velocity`, `done`, ...
+(readable and assignable, as test_sac_multi_plot_trajectory.py:46-47 and test_ddpg_multi.py:122-126 use them), and
+the counters `steps`, `target_reach_count`, `collision_count` live on the env object.  They exist so that the
+reference's loops run unchanged against the CUDA path (parity, migration); throughput comes from the batched
+classes in `batched.py`.  Differences, all forced by the design: episodes are drawn from the counter-based Philox
+stream (`seed=` kwarg) instead of the global `np.random`; observations/rewards are float32 values widened to
+float64; in-place edits of a returned array (`agent.location[0] = x`) do not reach the device — assign the
+attribute instead; `render()` is a no-op.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .batched import BatchedMultiUAVWorld2D, BatchedUAVWorld2D
+
+GYM_IDS = {  # gym_uav_collision_avoidance/__init__.py:3-10
+    "gym_uav_collision_avoidance/UAVWorld2D-v0": "gym_uav_collision_avoidance_b200.compat:UAVWorld2D",
+    "gym_uav_collision_avoidance/MultiUAVWorld2D-v0": "gym_uav_collision_avoidance_b200.compat:MultiUAVWorld2D",
+}
+
+
+def register_gym_ids() -> bool:
+    """Register the reference's ids with gym / gymnasium when one of them is importable."""
+    for mod in ("gym", "gymnasium"):
+        try:
+            reg = __import__(mod + ".envs.registration", fromlist=["register"]).register
+        except Exception:
+            continue
+        for gid, entry in GYM_IDS.items():
+            try:
+                reg(id=gid, entry_point=entry)
+            except Exception:
+                pass
+        return True
+    return False
+
+
+class _AgentView:
+    """`UAVAgent` (uav_agent.py:7-20) as a window onto UAV `i` of the device state."""
+
+    def __init__(self, env: "MultiUAVWorld2D", i: int, color):
+        self._env, self._i, self.color = env, i, color
+        self.max_speed = env.max_speed.copy()
+        self.max_acceleration = env.max_acceleratoin.copy()
+        self.tau = env.tau
+
+    def _get(self, field):
+        return getattr(self._env._b.state, field)[0, self._i].cpu().numpy()
+
+    def _set(self, field, value):
+        t = getattr(self._env._b.state, field)
+        t[0, self._i] = torch.as_tensor(np.asarray(value, dtype=np.float64)).to(t.dtype)
+
+    location = property(lambda s: s._get("pos"), lambda s, v: s._set("pos", v))
+    target_location = property(lambda s: s._get("tgt"), lambda s, v: s._set("tgt", v))
+    velocity = property(lambda s: s._get("vel"), lambda s, v: s._set("vel", v))
+    velocity_prev = property(lambda s: s._get("vel"), lambda s, v: s._set("vel", v))  # both names hold v after a step
+    init_distance = property(lambda s: np.float32(s._get("init")), lambda s, v: s._set("init", v))
+    prev_distance = property(lambda s: np.float32(s._get("prev")), lambda s, v: s._set("prev", v))
+
+    def _flag(self, bit):
+        return bool(int(self._env._b.state.flags[0, self._i].item()) & bit)
+
+    def _set_flag(self, bit, on):
+        f = self._env._b.state.flags
+        cur = int(f[0, self._i].item())
+        f[0, self._i] = (cur | bit) if on else (cur & ~bit)
+
+    done = property(lambda s: s._flag(1), lambda s, v: s._set_flag(1, bool(v)))
+    collided = property(lambda s: s._flag(2), lambda s, v: s._set_flag(2, bool(v)))
+
+
+class MultiUAVWorld2D:
+    metadata = {"render_fps": 1000}
+
+    def __init__(self, x_size=50.0, y_size=50.0, max_speed=10.0, max_acceleration=5.0, num_agents=4, collider_radius=1.0,
+                 d_sense=15, *, seed=0, device=None):
+        import colorsys
+
+        kw = dict(x_size=x_size, y_size=y_size, max_speed=max_speed, max_acceleration=max_acceleration,
+                  num_agents=num_agents, collider_radius=collider_radius, d_sense=d_sense, device=device, seed=seed)
+        self._b = BatchedMultiUAVWorld2D(1, **kw)
+        self._kw = kw
+        self._circ = None  # second handle sharing the state blob, created on the first reset(circular=True)
+        for name in ("x_size", "y_size", "map_diagonal_size", "min_location", "max_location", "max_speed", "min_speed",
+                     "max_acceleratoin", "min_acceleratoin", "tau", "collider_radius", "d_sense", "observation_space",
+                     "action_space"):
+            setattr(self, name, getattr(self._b, name))
+        self.num_agents = num_agents
+        self.map_dimension = np.array([x_size, y_size])
+        self.agent_list = []
+        for i in range(num_agents):  # multi_uav_world_2d.py:36-41
+            r, g, b = colorsys.hsv_to_rgb(i / num_agents, 1.0, 1.0)
+            self.agent_list.append(_AgentView(self, i, (int(255 * r), int(255 * g), int(255 * b))))
+        self.window = self.clock = None
+
+    # counters live in the device state (multi_uav_world_2d.py:166-168)
+    def _counter(name):
+        def get(self):
+            return int(getattr(self._b.state, name)[0].item())
+
+        def set_(self, v):
+            getattr(self._b.state, name)[0] = int(v)
+
+        return property(get, set_)
+
+    steps = _counter("steps")
+    target_reach_count = _counter("reach")
+    collision_count = _counter("coll")
+    del _counter
+
+    def _obs_list(self, obs: torch.Tensor):
+        o = obs[0].cpu().numpy().astype(np.float64)
+        return [o[i] for i in range(self.num_agents)]
+
+    def _get_obs(self, agent):
+        return self._obs_list(self._b.observe())[agent._i]
+
+    def reset(self, return_info=False, circular=False):
+        if circular:
+            if self._circ is None:
+                self._circ = BatchedMultiUAVWorld2D(1, circular=True, **self._kw)
+            self._circ.state.blob.copy_(self._b.state.blob)  # carries the episode counter
+            self._circ.reset()
+            self._b.state.blob.copy_(self._circ.state.blob)
+            obs = self._obs_list(self._b.observe())
+        else:
+            obs = self._obs_list(self._b.reset())
+        info = {"distance": 0}
+        return (obs, info) if return_info else obs
+
+    def step(self, n_action, evaluate=False):
+        a = torch.as_tensor(np.asarray(n_action, dtype=np.float64).reshape(1, self.num_agents, 2), dtype=torch.float32)
+        obs, reward, done, _ = self._b.step(a.to(self._b.device), evaluate=evaluate)
+        r = reward[0].cpu().numpy()
+        d = done[0].cpu().numpy()
+        return (self._obs_list(obs), [float(x) for x in r], [bool(x) for x in d], {"distance": 0})
+
+    def render(self, mode="human"):
+        return None
+
+    def close(self):
+        self._b.close()
+        if self._circ is not None:
+            self._circ.close()
+
+
+class UAVWorld2D:
+    metadata = {"render_fps": 1000}
+
+    def __init__(self, x_size=100.0, y_size=100.0, agent_num=4, max_speed=12.0, max_acceleration=5.0, *, seed=0,
+                 device=None, float32_actions=False):
+        # float32_actions: the caller feeds float32 arrays (`action_space.sample()`, run.py:11); the reference then forms
+        # the first quotient after a reset in float32 (uav_world_2d.py:122,142).  The SAC/TD3 loops feed float64.
+        self._b = BatchedUAVWorld2D(1, x_size=x_size, y_size=y_size, max_speed=max_speed, max_acceleration=max_acceleration,
+                                    device=device, seed=seed, float32_first_step=float32_actions)
+        for name in ("x_size", "y_size", "map_diagonal_size", "min_location", "max_location", "max_speed", "min_speed",
+                     "max_acceleratoin", "min_acceleratoin", "tau", "observation_space", "action_space"):
+            setattr(self, name, getattr(self._b, name))
+        self.map_dimension = np.array([x_size, y_size])
+        self.window = self.clock = None
+
+    def _field(name, scalar=False):
+        def get(self):
+            v = getattr(self._b.state, name)[0, 0].cpu().numpy()
+            return np.float32(v) if scalar else v
+
+        def set_(self, v):
+            t = getattr(self._b.state, name)
+            t[0, 0] = torch.as_tensor(np.asarray(v, dtype=np.float64)).to(t.dtype)
+
+        return property(get, set_)
+
+    _agent_location = _field("pos")
+    _target_location = _field("tgt")
+    _agent_speed = _field("vel")
+    _agent_speed_prev = _field("vel")
+    _init_target_distance = _field("init", True)
+    _prev_distance = _field("prev", True)
+    del _field
+
+    @property
+    def steps(self):
+        return int(self._b.state.steps[0].item())
+
+    @steps.setter
+    def steps(self, v):
+        self._b.state.steps[0] = int(v)
+
+    def _get_obs(self):
+        return self._b.observe()[0, 0].cpu().numpy().astype(np.float64)
+
+    def _get_info(self):  # uav_world_2d.py:114-117
+        return {"distance": np.float32(np.linalg.norm(self._target_location - self._agent_location))}
+
+    def reset(self, return_info=False, options=None):
+        obs = self._b.reset()[0, 0].cpu().numpy().astype(np.float64)
+        return (obs, self._get_info()) if return_info else obs
+
+    def step(self, action):
+        a = torch.as_tensor(np.asarray(action, dtype=np.float64).reshape(1, 1, 2), dtype=torch.float32)
+        obs, reward, done, info = self._b.step(a.to(self._b.device))
+        return (obs[0, 0].cpu().numpy().astype(np.float64), np.float32(reward[0, 0].item()), bool(done[0, 0].item()),
+                {"distance": np.float32(info["distance"][0].item())})
+
+    def render(self, mode="human"):
+        return None
+
+    def close(self):
+        self._b.close()

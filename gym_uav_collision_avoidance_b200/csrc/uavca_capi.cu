@@ -466,6 +466,20 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
   return 0;
 }
 
+int uavca_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs, const uint8_t* done,
+                      int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs, float* ring_action, float* ring_reward,
+                      float* ring_next_obs, float* ring_mask, int64_t capacity, int64_t head, void* stream) {
+  if (!obs || !action || !reward || !next_obs || !done || !ring_obs || !ring_action || !ring_reward || !ring_next_obs || !ring_mask)
+    return fail(-1, "null argument");
+  if (M < 0 || obs_dim <= 0 || act_dim <= 0 || capacity <= 0) return fail(-1, "bad sizes");
+  if (M > capacity) return fail(-1, "uavca_replay_push: M exceeds the ring capacity");
+  if (head < 0 || head >= capacity) return fail(-1, "uavca_replay_push: head out of range");
+  cudaError_t e = launch_replay_push(obs, action, reward, next_obs, done, M, obs_dim, act_dim, ring_obs, ring_action,
+                                     ring_reward, ring_next_obs, ring_mask, capacity, head, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_replay_push", e);
+  return 0;
+}
+
 int64_t uavca_launch_count(const uavca_handle* h) { return h ? h->launches : 0; }
 
 }  // extern "C"

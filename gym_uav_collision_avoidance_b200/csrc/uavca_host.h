@@ -18,6 +18,10 @@ cudaError_t launch_reset_single(const KernelArgs& a, const uint8_t* mask, cudaSt
 cudaError_t launch_observe_single(const KernelArgs& a, cudaStream_t st);
 cudaError_t launch_map_action(const Consts& c, const float* in, float* out, long long M, int mode, cudaStream_t st);
 cudaError_t launch_stats(const StateView& s, int B, long long* out8, cudaStream_t st);
+cudaError_t launch_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs,
+                               const uint8_t* done, long long M, int obs_dim, int act_dim, float* r_obs, float* r_act,
+                               float* r_rew, float* r_next, float* r_mask, long long capacity, long long head,
+                               cudaStream_t st);
 
 // Shift a view to the sub-range of envs starting at env0 (stats stay shared).
 inline StateView offset_view(const StateView& v, long long env0, int N) {

@@ -306,9 +306,38 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(StateView s, int B, lon
   }
 }
 
+// Replay ring append: every array is a run of whole rows, so the ring write is a flat copy whose destination index
+// wraps at capacity * row.  V = float2 when both row widths are even and the pointers 8-byte aligned, else float.
+template <typename V>
+__global__ void __launch_bounds__(kThreads) replay_push_kernel(const V* obs, const V* act, const float* rew, const V* nxt,
+                                                               const uint8_t* done, long long M, long long od, long long ad,
+                                                               V* r_obs, V* r_act, float* r_rew, V* r_nxt, float* r_mask,
+                                                               long long cap, long long head) {
+  const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (j < M * od) {
+    long long d = head * od + j;
+    if (d >= cap * od) d -= cap * od;
+    r_obs[d] = ld_stream(obs + j);
+    r_nxt[d] = ld_stream(nxt + j);
+  }
+  if (j < M * ad) {
+    long long d = head * ad + j;
+    if (d >= cap * ad) d -= cap * ad;
+    r_act[d] = ld_stream(act + j);
+  }
+  if (j < M) {
+    long long d = head + j;
+    if (d >= cap) d -= cap;
+    r_rew[d] = ld_stream(rew + j);
+    r_mask[d] = done[j] ? 0.0f : 1.0f;
+  }
+}
+
 // ================================================================================================================
 // Launchers
 // ================================================================================================================
+
+static inline int flat_grid(long long n) { return (int)((n + kThreads - 1) / kThreads); }
 
 static inline int multi_grid(int B, int N) {
   const int epw = 32 / N;
@@ -471,8 +500,6 @@ cudaError_t launch_observe_multi(const KernelArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-static inline int flat_grid(long long n) { return (int)((n + kThreads - 1) / kThreads); }
-
 cudaError_t launch_step_single(const KernelArgs& a, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
   step_single_kernel<<<flat_grid(a.B), kThreads, 0, st>>>(a);
@@ -495,6 +522,29 @@ cudaError_t launch_map_action(const Consts& c, const float* in, float* out, long
   if (M <= 0) return cudaSuccess;
   map_action_kernel<<<flat_grid(M), kThreads, 0, st>>>(c, reinterpret_cast<const float2*>(in),
                                                        reinterpret_cast<float2*>(out), M, mode);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs,
+                               const uint8_t* done, long long M, int obs_dim, int act_dim, float* r_obs, float* r_act,
+                               float* r_rew, float* r_next, float* r_mask, long long capacity, long long head,
+                               cudaStream_t st) {
+  if (M <= 0) return cudaSuccess;
+  auto a8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
+  const bool wide = (obs_dim % 2 == 0) && (act_dim % 2 == 0) && a8(obs) && a8(action) && a8(next_obs) && a8(r_obs) &&
+                    a8(r_act) && a8(r_next);
+  const long long widest = (long long)(obs_dim > act_dim ? obs_dim : act_dim);
+  if (wide) {
+    const long long n = M * (widest / 2) > M ? M * (widest / 2) : M;
+    replay_push_kernel<float2><<<flat_grid(n), kThreads, 0, st>>>(
+        reinterpret_cast<const float2*>(obs), reinterpret_cast<const float2*>(action), reward,
+        reinterpret_cast<const float2*>(next_obs), done, M, obs_dim / 2, act_dim / 2, reinterpret_cast<float2*>(r_obs),
+        reinterpret_cast<float2*>(r_act), r_rew, reinterpret_cast<float2*>(r_next), r_mask, capacity, head);
+  } else {
+    const long long n = M * (widest > 1 ? widest : 1);
+    replay_push_kernel<float><<<flat_grid(n), kThreads, 0, st>>>(obs, action, reward, next_obs, done, M, obs_dim, act_dim,
+                                                                  r_obs, r_act, r_rew, r_next, r_mask, capacity, head);
+  }
   return cudaGetLastError();
 }
 

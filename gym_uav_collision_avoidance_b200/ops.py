@@ -81,3 +81,19 @@ def stats(handle: int, state: torch.Tensor, out8: torch.Tensor) -> None:
     """Episode statistics (env.steps / target_reach_count / collision_count, multi_uav_world_2d.py:166-168)."""
     _need_cuda(state, out8)
     _capi.check(_capi.load().uavca_stats(handle, state.data_ptr(), out8.data_ptr(), _stream(state)), "uavca_stats")
+
+
+@torch.library.custom_op("uavca::replay_push",
+                         mutates_args=("ring_obs", "ring_action", "ring_reward", "ring_next_obs", "ring_mask"))
+def replay_push(obs: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, next_obs: torch.Tensor, done: torch.Tensor,
+                ring_obs: torch.Tensor, ring_action: torch.Tensor, ring_reward: torch.Tensor, ring_next_obs: torch.Tensor,
+                ring_mask: torch.Tensor, head: int) -> None:
+    """Append M transitions to a device replay ring at slot `head` (ReplayMemory.push,
+    pytorch_sac_temp/replay_memory.py:15-19, for all B*N transitions of a step at once)."""
+    _need_cuda(obs, action, reward, next_obs, done, ring_obs, ring_action, ring_reward, ring_next_obs, ring_mask)
+    M = reward.numel()
+    _capi.check(_capi.load().uavca_replay_push(obs.data_ptr(), action.data_ptr(), reward.data_ptr(), next_obs.data_ptr(),
+                                               done.data_ptr(), M, obs.numel() // max(M, 1), action.numel() // max(M, 1),
+                                               ring_obs.data_ptr(), ring_action.data_ptr(), ring_reward.data_ptr(),
+                                               ring_next_obs.data_ptr(), ring_mask.data_ptr(), ring_reward.numel(), head,
+                                               _stream(obs)), "uavca_replay_push")

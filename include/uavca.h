@@ -154,6 +154,17 @@ int uavca_stats(uavca_handle* h, const void* state, int64_t* out8, void* stream)
 int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int action_mode, int evaluate,
                     float* host_obs, float* host_reward, uint8_t* host_done);
 
+/* Device-resident replay ring, the hand-off to the learner side ("next" row; replaces ReplayMemory.push,
+ * pytorch_sac_temp/replay_memory.py:15-19, and ReplayBuffer.append, pytorch_ddpg/buffer_tensor.py:40-59).
+ * Appends M transitions at ring slot `head`, wrapping at `capacity`, in one launch:
+ *   obs, next_obs float [M][obs_dim]; action float [M][act_dim]; reward float [M]; done uint8 [M]
+ *   ring_* float [capacity][...]; ring_mask[slot] = 1 - done  (mask = float(not done), test_sac_multi.py:101-103)
+ * No handle: the ring belongs to the caller.  M <= capacity. */
+int uavca_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs,
+                      const uint8_t* done, int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs,
+                      float* ring_action, float* ring_reward, float* ring_next_obs, float* ring_mask,
+                      int64_t capacity, int64_t head, void* stream);
+
 /* Launch bookkeeping: number of kernels this handle has launched so far. */
 int64_t uavca_launch_count(const uavca_handle* h);
 

@@ -1,0 +1,205 @@
+"""GPU: the rows either side of the hot path — B=1 drop-in classes (compat), device replay ring, batched acting
+path — against the reference's golden vectors and plain PyTorch restatements."""
+import numpy as np
+import pytest
+import torch
+
+from _golden import Case, obs_close
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-6
+
+
+def _close(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b) <= RTOL * np.abs(b) + ATOL
+
+
+# ---- compat: the reference's loop shape, lists in / lists out ------------------------------------------------------
+
+
+def test_compat_multi_runs_the_reference_loop_on_golden_vectors():
+    from gym_uav_collision_avoidance_b200 import compat
+
+    case = Case("multi_n8")
+    z, N = case.z, case.N
+    for e in range(2):  # env e of the golden batch, through the B=1 class
+        env = compat.MultiUAVWorld2D(num_agents=N)
+        env.reset()
+        for i, ag in enumerate(env.agent_list):  # state injection the way the scripts do it (attribute assignment)
+            ag.location = z["init_pos"][e, i]
+            ag.target_location = z["init_tgt"][e, i]
+            ag.velocity = z["init_vel"][e, i]
+            ag.init_distance = z["init_init"][e, i]
+            ag.prev_distance = z["init_prev"][e, i]
+            ag.done = bool(z["init_flags"][e, i] & 1)
+            ag.collided = bool(z["init_flags"][e, i] & 2)
+        env.steps = env.target_reach_count = env.collision_count = 0
+        for t in range(60):
+            actions = [z["action"][t, e, i].astype(np.float64) for i in range(N)]
+            obs, rewards, dones, info = env.step(actions)
+            assert isinstance(obs, list) and len(obs) == N and obs[0].shape == (10,) and obs[0].dtype == np.float64
+            assert isinstance(rewards, list) and isinstance(rewards[0], float)
+            assert isinstance(dones, list) and isinstance(dones[0], bool) and info == {"distance": 0}
+            assert dones == [bool(d) for d in z["done"][t, e]], f"done flags env {e} step {t}"
+            assert _close(rewards, z["reward"][t, e]).all()
+            assert obs_close(np.stack(obs), z["obs"][t, e], RTOL, ATOL).all()
+            assert np.array_equal(np.stack([a.location for a in env.agent_list]), z["pos"][t, e])
+            assert env.steps == int(z["steps"][t, e]) and env.collision_count == int(z["coll"][t, e])
+            assert env.target_reach_count == int(z["reach"][t, e])
+        env.close()
+
+
+def test_compat_multi_surface():
+    from gym_uav_collision_avoidance_b200 import compat
+
+    env = compat.MultiUAVWorld2D(num_agents=5, seed=3)
+    assert env.observation_space.shape[0] == 10 and env.action_space.shape[0] == 2
+    assert np.allclose(np.linalg.norm(env.action_space.high), 200 ** 0.5)
+    assert env.max_acceleratoin[0] == 5.0 and env.max_speed[0] == 10.0 and env.d_sense == 15 and env.collider_radius == 1.0
+    obs, info = env.reset(return_info=True)
+    assert len(obs) == 5 and info == {"distance": 0} and env.steps == 0
+    loc = np.stack([a.location for a in env.agent_list])
+    assert loc.dtype == np.float32 and (np.abs(loc) <= 25).all()
+    obs2 = env.reset()
+    assert not np.allclose(np.stack(obs), np.stack(obs2))  # a new episode is a new draw
+    ring = env.reset(circular=True)  # multi_uav_world_2d.py:157-163
+    loc = np.stack([a.location for a in env.agent_list]).astype(np.float64)
+    assert np.allclose(np.linalg.norm(loc, axis=1), 20.0, atol=1e-5) and len(ring) == 5
+    tgt = np.stack([a.target_location for a in env.agent_list]).astype(np.float64)
+    assert np.allclose(np.linalg.norm(tgt, axis=1), 23.0, atol=1e-5)
+    env.agent_list[2].location = np.array([1.5, -2.5])
+    assert np.array_equal(env.agent_list[2].location, np.array([1.5, -2.5], np.float32))
+    for _ in range(3):
+        env.step([env.action_space.sample() for _ in range(5)])
+    assert env.steps == 3
+    env.render()
+    env.close()
+
+
+def test_compat_single_runs_the_reference_loop_on_golden_vectors():
+    from gym_uav_collision_avoidance_b200 import compat
+
+    for name, f32 in (("single_f64_actions", False), ("single_f32_actions", True)):
+        case = Case(name)
+        z = case.z
+        env = compat.UAVWorld2D(float32_actions=f32)
+        env.reset()
+        e = 1
+        env._agent_location = z["init_pos"][e, 0]
+        env._target_location = z["init_tgt"][e, 0]
+        env._agent_speed = z["init_vel"][e, 0]
+        env._init_target_distance = z["init_init"][e, 0]
+        env._prev_distance = z["init_prev"][e, 0]
+        env.steps = 0
+        for t in range(40):
+            if z["reset_mask"][t, e]:
+                break
+            obs, reward, done, info = env.step(z["action"][t, e, 0])
+            assert obs.shape == (4,) and obs.dtype == np.float64 and isinstance(done, bool)
+            assert done == bool(z["done"][t, e, 0])
+            assert _close(reward, z["reward"][t, e, 0]) and info["distance"] == z["distance"][t, e]
+            assert obs_close(obs[None], case.final_obs(t)[e], RTOL, ATOL).all()
+            assert np.array_equal(env._agent_location, z["pos"][t, e, 0])
+            if done:
+                break
+        env.close()
+
+
+# ---- replay ring ------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("obs_dim,act_dim", [(10, 2), (4, 2), (5, 3)])
+def test_replay_push_wraps_like_a_ring(obs_dim, act_dim):
+    import gym_uav_collision_avoidance_b200 as G
+
+    cap, M = 1000, 384
+    rb = G.DeviceReplay(cap, obs_dim, act_dim, seed=1)
+    ref = dict(s=torch.zeros(cap, obs_dim), a=torch.zeros(cap, act_dim), r=torch.zeros(cap), n=torch.zeros(cap, obs_dim),
+               m=torch.zeros(cap))
+    gen = torch.Generator().manual_seed(0)
+    pos = 0
+    for k in range(7):
+        s, a = torch.randn(M // 4, 4, obs_dim, generator=gen), torch.randn(M // 4, 4, act_dim, generator=gen)
+        r, n = torch.randn(M // 4, 4, generator=gen), torch.randn(M // 4, 4, obs_dim, generator=gen)
+        d = (torch.rand(M // 4, 4, generator=gen) < 0.3).to(torch.uint8)
+        rb.push(s.cuda(), a.cuda(), r.cuda(), n.cuda(), d.cuda())
+        idx = (pos + torch.arange(M)) % cap
+        ref["s"][idx], ref["a"][idx], ref["r"][idx] = s.view(M, -1), a.view(M, -1), r.view(M)
+        ref["n"][idx], ref["m"][idx] = n.view(M, -1), 1.0 - d.view(M).float()  # mask = float(not done)
+        pos = (pos + M) % cap
+        assert rb.position == pos and len(rb) == min(cap, (k + 1) * M)
+    for name, t in (("s", rb.state), ("a", rb.action), ("r", rb.reward), ("n", rb.next_state), ("m", rb.mask)):
+        assert torch.equal(t.cpu(), ref[name]), name
+    st, ac, rw, nx, mk = rb.sample(256)
+    assert st.shape == (256, obs_dim) and ac.shape == (256, act_dim) and rw.shape == (256,) and mk.shape == (256,)
+    assert set(mk.unique().tolist()) <= {0.0, 1.0}
+    with pytest.raises(ValueError):
+        rb.push(torch.zeros(cap + 1, obs_dim).cuda(), torch.zeros(cap + 1, act_dim).cuda(), torch.zeros(cap + 1).cuda(),
+                torch.zeros(cap + 1, obs_dim).cuda(), torch.zeros(cap + 1, dtype=torch.uint8).cuda())
+
+
+def test_replay_recency_weighted_sampling_prefers_new_transitions():
+    import gym_uav_collision_avoidance_b200 as G
+
+    rb = G.DeviceReplay(4096, 4, 2, seed=5)
+    for k in range(6):  # 6144 transitions through a ring of 4096: reward carries the insertion order
+        r = torch.arange(k * 1024, (k + 1) * 1024, dtype=torch.float32).cuda()
+        z = torch.zeros(1024, 4).cuda()
+        rb.push(z, z[:, :2], r, z, torch.zeros(1024, dtype=torch.uint8).cuda())
+    _, _, rw_u, _, _ = rb.sample(200000)
+    _, _, rw_w, _, _ = rb.sample(200000, recency_weighted=True)
+    assert rw_u.min() >= 2048 and rw_w.min() >= 2048  # only live transitions
+    mid = 2048 + 2048
+    assert abs((rw_u >= mid).float().mean().item() - 0.5) < 0.01
+    assert abs((rw_w >= mid).float().mean().item() - 0.75) < 0.01  # p_i ~ i: the newer half carries 3/4 of the mass
+
+
+# ---- batched acting path ----------------------------------------------------------------------------------------------
+
+
+def test_rollout_feeds_the_replay_ring_with_the_steps_own_transitions():
+    import gym_uav_collision_avoidance_b200 as G
+
+    torch.manual_seed(0)
+    B, N = 64, 10
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=25, seed=11)
+    policy = G.GaussianPolicy(10, 2).cuda()
+    rb = G.DeviceReplay(B * N * 8, 10, 2, seed=0)
+    ro = G.BatchedRollout(env, policy, rb, action_mode="polar")
+    obs0 = ro.reset().clone()
+    ro.step()
+    # the first B*N slots: state = reset observation, next_state = the step's own (pre-reset) observation
+    assert torch.equal(rb.state[:B * N].view(B, N, 10), obs0)
+    assert torch.equal(rb.next_state[:B * N].view(B, N, 10), env.final_obs)
+    assert torch.equal(rb.reward[:B * N].view(B, N), env.reward)
+    assert torch.equal(rb.mask[:B * N].view(B, N), 1.0 - env.done.float())
+    assert (rb.action[:B * N].abs() <= 1).all()  # the policy's squashed action, mapped to cartesian inside the step
+    ro.run(40)
+    assert len(rb) == B * N * 8 and ro.steps == 41
+    sr, cr, episodes = ro.success_collision_rates()
+    assert episodes > 0 and 0.0 <= sr <= 1.0 and cr >= 0.0
+    # where an env auto-reset, the policy's next observation differs from the stored terminal observation
+    m = env.reset_mask.bool()
+    if m.any():
+        assert not torch.equal(env.obs[m], env.final_obs[m])
+
+
+def test_gaussian_policy_matches_the_reference_formulas():
+    import gym_uav_collision_avoidance_b200 as G
+
+    torch.manual_seed(1)
+    p = G.GaussianPolicy(10, 2).cuda()
+    assert [n for n, _ in p.named_parameters()] == [
+        "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias", "mean_linear.weight", "mean_linear.bias",
+        "log_std_linear.weight", "log_std_linear.bias"]  # pytorch_sac_temp/model.py:68-72: checkpoints load unchanged
+    x = torch.randn(512, 10).cuda()
+    mean, log_std = p(x)
+    assert (log_std >= -20).all() and (log_std <= 2).all()
+    torch.manual_seed(2)
+    a, logp, _ = p.sample(x)
+    torch.manual_seed(2)
+    normal = torch.distributions.Normal(mean, log_std.exp())
+    x_t = mean + log_std.exp() * torch.randn_like(mean)
+    ref_logp = (normal.log_prob(x_t) - torch.log(1 - torch.tanh(x_t).pow(2) + 1e-6)).sum(1, keepdim=True)
+    assert torch.allclose(a, torch.tanh(x_t)) and torch.allclose(logp, ref_logp, atol=1e-5)

@@ -21,10 +21,22 @@ for k in range(2 * ring):
     envs[k % ring].step(acts[k % len(acts)])
 torch.cuda.synchronize()
 st = torch.cuda.Stream()
+S = int(os.environ.get("STREAMS", "1"))  # independent batches of the ring pipelined over S streams
+side = [torch.cuda.Stream() for _ in range(S - 1)]
 g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g, stream=st):
+    fork = torch.cuda.Event()
+    fork.record(st)
+    for s_ in side:
+        s_.wait_event(fork)
     for k in range(G_STEPS):
-        envs[k % ring].step(acts[(k + k // ring) % len(acts)])
+        lane = (k % ring) % S  # a batch always runs on the same stream: its own steps stay ordered
+        with torch.cuda.stream(st if lane == 0 else side[lane - 1]):
+            envs[k % ring].step(acts[(k + k // ring) % len(acts)])
+    for s_ in side:
+        j = torch.cuda.Event()
+        j.record(s_)
+        st.wait_event(j)
 g.replay()
 torch.cuda.synchronize()
 reps = max(1, steps // G_STEPS)
@@ -39,5 +51,5 @@ for _ in range(3):
     st.synchronize()
     best = min(best, e0.elapsed_time(e1) * 1e3 / (reps * G_STEPS))
 alg = 107 + 24 / N
-print(f"{os.environ.get('UAVCA_LIB', 'default').split('/')[-1]:28s} path={os.environ.get('UAVCA_STEP_PATH', 'auto'):5s} N={N} B={B} ring={ring} "
+print(f"{os.environ.get('UAVCA_LIB', 'default').split('/')[-1]:28s} path={os.environ.get('UAVCA_STEP_PATH', 'lanes'):5s} streams={S} N={N} B={B} ring={ring} "
       f"{best:9.2f} us/step  {B * N / best / 1e3:7.2f} G UAV-steps/s  frac {B * N * alg / best / 1e3 / 6515.7:.3f}", flush=True)
