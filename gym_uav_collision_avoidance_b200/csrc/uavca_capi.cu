@@ -137,6 +137,7 @@ Consts derive_consts(const uavca_config& g) {
   c.rs_any_mask = (g.reset_mode & UAVCA_RESET_ON_ANY_DONE) ? 0xffffffffu : ((g.reset_mode & UAVCA_RESET_ON_DONE0) ? 1u : 0u);
   c.rs_all_off = (g.reset_mode & UAVCA_RESET_ON_ALL_DONE) ? 0u : 1u;
   c.steps_limit = g.max_episode_steps > 0 ? g.max_episode_steps : 0x7fffffff;
+  c.key_mask = ~31;
   c.reset_source = g.reset_source;
   c.circular = g.circular;
   c.single_f32_first_step = g.single_f32_first_step;

@@ -54,6 +54,7 @@ struct Consts {
   int reset_mode, max_steps, reset_source, circular, single_f32_first_step;
   unsigned rs_any_mask, rs_all_off;  // reset_mode as masks over an env's done bits (step_core)
   int steps_limit;                   // max_steps, or INT_MAX when there is no limit
+  int key_mask;                      // ~31: distance-bits mask of the neighbour keys (pair_scan)
   unsigned seed_lo, seed_hi;
   long long env_base;
 };

@@ -122,46 +122,87 @@ __device__ __forceinline__ void publish(const WarpScratch& ws, const Lane& L, fl
   __syncwarp();
 }
 
-// Two nearest other UAVs of the env, ordered by (squared float32 distance, index).
-struct Top2 {
-  float s1, s2;
-  int j1, j2;
-};
+// ---- neighbour search -----------------------------------------------------------------------------------------------
+// The two nearest other UAVs of the env, ordered by (squared float32 distance, ring offset) — the order of
+// `relative_distances.argsort()` (uav_agent.py:62) with the lowest ring offset first among exactly equal distances
+// (the reference's own order of exact ties is undefined).  Results are ring offsets k (neighbour
+// slot = own slot + k); 0 = none.
 
-// branch-free insertion; visiting the ring offsets k in ascending order keeps the nearer ring offset first among
-// exactly equal distances (the reference's own order of exact ties is undefined)
-__device__ __forceinline__ void top2_insert(Top2& t, float s, int k) {
-  const bool p1 = s < t.s1, p2 = s < t.s2;
-  t.j2 = p1 ? t.j1 : (p2 ? k : t.j2);
-  t.s2 = p1 ? t.s1 : (p2 ? s : t.s2);
-  t.j1 = p1 ? k : t.j1;
-  t.s1 = p1 ? s : t.s1;
+// Exact reference selection: branch-free insertion on the float32 squared distances themselves.  Out of line: it
+// only runs for the rare lanes whose fast selection below is ambiguous.
+static __device__ __noinline__ int nearest2_exact(const float4* row, float px, float py, int N) {
+  const float inf = __int_as_float(0x7f800000);
+  float s1 = inf, s2 = inf;
+  int j1 = 0, j2 = 0;
+  for (int k = 1; k < N; ++k) {
+    const float4 q = row[k];
+    const float s = sq32(__fsub_rn(q.y, px), __fsub_rn(q.w, py));
+    const bool p1 = s < s1, p2 = s < s2;
+    j2 = p1 ? j1 : (p2 ? k : j2);
+    s2 = p1 ? s1 : (p2 ? s : s2);
+    j1 = p1 ? k : j1;
+    s1 = p1 ? s : s1;
+  }
+  return j1 | (j2 << 8);
 }
 
 // One sweep over the env's other UAVs serving both pairwise passes of MultiUAVWorld2D.step:
 //   pass A (multi_uav_world_2d.py:198-210): nearest neighbour with j<i at the NEW position and j>i at the OLD one
-//                                           (the reference moves and tests the UAVs one after the other);
-//   pass B (:75 via _get_obs):              the two nearest neighbours with every UAV at its NEW position.
-// Top2.j1/j2 are ring offsets k (neighbour slot = own slot + k); 0 = none.
+//                                           (the reference moves and tests the UAVs one after the other) -> smin;
+//   pass B (:75 via _get_obs):              the two nearest neighbours with every UAV at its NEW position -> j1, j2.
+// Pass B keeps the THREE smallest integer keys (distance bits with the low 5 bits replaced by the ring offset):
+// integer min/max only, two neighbours merged per step with the k-th-smallest-of-two-sorted-lists identities
+//   t1' = min(t1, a)   t2' = min(t2, max(t1, a), b)   t3' = min(t3, max(t2, a), max(t1, b))       (a <= b).
+// A key orders like (distance truncated to 19 mantissa bits, offset).  If the truncated distances of the three
+// smallest keys are pairwise different, truncation cannot have reordered anything and t1, t2 are exactly the
+// reference's two nearest; otherwise (two of them within 2^-18 relative, ~1e-4 of the lanes at N=32) the lane
+// re-runs the exact selection.
 template <int NT>
-__device__ __forceinline__ void pair_scan(const WarpScratch& ws, const Lane& L, float px, float py, float& smin, Top2& t) {
-  const float inf = __int_as_float(0x7f800000);
-  smin = inf;
-  t = Top2{inf, inf, 0, 0};
+__device__ __forceinline__ void pair_scan(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
+                                          float& smin, int& j1, int& j2) {
   const int N = NT > 0 ? NT : L.N;
   const float4* row = ws.ring + 2 * L.base + L.i;
-  const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py);
-#pragma unroll
-  for (int k = 1; k < N; ++k) {
+  const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py), zero = make_float2(0.f, 0.f);
+  // (a.x - p.x, n.x - p.x), (a.y - p.y, n.y - p.y); squares and sum rounded separately, exactly as sq32().  The
+  // squares are FFMA2 with a +0 addend: a plain mul.rn.f32x2 feeding add.rn.f32x2 is contracted into one FFMA2 by
+  // ptxas 12.9 (even under -fmad=false), which would break the unfused np.linalg.norm order.
+  auto dist2 = [&](int k) {
     const float4 q = row[k];
-    // (a.x - p.x, n.x - p.x), (a.y - p.y, n.y - p.y); squares and sum rounded separately, exactly as sq32()
     const float2 dx = __fadd2_rn(make_float2(q.x, q.y), npx), dy = __fadd2_rn(make_float2(q.z, q.w), npy);
-    // the final sum is two SCALAR adds on purpose: ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
-    // even though both carry .rn (and even under -fmad=false), which would break the unfused np.linalg.norm order
-    const float2 xx = __fmul2_rn(dx, dx), yy = __fmul2_rn(dy, dy);
-    const float2 s = make_float2(__fadd_rn(xx.x, yy.x), __fadd_rn(xx.y, yy.y));
-    smin = fminf(smin, s.x);
-    top2_insert(t, s.y, k);
+    return __fadd2_rn(__ffma2_rn(dx, dx, zero), __ffma2_rn(dy, dy, zero));
+  };
+  // the mask (~31) comes from the constant bank on purpose: with an opaque mask and an immediate offset the key is
+  // ONE LOP3 ((s & mask) | k); as two literals it would be two
+  const int mask = c.key_mask;
+  auto key = [mask](float sq, int k) { return (__float_as_int(sq) & mask) | k; };
+  smin = __int_as_float(0x7f800000);
+  int t1 = 0x7f800000, t2 = 0x7f800020, t3 = 0x7f800040;  // "none": above every real key, pairwise unambiguous
+  int k = 1;
+#pragma unroll
+  for (; k + 1 < N; k += 2) {
+    const float2 s0 = dist2(k), s1 = dist2(k + 1);
+    smin = fminf(smin, fminf(s0.x, s1.x));
+    const int ka = key(s0.y, k), kb = key(s1.y, k + 1);
+    const int a = min(ka, kb), b = max(ka, kb);
+    const int m1a = max(t1, a), m2a = max(t2, a), m1b = max(t1, b);
+    t3 = __vimin3_s32(t3, m2a, m1b);
+    t2 = __vimin3_s32(t2, m1a, b);
+    t1 = min(t1, a);
+  }
+  if (k < N) {
+    const float2 s0 = dist2(k);
+    smin = fminf(smin, s0.x);
+    const int a = key(s0.y, k);
+    t3 = min(t3, max(t2, a));
+    t2 = min(t2, max(t1, a));
+    t1 = min(t1, a);
+  }
+  j1 = t1 & 31;
+  j2 = t2 & 31;
+  if (((unsigned)(t1 ^ t2) < 32u) | ((unsigned)(t2 ^ t3) < 32u)) {
+    const int e = nearest2_exact(row, px, py, N);
+    j1 = e & 0xff;
+    j2 = e >> 8;
   }
 }
 
@@ -171,23 +212,25 @@ struct ObsTail {
   float2 a, b, c;  // (o4, o5) (o6, o7) (o8, o9)
 };
 __device__ __forceinline__ ObsTail obs_neighbours(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
-                                                  float th_u, const Top2& t) {
-  const bool have1 = t.s1 < c.s_dsense_lt;       // uav_agent.py:52 strict <  (s = +inf when there is no other UAV)
-  const bool have2 = have1 & (t.s2 < c.s_dsense_lt);
+                                                  float th_u, int j1, int j2) {
   const int slot = 2 * L.base + L.i;
-  const float4 q1 = ws.ring[slot + t.j1], q2 = ws.ring[slot + t.j2];
-  const float h1 = ws.th[slot + t.j1], h2 = ws.th[slot + t.j2];
-  const float2 b = fast_atan2_pair(__fsub_rn(q1.w, py), __fsub_rn(q1.y, px), __fsub_rn(q2.w, py), __fsub_rn(q2.y, px));
+  const float4 q1 = ws.ring[slot + j1], q2 = ws.ring[slot + j2];
+  const float h1 = ws.th[slot + j1], h2 = ws.th[slot + j2];
+  const float dx1 = __fsub_rn(q1.y, px), dy1 = __fsub_rn(q1.w, py), dx2 = __fsub_rn(q2.y, px), dy2 = __fsub_rn(q2.w, py);
+  const float s1 = sq32(dx1, dy1), s2 = sq32(dx2, dy2);  // the exact squared distances of the two winners
+  const bool have1 = (j1 != 0) & (s1 < c.s_dsense_lt);  // uav_agent.py:52 strict <
+  const bool have2 = have1 & (j2 != 0) & (s2 < c.s_dsense_lt);
+  const float2 b = fast_atan2_pair(dy1, dx1, dy2, dx2);
   const float2 nth = make_float2(-th_u, -th_u);
   const float2 w1 = wrap_units2(__ffma2_rn(b, make_float2(c.inv_pi, c.inv_pi), nth));  // bearings relative to the heading
   const float2 w2 = wrap_units2(__fadd2_rn(make_float2(h1, h2), nth));                 // neighbour headings, relative
   ObsTail o;
-  o.a.x = have1 ? sqrt_approx(t.s1) * c.inv_dsense : 1.0f;  // :77
-  o.a.y = have1 ? w1.x : 1.0f;                              // :78-81 (no neighbour: bearing pi)
-  o.b.x = have1 ? w2.x : 0.0f;                              // :82-85
-  o.b.y = have2 ? sqrt_approx(t.s2) * c.inv_dsense : 1.0f;  // :87
-  o.c.x = have2 ? w1.y : 1.0f;                              // :88-91
-  o.c.y = have2 ? w2.y : 0.0f;                              // :92-95
+  o.a.x = have1 ? sqrt_approx(s1) * c.inv_dsense : 1.0f;  // :77
+  o.a.y = have1 ? w1.x : 1.0f;                            // :78-81 (no neighbour: bearing pi)
+  o.b.x = have1 ? w2.x : 0.0f;                            // :82-85
+  o.b.y = have2 ? sqrt_approx(s2) * c.inv_dsense : 1.0f;  // :87
+  o.c.x = have2 ? w1.y : 1.0f;                            // :88-91
+  o.c.y = have2 ? w2.y : 0.0f;                            // :92-95
   return o;
 }
 
@@ -239,11 +282,11 @@ __device__ __forceinline__ void observe_state(const Consts& c, const WarpScratch
   __syncwarp();
   publish(ws, L, u.px, u.py, u.px, u.py, w.th_u);
   float smin;
-  Top2 t;
-  pair_scan<NT>(ws, L, u.px, u.py, smin, t);
+  int j1, j2;
+  pair_scan<NT>(c, ws, L, u.px, u.py, smin, j1, j2);
   float2 o01, o23;
   obs_own(c, w, w.vsq, o01, o23);
-  const ObsTail n = obs_neighbours(c, ws, L, u.px, u.py, w.th_u, t);
+  const ObsTail n = obs_neighbours(c, ws, L, u.px, u.py, w.th_u, j1, j2);
   o[0] = o01.x; o[1] = o01.y; o[2] = o23.x; o[3] = o23.y;
   o[4] = n.a.x; o[5] = n.a.y; o[6] = n.b.x; o[7] = n.b.y; o[8] = n.c.x; o[9] = n.c.y;
 }
@@ -438,8 +481,8 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
 
   // ---- both pairwise passes in one sweep over the env's UAVs
   float smin;
-  Top2 t;
-  pair_scan<NT>(ws, L, u.px, u.py, smin, t);
+  int j1, j2;
+  pair_scan<NT>(c, ws, L, u.px, u.py, smin, j1, j2);
 
   // ---- collisions (:199-210), decided in squared-distance space (the thresholds already include "in sensing range")
   const bool collision = smin <= c.s_coll_le;
@@ -467,7 +510,7 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
     float2 o01, o23;
     obs_own(c, w, vsq_obs, o01, o23);
     io.put_own(o01, o23);
-    io.put_neighbours(obs_neighbours(c, ws, L, u.px, u.py, w.th_u, t));
+    io.put_neighbours(obs_neighbours(c, ws, L, u.px, u.py, w.th_u, j1, j2));
   }
   io.store_reward_done(r, done);
 
