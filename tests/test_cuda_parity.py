@@ -303,7 +303,7 @@ def test_neighbour_order_across_the_key_granularity(n, spread):
     d = st.pos[:, 1:] - st.pos[:, :1]
     s = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(np.float32)
     srt = np.sort(s, axis=1)
-    untied = (np.diff(srt, axis=1) != 0).all(axis=1) if n > 2 else np.ones(B, bool)
+    untied = (np.diff(srt[:, :4], axis=1) != 0).all(axis=1) if n > 2 else np.ones(B, bool)  # the three smallest (+1) differ
     assert untied.mean() > 0.5
     obs = env.obs.cpu().numpy()
     ok = obs_close(obs[untied, 0], out["obs"][untied, 0], RTOL, ATOL)
