@@ -421,19 +421,49 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
   const int D = h->cfg.kind == UAVCA_KIND_SINGLE ? UAVCA_OBS_DIM_SINGLE : UAVCA_OBS_DIM_MULTI;
   const size_t M = (size_t)B * N;
   cudaError_t e = cudaSuccess;
-  if (!h->d_action) {
+  if (!h->hs[0]) {
     for (auto& s : h->hs) {
       e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
       if (e != cudaSuccess) return fail_cuda("stream create", e);
     }
+  }
+  // the caller's earlier work on `state` (any stream) must be visible before the internal streams touch it
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail_cuda("device synchronize", e);
+  // Zero-copy path: when all four host buffers are pinned (page-locked, hence mapped into the device's address
+  // space under UVA) the step kernel reads the actions and writes obs/reward/done THROUGH PCIe itself — one launch,
+  // no staging copies, the stores stream out as posted writes while the SMs work on the next warps.
+  // UAVCA_HOST_PATH=staged forces the chunked copy pipeline below.
+  auto mapped = [&](const void* p) -> void* {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  };
+  const char* hp = std::getenv("UAVCA_HOST_PATH");
+  const bool want_staged = hp && std::strcmp(hp, "staged") == 0;
+  void *m_act = nullptr, *m_obs = nullptr, *m_rew = nullptr, *m_done = nullptr;
+  if (!want_staged) { m_act = mapped(host_action); m_obs = mapped(host_obs); m_rew = mapped(host_reward); m_done = mapped(host_done); }
+  if (m_act && m_obs && m_rew && m_done) {
+    KernelArgs a = make_args(h, state);
+    a.io.action = reinterpret_cast<const float2*>(m_act);
+    a.io.obs = reinterpret_cast<float*>(m_obs); a.io.reward = reinterpret_cast<float*>(m_rew);
+    a.io.done = reinterpret_cast<uint8_t*>(m_done);
+    a.io.action_mode = action_mode; a.io.evaluate = evaluate;
+    cudaStream_t st = h->hs[0];
+    int launched = 1;
+    e = h->cfg.kind == UAVCA_KIND_SINGLE ? launch_step_single(a, st) : launch_step_multi(a, st, &launched, h->path);
+    h->launches += launched;
+    if (e != cudaSuccess) return fail_cuda("uavca_step_host launch", e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail_cuda("stream synchronize", e);
+    return 0;
+  }
+  // Staged path (pageable host memory): chunk the env range so that H2D of chunk k+1, the step of chunk k and D2H of
+  // chunk k-1 overlap
+  if (!h->d_action) {
     if ((e = cudaMalloc(&h->d_action, M * 2 * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_obs, M * D * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_reward, M * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_done, M)) != cudaSuccess) return fail_cuda("cudaMalloc", e);
   }
-  // the caller's earlier work on `state` (any stream) must be visible before the internal streams touch it
-  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail_cuda("device synchronize", e);
-  // chunk the env range so that H2D of chunk k+1, the step of chunk k and D2H of chunk k-1 overlap
   int chunks = 8;
   long long per = ((long long)B + chunks - 1) / chunks;
   per = (per + 63) / 64 * 64;  // keeps every chunk's rows 16-byte aligned for any N

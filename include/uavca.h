@@ -148,9 +148,10 @@ int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* o
  * same three counters summed over the episodes in flight (reach, collisions, steps) and B. */
 int uavca_stats(uavca_handle* h, const void* state, int64_t* out8, void* stream);
 
-/* End-to-end form with HOST buffers (pinned for full speed): copies the actions in, steps, copies
- * obs/reward/done out, pipelined in chunks over internal streams, and returns when the outputs are in
- * host memory.  `state` stays on the device.  Works for both kinds (obs_dim from the config). */
+/* End-to-end form with HOST buffers; returns when the outputs are in host memory.  `state` stays on the
+ * device.  Pinned (page-locked) buffers take the zero-copy path: one launch whose loads/stores go through
+ * PCIe directly (mapped host memory).  Pageable buffers are staged: H2D actions, step, D2H obs/reward/done,
+ * pipelined in chunks over internal streams.  Works for both kinds (obs_dim from the config). */
 int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int action_mode, int evaluate,
                     float* host_obs, float* host_reward, uint8_t* host_done);
 

@@ -424,10 +424,14 @@ def test_action_modes(mode):
         assert np.allclose(orc.map_action(an, O.ACTION_POLAR if mode == "polar" else O.ACTION_SCALED), ref, rtol=1e-5, atol=2e-6)
 
 
+@pytest.mark.parametrize("pinned", [True, False])
 @pytest.mark.parametrize("kind", ["multi", "single"])
-def test_step_host_matches_device_step(kind):
+def test_step_host_matches_device_step(kind, pinned):
+    """Host-buffer step: pinned buffers take the zero-copy path (the kernel reads/writes mapped host memory through
+    PCIe), pageable buffers the staged chunked-copy pipeline; both must equal the device-resident step."""
     G = _b200()
     B = 5000
+    pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
     if kind == "multi":
         mk = lambda: G.BatchedMultiUAVWorld2D(B, num_agents=7, seed=8, reset_mode=O.RESET_ON_DONE0, max_episode_steps=30)  # noqa: E731
         N, D = 7, 10
@@ -437,10 +441,10 @@ def test_step_host_matches_device_step(kind):
     e1, e2 = mk(), mk()
     e1.reset()
     e2.reset()
-    act = torch.empty((B, N, 2), dtype=torch.float32).pin_memory()
-    obs = torch.empty((B, N, D), dtype=torch.float32).pin_memory()
-    rew = torch.empty((B, N), dtype=torch.float32).pin_memory()
-    done = torch.empty((B, N), dtype=torch.uint8).pin_memory()
+    act = pin(torch.empty((B, N, 2), dtype=torch.float32))
+    obs = pin(torch.empty((B, N, D), dtype=torch.float32))
+    rew = pin(torch.empty((B, N), dtype=torch.float32))
+    done = pin(torch.empty((B, N), dtype=torch.uint8))
     g = torch.Generator().manual_seed(0)
     for _ in range(50):
         act.copy_(torch.rand((B, N, 2), generator=g) * 20 - 10)
