@@ -33,9 +33,9 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # name: kind, N, B per GPU, algorithmic bytes per UAV-step (SURVEY.md §8d / DESIGN.md §5), default steps
     "c3": dict(kind="multi", N=8, B=65536, desc="multi-UAV N=8, B=65,536 envs/GPU (BASELINE configs[2])", steps=20000),
-    "c2": dict(kind="single", N=1, B=65536, desc="single-UAV, B=65,536 envs/GPU (BASELINE configs[1])", steps=20000),
+    "c2": dict(kind="single", N=1, B=65536, desc="single-UAV, B=65,536 envs/GPU (BASELINE configs[1])", steps=20000, streams=4),
     "c4": dict(kind="multi", N=32, B=1048576, desc="multi-UAV N=32, B=1,048,576 envs/GPU (BASELINE configs[3] shape)", steps=300),
-    "c5": dict(kind="multi", N=10, B=16384, desc="multi-UAV N=10, B=16,384 envs/GPU (BASELINE configs[4] env part)", steps=20000),
+    "c5": dict(kind="multi", N=10, B=16384, desc="multi-UAV N=10, B=16,384 envs/GPU (BASELINE configs[4] env part)", steps=20000, streams=4),
 }
 L2_BYTES = 126e6
 GRAPH_STEPS = 200
@@ -390,7 +390,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=2, help="streams the independent batches of the ring are pipelined over")
+    ap.add_argument("--streams", type=int, default=None,
+                    help="streams the independent batches of the ring are pipelined over (default: 2; 4 for the small c2/c5 batches)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -398,6 +399,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.steps is None:
         args.steps = wl["steps"] if args.impl == "ours" else 100
+    if args.streams is None:
+        args.streams = wl.get("streams", 2)
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
         return
