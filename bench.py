@@ -342,7 +342,7 @@ def run_ours(args, wl, rank, world, local_rank):
         launch_s = ms * 1e-3 / K
         achieved = units_per_step * alg / launch_s / 1e9
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # a reported baseline, timed on rank 0 at N=1 only
             c_envs = min(B, 4096 if N <= 8 else 512)
             c_steps = max(20, int(12e6 // (c_envs * N)))
             ups, dt = time_oracle(kind, N, c_envs, c_steps, 1)

@@ -511,6 +511,21 @@ int uavca_replay_push(const float* obs, const float* action, const float* reward
   return 0;
 }
 
+int uavca_policy_act(const float* obs, int64_t M, const void* w1, const void* w2, const void* w2b, const void* w3,
+                     const void* w3b, const float* noise, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
+                     float* action, float* head, void* stream) {
+  if (!obs || !w1 || !w2 || !w2b || !w3 || !w3b || !action) return fail(-1, "null argument");
+  if (M < 0) return fail(-1, "bad size");
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!a16(w1) || !a16(w2) || !a16(w2b) || !a16(w3) || !a16(w3b) || (reinterpret_cast<uintptr_t>(obs) & 7u) ||
+      (reinterpret_cast<uintptr_t>(action) & 7u) || (head && !a16(head)) || (noise && (reinterpret_cast<uintptr_t>(noise) & 7u)))
+    return fail(-1, "uavca_policy_act: misaligned buffer (weights/head 16 bytes, obs/action/noise 8 bytes)");
+  cudaError_t e = launch_policy_act(obs, M, w1, w2, w2b, w3, w3b, noise, seed, counter,
+                                    reinterpret_cast<const unsigned long long*>(counter_dev), action, head, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_policy_act", e);
+  return 0;
+}
+
 int64_t uavca_launch_count(const uavca_handle* h) { return h ? h->launches : 0; }
 
 }  // extern "C"

@@ -23,6 +23,10 @@ cudaError_t launch_replay_push(const float* obs, const float* action, const floa
                                float* r_rew, float* r_next, float* r_mask, long long capacity, long long head,
                                cudaStream_t st);
 
+cudaError_t launch_policy_act(const float* obs, long long M, const void* w1, const void* w2, const void* w2b, const void* w3,
+                              const void* w3b, const float* noise, unsigned long long seed, unsigned long long counter,
+                              const unsigned long long* counter_dev, float* action, float* head, cudaStream_t st);
+
 // Shift a view to the sub-range of envs starting at env0 (stats stay shared).
 inline StateView offset_view(const StateView& v, long long env0, int N) {
   StateView o = v;

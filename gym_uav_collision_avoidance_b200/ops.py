@@ -97,3 +97,15 @@ def replay_push(obs: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, n
                                                ring_obs.data_ptr(), ring_action.data_ptr(), ring_reward.data_ptr(),
                                                ring_next_obs.data_ptr(), ring_mask.data_ptr(), ring_reward.numel(), head,
                                                _stream(obs)), "uavca_replay_push")
+
+
+@torch.library.custom_op("uavca::policy_act", mutates_args=("action", "head"))
+def policy_act(obs: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w2b: torch.Tensor, w3: torch.Tensor, w3b: torch.Tensor,
+               noise: Optional[torch.Tensor], seed: int, counter: int, counter_dev: Optional[torch.Tensor],
+               action: torch.Tensor, head: Optional[torch.Tensor]) -> None:
+    """GaussianPolicy acting path (pytorch_sac_temp/model.py:74-101) for all rows of `obs` in one tcgen05 kernel.
+    Weight operands are the fp16 packings described in include/uavca.h."""
+    _need_cuda(obs, w1, w2, w2b, w3, w3b, noise, counter_dev, action, head)
+    _capi.check(_capi.load().uavca_policy_act(obs.data_ptr(), obs.numel() // 10, w1.data_ptr(), w2.data_ptr(), w2b.data_ptr(),
+                                              w3.data_ptr(), w3b.data_ptr(), _ptr(noise), seed, counter, _ptr(counter_dev),
+                                              action.data_ptr(), _ptr(head), _stream(obs)), "uavca_policy_act")

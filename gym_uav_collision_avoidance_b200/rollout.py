@@ -56,15 +56,79 @@ class GaussianPolicy(nn.Module):
 
     @torch.no_grad()
     def act(self, state, evaluate=False):
-        a, _, e = self.sample(state)
-        return e if evaluate else a
+        """Acting only (SAC.select_action, pytorch_sac_temp/sac.py:38-44): tanh(mean + std * eps) — in the reference both
+        the training action and the `evaluate=True` action are samples (model.py:90,101), so one code path serves both;
+        the log-probability is not needed to act and is not computed."""
+        mean, log_std = self.forward(state)
+        return torch.tanh(torch.addcmul(mean, log_std.exp(), torch.randn_like(mean)))
+
+
+class FusedGaussianPolicy:
+    """The acting path of a `GaussianPolicy` (10 -> 256 -> 256 -> 2+2) as ONE tcgen05 kernel (`uavca_policy_act`,
+    csrc/uavca_policy.cu): both hidden layers on the tensor cores with the activations kept in shared memory / TMEM,
+    output heads, tanh-Gaussian sampling (Philox noise) fused.  Operands are fp16 with fp32 accumulation.  Weights are
+    packed once from the module; call `refresh()` after the learner updated it (test_sac_multi.py:85-91)."""
+
+    def __init__(self, policy: GaussianPolicy, seed: int = 0):
+        self.policy = policy
+        self.seed = int(seed)
+        self.calls = 0  # host-side offset of the Philox counter (set it to replay a draw)
+        self.refresh()
+        # device-side call counter: advanced by a one-element kernel after every act(), so a CUDA-graph replay of the
+        # acting step draws fresh noise each time
+        self.counter = torch.zeros(1, dtype=torch.int64, device=self.w2.device)
+
+    @torch.no_grad()
+    def refresh(self):
+        p = self.policy
+        w1, w2 = p.linear1.weight, p.linear2.weight
+        if tuple(w1.shape) != (256, 10) or tuple(w2.shape) != (256, 256) or p.mean_linear.weight.shape[0] != 2:
+            raise ValueError("the fused acting kernel is built for the reference architecture 10 -> 256 -> 256 -> 2")
+        if not w1.is_cuda:
+            raise ValueError("the policy must live on a CUDA device")
+        dev, h = w1.device, torch.float16
+        # fp16 K-major operands; every bias rides in an extra input column (include/uavca.h)
+        self.w1 = torch.zeros((256, 16), dtype=h, device=dev)
+        self.w1[:, :10] = w1.to(h)
+        self.w1[:, 10] = p.linear1.bias.to(h)
+        self.w2 = w2.to(h).contiguous()
+        self.w2b = torch.zeros((256, 16), dtype=h, device=dev)
+        self.w2b[:, 0] = p.linear2.bias.to(h)
+        self.w3 = torch.zeros((16, 256), dtype=h, device=dev)
+        self.w3[0:2] = p.mean_linear.weight.to(h)
+        self.w3[2:4] = p.log_std_linear.weight.to(h)
+        self.w3b = torch.zeros((16, 16), dtype=h, device=dev)
+        self.w3b[0:2, 0] = p.mean_linear.bias.to(h)
+        self.w3b[2:4, 0] = p.log_std_linear.bias.to(h)
+
+    def act(self, state: torch.Tensor, evaluate: bool = False, out: Optional[torch.Tensor] = None,
+            noise: Optional[torch.Tensor] = None, head: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """state [M, 10] float32 CUDA -> action [M, 2] in (-1, 1).  `noise` [M, 2] overrides the Philox draws (tests);
+        `head` [M, 4] receives (mean, log_std)."""
+        from . import ops
+
+        state = state.contiguous()
+        M = state.numel() // 10
+        if out is None:
+            out = torch.empty((M, 2), dtype=torch.float32, device=state.device)
+        ops.policy_act(state, self.w1, self.w2, self.w2b, self.w3, self.w3b, noise, self.seed, self.calls, self.counter,
+                       out, head)
+        self.counter += 1
+        return out
 
 
 class BatchedRollout:
     """obs -> policy -> step(action_mode) -> replay, all on the device; optionally replayed from a CUDA graph."""
 
     def __init__(self, env, policy: Optional[nn.Module] = None, replay: Optional[DeviceReplay] = None,
-                 action_mode="polar", evaluate=False, warmup_uniform=False):
+                 action_mode="polar", evaluate=False, warmup_uniform=False, precision="fp32"):
+        """precision of the policy forward: "fp32" (the reference's arithmetic: PyTorch default, TF32 off), "tf32"
+        (tensor-core GEMMs on fp32 storage), "bf16" (autocast) or "fused" (the one-kernel tcgen05 acting path,
+        `FusedGaussianPolicy`).  The env step itself is unaffected."""
+        if precision not in ("fp32", "tf32", "bf16", "fused"):
+            raise ValueError("precision must be fp32, tf32, bf16 or fused")
+        self.precision = precision
+        self.fused = FusedGaussianPolicy(policy) if precision == "fused" else None
         self.env, self.policy, self.replay = env, policy, replay
         self.action_mode, self.evaluate, self.warmup_uniform = action_mode, evaluate, warmup_uniform
         B, N, D = env.num_envs, env.num_agents, env.obs_dim
@@ -85,7 +149,22 @@ class BatchedRollout:
         if self.policy is None or self.warmup_uniform:  # test_sac_multi.py:72-73: uniform actions during warm-up
             self.action.uniform_(-1.0, 1.0)
         else:
-            a = self.policy.act(self.state.view(-1, env.obs_dim), evaluate=self.evaluate)
+            x = self.state.view(-1, env.obs_dim)
+            if self.precision == "fused":
+                self.fused.act(x, evaluate=self.evaluate, out=self.action.view(-1, 2))
+                return
+            if self.precision == "bf16":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    a = self.policy.act(x, evaluate=self.evaluate)
+            elif self.precision == "tf32":
+                prev = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = True
+                try:
+                    a = self.policy.act(x, evaluate=self.evaluate)
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev
+            else:
+                a = self.policy.act(x, evaluate=self.evaluate)
             self.action.copy_(a.view_as(self.action))
 
     def _env_step(self):

@@ -166,6 +166,24 @@ int uavca_replay_push(const float* obs, const float* action, const float* reward
                       float* ring_action, float* ring_reward, float* ring_next_obs, float* ring_mask,
                       int64_t capacity, int64_t head, void* stream);
 
+/* Fused acting path of the shared SAC policy ("next" row; replaces the per-UAV SAC.select_action round trips,
+ * pytorch_sac_temp/sac.py:38-44, with GaussianPolicy.forward/sample, pytorch_sac_temp/model.py:74-101, for all
+ * M = B*N observations in one tcgen05 kernel).  Fixed architecture 10 -> 256 -> 256 -> (2 + 2); all weight
+ * operands fp16, K-major, biases carried as an extra input column:
+ *   obs float [M][10];
+ *   w1  fp16 [256][16]  : linear1.weight in columns 0..9, linear1.bias in column 10, zeros elsewhere;
+ *   w2  fp16 [256][256] : linear2.weight;            w2b fp16 [256][16] : linear2.bias in column 0, zeros;
+ *   w3  fp16 [16][256]  : rows 0,1 mean_linear.weight, rows 2,3 log_std_linear.weight, zeros;
+ *   w3b fp16 [16][16]   : mean_linear.bias, log_std_linear.bias in column 0 of rows 0..3, zeros;
+ *   noise float [M][2] standard-normal draws or NULL (then Philox4x32-10 keyed by seed, row and
+ *   counter + *counter_dev; counter_dev is a nullable DEVICE uint64 the caller advances between calls, which keeps
+ *   a CUDA-graph replay of the call from repeating its noise);
+ *   action float [M][2] = tanh(mean + exp(clamp(log_std, -20, 2)) * noise);  head (nullable) float [M][4] = mean, log_std.
+ * No handle: weights and buffers belong to the caller. */
+int uavca_policy_act(const float* obs, int64_t M, const void* w1, const void* w2, const void* w2b, const void* w3,
+                     const void* w3b, const float* noise, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
+                     float* action, float* head, void* stream);
+
 /* Launch bookkeeping: number of kernels this handle has launched so far. */
 int64_t uavca_launch_count(const uavca_handle* h);
 

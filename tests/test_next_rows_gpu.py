@@ -203,3 +203,72 @@ def test_gaussian_policy_matches_the_reference_formulas():
     x_t = mean + log_std.exp() * torch.randn_like(mean)
     ref_logp = (normal.log_prob(x_t) - torch.log(1 - torch.tanh(x_t).pow(2) + 1e-6)).sum(1, keepdim=True)
     assert torch.allclose(a, torch.tanh(x_t)) and torch.allclose(logp, ref_logp, atol=1e-5)
+
+
+# ---- fused tcgen05 acting kernel ----------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("M", [1, 100, 128, 1000, 163840])
+def test_fused_policy_matches_the_pytorch_policy(M):
+    """`uavca_policy_act` (tcgen05, fp16 operands / fp32 accumulate) against the fp32 PyTorch GaussianPolicy: the heads
+    (mean, log_std) within 2e-2, the action with caller-supplied noise within 3e-2; ragged and tiny row counts."""
+    import gym_uav_collision_avoidance_b200 as G
+
+    torch.manual_seed(3)
+    p = G.GaussianPolicy(10, 2).cuda()
+    with torch.no_grad():  # non-trivial biases and a log_std head away from 0
+        for lin in (p.linear1, p.linear2, p.mean_linear, p.log_std_linear):
+            lin.bias.uniform_(-0.3, 0.3)
+    f = G.FusedGaussianPolicy(p, seed=9)
+    obs = torch.rand(M, 10, device="cuda") * 2 - 1
+    noise = torch.randn(M, 2, device="cuda")
+    head = torch.zeros(M, 4, device="cuda")
+    act = f.act(obs, noise=noise, head=head)
+    with torch.no_grad():
+        mean, log_std = p(obs)
+    ref_head = torch.cat([mean, log_std], 1)
+    assert (head - ref_head).abs().max().item() < 2e-2, (head - ref_head).abs().max().item()
+    ref_act = torch.tanh(mean + log_std.exp() * noise)
+    assert (act - ref_act).abs().max().item() < 3e-2
+    assert act.abs().max().item() <= 1.0
+
+
+def test_fused_policy_philox_noise_is_standard_normal_and_counter_keyed():
+    import gym_uav_collision_avoidance_b200 as G
+
+    p = G.GaussianPolicy(10, 2).cuda()
+    with torch.no_grad():
+        for prm in p.parameters():
+            prm.zero_()  # mean = 0, log_std = 0: action = tanh(eps)
+    f = G.FusedGaussianPolicy(p, seed=1234)
+    obs = torch.zeros(200000, 10, device="cuda")
+    a0 = f.act(obs).clone()
+    a1 = f.act(obs).clone()
+    assert not torch.equal(a0, a1)  # the call counter advances the stream
+    f.counter.zero_()
+    assert torch.equal(f.act(obs), a0)  # same (seed, row, counter) -> same draw
+    g = torch.cuda.CUDAGraph()  # captured once, replayed: the device-side counter keeps the draws fresh
+    out = torch.empty_like(a0)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        f.act(obs, out=out)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=s):
+        f.act(obs, out=out)
+    g.replay(); torch.cuda.synchronize(); r1 = out.clone()
+    g.replay(); torch.cuda.synchronize()
+    assert not torch.equal(out, r1)
+    eps = torch.atanh(a0.double().clamp(-1 + 1e-12, 1 - 1e-12))
+    assert abs(eps.mean().item()) < 0.01 and abs(eps.std().item() - 1.0) < 0.01
+    assert abs((eps ** 4).mean().item() - 3.0) < 0.1 and abs((eps[:, 0] * eps[:, 1]).mean().item()) < 0.01
+
+
+def test_rollout_with_the_fused_policy():
+    import gym_uav_collision_avoidance_b200 as G
+
+    torch.manual_seed(0)
+    env = G.BatchedMultiUAVWorld2D(512, num_agents=10, reset_mode=G.RESET_ON_DONE0, max_episode_steps=50, seed=2)
+    ro = G.BatchedRollout(env, G.GaussianPolicy(10, 2).cuda(), G.DeviceReplay(512 * 10 * 4, 10, 2), precision="fused")
+    ro.reset()
+    ro.run(20)
+    assert len(ro.replay) == 512 * 10 * 4 and ro.action.abs().max().item() <= 1.0 and bool(torch.isfinite(env.obs).all())

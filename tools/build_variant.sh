@@ -7,5 +7,5 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 mkdir -p "$root/build/variants"
 cd "$root/gym_uav_collision_avoidance_b200/csrc"
 /usr/local/cuda/bin/nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC "$@" \
-  -shared -o "$root/build/variants/libuavca_$name.so" uavca_kernels.cu uavca_capi.cu
+  -shared -o "$root/build/variants/libuavca_$name.so" uavca_kernels.cu uavca_policy.cu uavca_capi.cu
 echo "$root/build/variants/libuavca_$name.so"

@@ -43,18 +43,19 @@ def timed(fn, n_graph=50):
     return best
 
 
-env = G.BatchedMultiUAVWorld2D(B, num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=1500, seed=0x5EED)
-policy = G.GaussianPolicy(10, 2).to(dev)
-replay = G.DeviceReplay(min(B * N * 16, 4_000_000), 10, 2, device=dev)
-ro = G.BatchedRollout(env, policy, replay, action_mode="polar")
-ro.reset()
-t_all = timed(ro.step)
-t_act = timed(ro._act)
-t_env = timed(ro._env_step)
-t_push = timed(lambda: replay.push(ro.state, ro.action, env.reward, env.final_obs, env.done))
-sr, cr, eps = ro.success_collision_rates()
-print(json.dumps({
-    "workload": f"SAC-style rollout, B={B} envs x N={N} UAVs, policy 10-256-256-2 fp32 (random init), polar map fused, device replay",
-    "us_per_step": t_all, "env_steps_per_s": B / t_all * 1e6, "uav_steps_per_s": B * N / t_all * 1e6,
-    "split_us": {"policy_forward_and_sample": t_act, "env_step_kernel": t_env, "replay_push_kernel": t_push},
-    "episodes": eps, "SR": sr, "CR": cr}))
+for precision in ("fp32", "tf32", "bf16", "fused"):
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=1500, seed=0x5EED)
+    policy = G.GaussianPolicy(10, 2).to(dev)
+    replay = G.DeviceReplay(min(B * N * 16, 4_000_000), 10, 2, device=dev)
+    ro = G.BatchedRollout(env, policy, replay, action_mode="polar", precision=precision)
+    ro.reset()
+    t_all = timed(ro.step)
+    t_act = timed(ro._act)
+    t_env = timed(ro._env_step)
+    t_push = timed(lambda: replay.push(ro.state, ro.action, env.reward, env.final_obs, env.done))
+    sr, cr, eps = ro.success_collision_rates()
+    print(json.dumps({
+        "workload": f"SAC-style rollout, B={B} envs x N={N} UAVs, policy 10-256-256-2 {precision} (random init), polar map fused, device replay",
+        "us_per_step": t_all, "env_steps_per_s": B / t_all * 1e6, "uav_steps_per_s": B * N / t_all * 1e6,
+        "split_us": {"policy_forward_and_sample": t_act, "env_step_kernel": t_env, "replay_push_kernel": t_push},
+        "episodes": eps, "SR": sr, "CR": cr}), flush=True)
