@@ -6,8 +6,9 @@
 //   reset_*/observe_*   standalone reset() and _get_obs()
 //
 // One pass over HBM per step: every state field and every output is read/written exactly once with coalesced,
-// streaming accesses; neighbour interaction stays in registers (warp shuffles).  No tensor cores: there is no
-// dense contraction anywhere in the step.
+// streaming accesses; neighbour interaction stays on chip (per-warp shared-memory ring, uavca_multi.cuh).  No tensor
+// cores: there is no dense contraction anywhere in the step.  (The fused policy kernel, which is GEMM-shaped, lives
+// in uavca_policy.cu.)
 #include "uavca_host.h"
 #include "uavca_multi.cuh"
 #include "uavca_tma.cuh"
