@@ -41,7 +41,7 @@ def make_env(cfg: O.Config, **kw):
     return G.BatchedMultiUAVWorld2D(cfg.num_envs, x_size=cfg.x_size, y_size=cfg.y_size, max_speed=cfg.max_speed,
                                     max_acceleration=cfg.max_acceleration, num_agents=cfg.num_agents,
                                     collider_radius=cfg.collider_radius, d_sense=cfg.d_sense,
-                                    circular=bool(cfg.circular), **common)
+                                    hard_collision_radius=cfg.hard_collision_radius, circular=bool(cfg.circular), **common)
 
 
 def load_state(blob, st: O.State):
@@ -202,6 +202,23 @@ def test_multi_c3_full_batch_short():
 def test_multi_n32_rollout():
     cfg = O.multi_config(4096, 32, reset_mode=O.RESET_ON_DONE0, max_episode_steps=100, seed=32)
     rollout_vs_oracle(cfg, steps=150, seed=6, check_every=3)
+
+
+@pytest.mark.parametrize("trial", range(16))
+def test_multi_rollout_random_constructor_arguments(trial):
+    """Non-default worlds: box, speed / acceleration bounds, collider and hard-collision radii and sensing range drawn
+    at random (including a sensing range shorter than the collision distance).  Every threshold the kernel tests in
+    squared-distance space is derived on the host from these; the oracle uses the reference's own comparisons."""
+    rng = np.random.default_rng(7000 + trial)
+    n = int(rng.choice([2, 3, 5, 8, 11, 16, 32]))
+    r = float(rng.uniform(0.3, 3.0))
+    kw = dict(x_size=float(rng.uniform(8, 120)), y_size=float(rng.uniform(8, 120)), max_speed=float(rng.uniform(2, 30)),
+              max_acceleration=float(rng.uniform(1, 20)), collider_radius=r,
+              hard_collision_radius=float(rng.uniform(0.1, 1.0) * r),
+              d_sense=float(rng.choice([rng.uniform(0.5, 2.0) * r, rng.uniform(5, 60)])))
+    cfg = O.multi_config(300, n, reset_mode=O.RESET_ON_DONE0, max_episode_steps=80, seed=trial, **kw)
+    ev, _ = rollout_vs_oracle(cfg, steps=100, seed=trial, crowd=float(rng.choice([0.0, 0.5, 1.5])) or None, check_every=2)
+    assert ev["resets"] > 0
 
 
 def test_multi_c4_full_size_properties_and_window():
