@@ -204,6 +204,9 @@ def run_ours(args, wl, rank, world, local_rank):
     # ring of independent batches: combined footprint > 3x L2 so that every launch streams from HBM
     per_batch = units_per_step * footprint_bytes_per_unit(kind)
     ring = max(1, int(-(-3.2 * L2_BYTES // per_batch)))
+    S = max(1, min(args.streams, ring))
+    if ring > 1 and ring % S:
+        ring += S - ring % S  # every stream serves the same number of batches (no idle stream at the end of a ring cycle)
     amax = 12.0 if kind == "single" else 10.0
     envs = []
     for r in range(ring):
@@ -224,7 +227,6 @@ def run_ours(args, wl, rank, world, local_rank):
     # The batches of the ring are independent environments: like a double-buffered env pool they are pipelined over
     # `S` streams, so that one batch's ramp-up overlaps the previous batch's tail.  A batch always runs on the same
     # stream (its own steps stay ordered).  S=1 (--streams 1) serialises every launch behind the previous one.
-    S = max(1, min(args.streams, ring))
 
     # warm-up (eager), then capture graphs of GRAPH_STEPS steps and of the remainder
     for k in range(W):
