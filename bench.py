@@ -179,7 +179,7 @@ def run_reference(args, wl, rank, world):
         "e2e": {"value": ups, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- GPU side ---------------------------------------------------------------------------------------------------
@@ -379,9 +379,28 @@ def run_ours(args, wl, rank, world, local_rank):
             "clocks": clocks.summary(),
             "episode_stats": stats,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries print there too (NCCL announces its version on stdout at
+    init): point fd 1 at stderr for the whole run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -395,6 +414,7 @@ def main():
     ap.add_argument("--streams", type=int, default=None,
                     help="streams the independent batches of the ring are pipelined over (default: 2; 4 for the small c2/c5 batches)")
     args = ap.parse_args()
+    protect_stdout()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -412,7 +432,7 @@ def main():
 
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29513", os.path.abspath(__file__)] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))  # the ranks inherit the REAL stdout
     run_ours(args, wl, rank, world, local_rank)
 
 
