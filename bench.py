@@ -35,6 +35,8 @@ WORKLOADS = {
     "c3": dict(kind="multi", N=8, B=65536, desc="multi-UAV N=8, B=65,536 envs/GPU (BASELINE configs[2])", steps=20000),
     "c2": dict(kind="single", N=1, B=65536, desc="single-UAV, B=65,536 envs/GPU (BASELINE configs[1])", steps=20000, streams=4),
     "c4": dict(kind="multi", N=32, B=1048576, desc="multi-UAV N=32, B=1,048,576 envs/GPU (BASELINE configs[3] shape)", steps=300),
+    "c4s": dict(kind="multi", N=32, B=1048576, desc="multi-UAV N=32, B=1,048,576 envs IN TOTAL, sharded over the GPUs (BASELINE configs[3])",
+                steps=300, shard_total=True),
     "c5": dict(kind="multi", N=10, B=16384, desc="multi-UAV N=10, B=16,384 envs/GPU (BASELINE configs[4] env part)", steps=20000, streams=4),
 }
 L2_BYTES = 126e6
@@ -199,6 +201,10 @@ def run_ours(args, wl, rank, world, local_rank):
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
     kind, N, B = wl["kind"], wl["N"], wl["B"]
+    if wl.get("shard_total"):  # strong scaling: the named total is cut into contiguous shards
+        from gym_uav_collision_avoidance_b200 import sharding as _sh
+
+        B = _sh.shard_range(wl["B"], rank, world)[1]
     K, W = args.steps, max(args.warmup, 3)
     units_per_step = B * N
     # ring of independent batches: combined footprint > 3x L2 so that every launch streams from HBM
@@ -358,7 +364,7 @@ def run_ours(args, wl, rank, world, local_rank):
                 traffic = json.load(f).get(args.workload)
         line = {
             "metric": "UAV env-steps/sec", "value": value, "unit": "UAV env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if wl.get("shard_total") else "weak", "vs_baseline": None,
             "dtype": "f64 velocity / f32 position+obs (as the reference)", "data": "synthetic",
             "config": {"workload": wl["desc"], "envs_per_gpu": B, "uavs_per_env": N, "env_steps_per_s": value / N,
                        "actions": "uniform random cartesian, resident in HBM", "auto_reset": "on-device Philox, dones[0] or 1500 steps",

@@ -36,4 +36,4 @@ def test_algorithmic_bytes_follow_the_survey():
     assert bench.algorithmic_bytes_per_unit("multi", 8) == 110.0       # 41 read + 66 written + 24/N counters
     assert bench.algorithmic_bytes_per_unit("multi", 32) == 107.75
     assert bench.algorithmic_bytes_per_unit("single", 1) == 89.0
-    assert set(bench.WORKLOADS) == {"c2", "c3", "c4", "c5"} and bench.WORKLOADS["c3"]["B"] == 65536 and bench.WORKLOADS["c3"]["N"] == 8
+    assert set(bench.WORKLOADS) == {"c2", "c3", "c4", "c4s", "c5"} and bench.WORKLOADS["c3"]["B"] == 65536 and bench.WORKLOADS["c3"]["N"] == 8
