@@ -80,6 +80,10 @@ class StateBlob:
 
 class _BatchedBase:
     kind: int = KIND_MULTI
+    # step() reaches the C-ABI either through the registered PyTorch custom ops (`ops.py`: what torch.compile traces,
+    # ~27 us of Python dispatch per call) or, in plain eager code, by calling the same entry point directly
+    # (~8 us per call).  Set to True to force the custom-op route everywhere.
+    use_custom_ops: bool = False
 
     def __init__(self, num_envs: int, num_agents: int, cfg: _capi.Config, device=None):
         if not torch.cuda.is_available():
@@ -106,6 +110,14 @@ class _BatchedBase:
         self.final_obs: Optional[torch.Tensor] = None
         self.reset_mask = torch.zeros(B, dtype=torch.uint8, device=self.device)
         self._stats = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self._ptrs = (self.state.blob.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                      self.reset_mask.data_ptr())
+
+    def _direct(self) -> bool:
+        return not (self.use_custom_ops or torch.compiler.is_compiling())
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     # -- lifetime -----------------------------------------------------------------------------------------------
     def close(self):
@@ -212,8 +224,16 @@ class BatchedMultiUAVWorld2D(_BatchedBase):
     def step(self, action: torch.Tensor, evaluate: bool = False, action_mode="cartesian"):
         """action [B,N,2] float32 CUDA -> (obs [B,N,10], reward [B,N], done [B,N] uint8, info)."""
         action = self._check_action(action)
-        ops.step_multi(self._h, self.state.blob, action, _ACTION_MODES[action_mode], bool(evaluate), self.obs,
-                       self.reward, self.done, self.final_obs, self.reset_mask)
+        if self._direct():
+            sp, op, rp, dp, mp = self._ptrs
+            fp = None if self.final_obs is None else self.final_obs.data_ptr()
+            rc = self._lib.uavca_step_multi(self._h, sp, action.data_ptr(), _ACTION_MODES[action_mode], int(bool(evaluate)),
+                                            op, rp, dp, fp, mp, self._stream())
+            if rc:
+                _capi.check(rc, "uavca_step_multi")
+        else:
+            ops.step_multi(self._h, self.state.blob, action, _ACTION_MODES[action_mode], bool(evaluate), self.obs,
+                           self.reward, self.done, self.final_obs, self.reset_mask)
         info = {"distance": 0, "reset_mask": self.reset_mask}  # multi_uav_world_2d.py:111-114
         if self.final_obs is not None:
             info["final_obs"] = self.final_obs
@@ -252,8 +272,16 @@ class BatchedUAVWorld2D(_BatchedBase):
     def step(self, action: torch.Tensor, action_mode="cartesian"):
         """action [B,2] float32 CUDA -> (obs [B,1,4], reward [B,1], done [B,1] uint8, info)."""
         action = self._check_action(action)
-        ops.step_single(self._h, self.state.blob, action, _ACTION_MODES[action_mode], self.obs, self.reward, self.done,
-                        self.distance, self.final_obs, self.reset_mask)
+        if self._direct():
+            sp, op, rp, dp, mp = self._ptrs
+            fp = None if self.final_obs is None else self.final_obs.data_ptr()
+            rc = self._lib.uavca_step_single(self._h, sp, action.data_ptr(), _ACTION_MODES[action_mode], op, rp, dp,
+                                             self.distance.data_ptr(), fp, mp, self._stream())
+            if rc:
+                _capi.check(rc, "uavca_step_single")
+        else:
+            ops.step_single(self._h, self.state.blob, action, _ACTION_MODES[action_mode], self.obs, self.reward, self.done,
+                            self.distance, self.final_obs, self.reset_mask)
         info = {"distance": self.distance, "reset_mask": self.reset_mask}  # uav_world_2d.py:114-117
         if self.final_obs is not None:
             info["final_obs"] = self.final_obs

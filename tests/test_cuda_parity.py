@@ -525,6 +525,26 @@ def test_step_host_matches_device_step(kind, pinned):
     assert torch.equal(e1.state.blob, e2.state.blob)
 
 
+def test_custom_op_route_equals_the_direct_route():
+    """step() calls the C-ABI directly in eager code and through torch.ops.uavca.* when asked to (or under
+    torch.compile): same entry point, same results; the ops are registered with their mutation signatures."""
+    G = _b200()
+    for kind in ("multi", "single"):
+        mk = (lambda: G.BatchedMultiUAVWorld2D(3000, num_agents=6, seed=4, reset_mode=O.RESET_ON_DONE0, max_episode_steps=25)) \
+            if kind == "multi" else (lambda: G.BatchedUAVWorld2D(3000, seed=4, reset_mode=O.RESET_ON_ANY_DONE, max_episode_steps=25))
+        e1, e2 = mk(), mk()
+        e2.use_custom_ops = True
+        e1.enable_final_obs(); e2.enable_final_obs()
+        e1.reset(); e2.reset()
+        gen = torch.Generator(device="cuda").manual_seed(2)
+        for _ in range(40):
+            a = torch.rand((3000, e1.num_agents, 2), generator=gen, device="cuda") * 20 - 10
+            e1.step(a); e2.step(a)
+        assert torch.equal(e1.state.blob, e2.state.blob) and torch.equal(e1.obs, e2.obs) and torch.equal(e1.final_obs, e2.final_obs)
+        assert torch.equal(e1.reward, e2.reward) and torch.equal(e1.done, e2.done) and torch.equal(e1.reset_mask, e2.reset_mask)
+    assert hasattr(torch.ops.uavca, "step_multi") and hasattr(torch.ops.uavca, "step_single") and hasattr(torch.ops.uavca, "policy_act")
+
+
 def test_step_in_cuda_graph():
     """The custom op captures into a CUDA graph (how bench.py and rollouts replay it)."""
     G = _b200()
