@@ -67,9 +67,10 @@ class FusedGaussianPolicy:
     """The acting path of a `GaussianPolicy` (10 -> 256 -> 256 -> 2+2) as ONE tcgen05 kernel (`uavca_policy_act`,
     csrc/uavca_policy.cu): both hidden layers on the tensor cores with the activations kept in shared memory / TMEM,
     output heads, tanh-Gaussian sampling (Philox noise) fused.  Operands are fp16 with fp32 accumulation.  Weights are
-    packed once from the module; call `refresh()` after the learner updated it (test_sac_multi.py:85-91)."""
+    packed once from the module; call `refresh()` after the learner updated it (test_sac_multi.py:85-91).  A TD3-style
+    deterministic actor (attributes l1, l2, l3: pytorch_td3_temp/td3.py:14-27) is accepted too: action = tanh(l3(...))."""
 
-    def __init__(self, policy: GaussianPolicy, seed: int = 0):
+    def __init__(self, policy: nn.Module, seed: int = 0):
         self.policy = policy
         self.seed = int(seed)
         self.calls = 0  # host-side offset of the Philox counter (set it to replay a draw)
@@ -81,8 +82,16 @@ class FusedGaussianPolicy:
     @torch.no_grad()
     def refresh(self):
         p = self.policy
-        w1, w2 = p.linear1.weight, p.linear2.weight
-        if tuple(w1.shape) != (256, 10) or tuple(w2.shape) != (256, 256) or p.mean_linear.weight.shape[0] != 2:
+        if hasattr(p, "l1") and hasattr(p, "l3"):
+            # deterministic TD3-style actor (pytorch_td3_temp/td3.py:14-27: l1, l2, l3, tanh): the same kernel with the
+            # log_std head pinned at its floor (std = e^-20, the sampled term vanishes below fp32 resolution)
+            lin1, lin2, mean_w, mean_b = p.l1, p.l2, p.l3.weight, p.l3.bias
+            std_w, std_b = torch.zeros_like(mean_w), torch.full_like(mean_b, -20.0)
+        else:
+            lin1, lin2, mean_w, mean_b = p.linear1, p.linear2, p.mean_linear.weight, p.mean_linear.bias
+            std_w, std_b = p.log_std_linear.weight, p.log_std_linear.bias
+        w1, w2 = lin1.weight, lin2.weight
+        if tuple(w1.shape) != (256, 10) or tuple(w2.shape) != (256, 256) or mean_w.shape[0] != 2:
             raise ValueError("the fused acting kernel is built for the reference architecture 10 -> 256 -> 256 -> 2")
         if not w1.is_cuda:
             raise ValueError("the policy must live on a CUDA device")
@@ -90,16 +99,16 @@ class FusedGaussianPolicy:
         # fp16 K-major operands; every bias rides in an extra input column (include/uavca.h)
         self.w1 = torch.zeros((256, 16), dtype=h, device=dev)
         self.w1[:, :10] = w1.to(h)
-        self.w1[:, 10] = p.linear1.bias.to(h)
+        self.w1[:, 10] = lin1.bias.to(h)
         self.w2 = w2.to(h).contiguous()
         self.w2b = torch.zeros((256, 16), dtype=h, device=dev)
-        self.w2b[:, 0] = p.linear2.bias.to(h)
+        self.w2b[:, 0] = lin2.bias.to(h)
         self.w3 = torch.zeros((16, 256), dtype=h, device=dev)
-        self.w3[0:2] = p.mean_linear.weight.to(h)
-        self.w3[2:4] = p.log_std_linear.weight.to(h)
+        self.w3[0:2] = mean_w.to(h)
+        self.w3[2:4] = std_w.to(h)
         self.w3b = torch.zeros((16, 16), dtype=h, device=dev)
-        self.w3b[0:2, 0] = p.mean_linear.bias.to(h)
-        self.w3b[2:4, 0] = p.log_std_linear.bias.to(h)
+        self.w3b[0:2, 0] = mean_b.to(h)
+        self.w3b[2:4, 0] = std_b.to(h)
 
     def act(self, state: torch.Tensor, evaluate: bool = False, out: Optional[torch.Tensor] = None,
             noise: Optional[torch.Tensor] = None, head: Optional[torch.Tensor] = None) -> torch.Tensor:

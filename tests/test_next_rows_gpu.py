@@ -272,3 +272,27 @@ def test_rollout_with_the_fused_policy():
     ro.reset()
     ro.run(20)
     assert len(ro.replay) == 512 * 10 * 4 and ro.action.abs().max().item() <= 1.0 and bool(torch.isfinite(env.obs).all())
+
+
+def test_fused_policy_accepts_a_td3_style_deterministic_actor():
+    """pytorch_td3_temp/td3.py:14-27 — l1 10->256, l2 256->256, l3 256->2, tanh — through the same tcgen05 kernel."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    import gym_uav_collision_avoidance_b200 as G
+
+    class Actor(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l1, self.l2, self.l3 = nn.Linear(10, 256), nn.Linear(256, 256), nn.Linear(256, 2)
+
+        def forward(self, s):
+            return torch.tanh(self.l3(F.relu(self.l2(F.relu(self.l1(s))))))
+
+    torch.manual_seed(5)
+    actor = Actor().cuda()
+    f = G.FusedGaussianPolicy(actor)
+    obs = torch.rand(5000, 10, device="cuda") * 2 - 1
+    with torch.no_grad():
+        ref = actor(obs)
+    a0, a1 = f.act(obs).clone(), f.act(obs).clone()
+    assert (a0 - ref).abs().max().item() < 5e-3 and (a0 - a1).abs().max().item() < 1e-6  # deterministic up to e^-20 noise
