@@ -131,6 +131,23 @@ class _BatchedBase:
         except Exception:
             pass
 
+    # -- checkpointing ---------------------------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        """Everything needed to resume bit-identically: the SoA state blob (positions, velocities, targets, latches,
+        counters, Philox episode counters, running totals) and the constructor configuration.  The reference never
+        checkpoints its environments; with counter-based RNG the blob IS the whole state."""
+        cfg = {name: getattr(self.cfg, name) for name, _ in self.cfg._fields_}
+        return {"config": cfg, "blob": self.state.blob.cpu().clone(), "obs": self.obs.cpu().clone()}
+
+    def load_state_dict(self, sd: dict) -> None:
+        for k, v in sd["config"].items():
+            if k != "env_index_base" and getattr(self.cfg, k) != v:
+                raise ValueError(f"checkpoint was taken with {k}={v}, this env has {getattr(self.cfg, k)}")
+        if sd["blob"].numel() != self.state.blob.numel():
+            raise ValueError("checkpoint holds a different number of environments / agents")
+        self.state.blob.copy_(sd["blob"])
+        self.obs.copy_(sd["obs"])
+
     # -- reset pool (host-supplied reset states) -----------------------------------------------------------------
     def make_pool(self, pool_envs: int) -> StateBlob:
         lay = _capi.Layout()

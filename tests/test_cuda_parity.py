@@ -545,6 +545,29 @@ def test_custom_op_route_equals_the_direct_route():
     assert hasattr(torch.ops.uavca, "step_multi") and hasattr(torch.ops.uavca, "step_single") and hasattr(torch.ops.uavca, "policy_act")
 
 
+def test_checkpoint_resume_is_bit_identical():
+    G = _b200()
+    mk = lambda: G.BatchedMultiUAVWorld2D(2000, num_agents=9, seed=12, reset_mode=O.RESET_ON_DONE0, max_episode_steps=15)  # noqa: E731
+    env = mk()
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    acts = [torch.rand((2000, 9, 2), generator=gen, device="cuda") * 20 - 10 for _ in range(40)]
+    for a in acts[:20]:
+        env.step(a)
+    sd = env.state_dict()
+    for a in acts[20:]:
+        env.step(a)
+    final_blob, final_obs = env.state.blob.clone(), env.obs.clone()
+    fresh = mk()  # a new handle: nothing but the checkpoint carries over (auto-resets keep drawing the same episodes)
+    fresh.load_state_dict(sd)
+    assert torch.equal(fresh.obs, torch.as_tensor(sd["obs"]).cuda())
+    for a in acts[20:]:
+        fresh.step(a)
+    assert torch.equal(fresh.state.blob, final_blob) and torch.equal(fresh.obs, final_obs)
+    with pytest.raises(ValueError):
+        G.BatchedMultiUAVWorld2D(2000, num_agents=9, seed=13).load_state_dict(sd)
+
+
 def test_step_in_cuda_graph():
     """The custom op captures into a CUDA graph (how bench.py and rollouts replay it)."""
     G = _b200()
