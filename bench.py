@@ -380,7 +380,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_unit": alg,
                          "units_per_launch": units_per_step, "launch_us": launch_s * 1e6,
-                         "launch_us_is": "timed region / launches" + (f" ({S} independent launches in flight)" if S > 1 else "")},
+                         "launch_us_is": "timed region / launches" + (f" ({S} independent launches in flight)" if S > 1 else ""),
+                         "frac_single_stream": (units_per_step * alg / (serial_us * 1e-6) / 1e9 / peak) if serial_us else None},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
             "episode_stats": stats,
