@@ -91,6 +91,14 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = os.environ.get("UAVCA_LIB") or LIB_PATH  # override: kernel-variant experiments only
+    if path == LIB_PATH and not os.path.exists(path):
+        # a fresh checkout (built artefacts are git-ignored): compile the product once, loudly, or fail below
+        try:
+            from . import build as _build
+
+            _build.build()
+        except Exception as exc:  # nvcc missing / compile error: no fallback of any kind
+            raise UavcaError(f"{path} is missing and could not be built ({exc}).  This package has no CPU fallback.") from exc
     if not os.path.exists(path):
         raise UavcaError(
             f"{path} is missing: build the CUDA extension first (python -m gym_uav_collision_avoidance_b200.build "
