@@ -382,6 +382,58 @@ def test_neighbour_order_across_the_key_granularity(n, spread):
     assert np.array_equal(env.done.cpu().numpy(), out["done"])
 
 
+def test_crafted_corner_states_match_the_oracle():
+    """Hand-built states for the reference's quirks: zero velocity (heading atan2(0,0) = 0), a UAV exactly
+    on its target, denormal-tiny velocities, parked UAVs earning +10 and being hit by a neighbour, out-of-bounds UAVs
+    that fly back in (done is not latched), UAVs with no neighbour in sensing range, evaluate=True."""
+    N = 3
+    scen = []
+
+    def add(pos, vel, tgt, flags=(0, 0, 0), act=((0, 0),) * 3):
+        scen.append(dict(pos=pos, vel=vel, tgt=tgt, flags=flags, act=act))
+
+    far = [(-20.0, -20.0), (20.0, 20.0), (-20.0, 20.0)]  # nobody senses anybody (d_sense = 15)
+    add(far, [(0, 0)] * 3, [(5, 5), (-5, -5), (0, 0)])                                   # zero velocity, zero action
+    add(far, [(0, 0)] * 3, far, act=((1, 0), (0, 0), (-3, 2)))                            # sitting exactly on the target
+    add(far, [(1e-40, 0), (0, -1e-39), (1e-41, 1e-41)], [(5, 5), (-5, -5), (0, 0)], act=((1e-40, 0), (0, -1e-39), (1e-41, 1e-41)))
+    add([(0.1, 0.0), (1.5, 0.0), (20, 20)], [(0.05, 0), (-3, 0), (0, 0)], [(0.0, 0.0), (-10, 0), (0, 0)],
+        flags=(1, 0, 0), act=((0, 0), (-10, 0), (0, 0)))                                  # parked UAV 0 gets hit by UAV 1
+    add([(0.2, 0.1), (10, 10), (-10, 5)], [(0.1, 0.05), (0, 0), (0, 0)], [(0.0, 0.0), (0, 0), (0, 0)],
+        act=((0, 0), (1, 1), (0, 0)))                                                     # UAV 0 reaches: slow and close
+    add([(25.05, 0.0), (-25.2, 3.0), (0.0, 25.0)], [(-8, 0), (9, 0), (0, 5)], [(0, 0)] * 3,
+        act=((-10, 0), (10, 0), (0, 10)))                                                 # outside flying in / on the edge flying out
+    add([(0, 0), (1.0, 0.0), (0.0, 0.99)], [(0, 0)] * 3, [(9, 9), (-9, 9), (9, -9)], flags=(0, 2, 0))  # hard collisions, latch set on UAV 1
+    add([(0, 0), (14.99, 0.0), (0.0, 15.0)], [(0, 0)] * 3, [(9, 9), (-9, 9), (9, -9)])     # sensing range: just inside / exactly on it
+    B = len(scen)
+    for evaluate in (False, True):
+        cfg = O.multi_config(B, N, seed=1)
+        st = O.State(B, N)
+        for b, sc in enumerate(scen):
+            st.pos[b] = np.asarray(sc["pos"], np.float32)
+            st.vel[b] = np.asarray(sc["vel"], np.float64)
+            st.tgt[b] = np.asarray(sc["tgt"], np.float32)
+            st.flags[b] = np.asarray(sc["flags"], np.uint8)
+        d = st.tgt - st.pos
+        st.init[...] = np.maximum(np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1], dtype=np.float32), np.float32(3.0))
+        st.prev[...] = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1], dtype=np.float32)
+        st.prev[st.flags & 1 == 1] = 0.0
+        env = make_env(cfg)
+        orc = O.Oracle(cfg)
+        orc.state = st.copy()
+        load_state(env.state, st)
+        obs0 = env.observe().cpu().numpy()
+        assert obs_close(obs0, orc.observe(), RTOL, ATOL).all(), "observation of the crafted states"
+        act = torch.tensor([sc["act"] for sc in scen], dtype=torch.float32, device="cuda")
+        for t in range(4):
+            env.step(act, evaluate=evaluate)
+            out = orc.step(act.cpu().numpy(), evaluate=evaluate)
+            assert_outputs(env, out, f"(crafted, evaluate={evaluate}, step {t})")
+            assert_state_equal(env, orc.state, f"(crafted, evaluate={evaluate}, step {t})")
+        if not evaluate:
+            assert out["done"][4, 0] == 1 and (orc.state.flags[4, 0] & 1)      # the slow, close UAV parked
+            assert (orc.state.flags[6] & 2).all() and orc.state.coll[6] >= 2   # hard collisions counted once per UAV
+
+
 # ---- reset ------------------------------------------------------------------------------------------------------
 
 
