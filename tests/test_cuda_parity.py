@@ -193,6 +193,35 @@ def test_multi_c3_1000_step_rollout_subset():
     assert int(orc.state.stats[0]) > 100, "the window should have gone through many episodes"
 
 
+def test_multi_c3_full_batch_1000_steps():
+    """The north-star criterion taken literally: BASELINE config 3 — ALL 65,536 envs x 8 UAVs — for 1,000 steps with
+    auto-reset, against the oracle on identical states and actions: done flags and reset masks bit-exact at every step,
+    positions / velocities / latches / counters bit-exact and rewards / observations within 1e-5 at checkpoints."""
+    G = _b200()
+    B, N = 65536, 8
+    kw = dict(reset_mode=O.RESET_ON_DONE0, max_episode_steps=400, seed=0xC3)
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=N, **kw)
+    orc = O.Oracle(O.multi_config(B, N, **kw), nthreads=O.max_threads())
+    env.reset()
+    orc.reset()
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    flagged = 0
+    for t in range(1000):
+        a = torch.rand((B, N, 2), generator=gen, device="cuda") * 20 - 10
+        obs, rew, done, info = env.step(a)
+        out = orc.step(a.cpu().numpy())
+        assert np.array_equal(done.cpu().numpy(), out["done"]), f"done flags differ at step {t}"
+        assert np.array_equal(info["reset_mask"].cpu().numpy(), out["reset_mask"]), f"reset mask differs at step {t}"
+        flagged += int(out["done"].sum())
+        if t % 50 == 49 or t < 3:
+            assert_state_equal(env, orc.state, f"(step {t})")
+            assert close(rew.cpu().numpy(), out["reward"]).all(), f"reward at step {t}"
+            assert obs_close(obs.cpu().numpy(), out["obs"], RTOL, ATOL).all(), f"observation at step {t}"
+    st = env.stats()
+    assert st["episodes"] == int(orc.state.stats[0]) > 2 * B and st["collisions"] == int(orc.state.stats[2]) > 0
+    assert flagged > 100000
+
+
 def test_multi_c3_full_batch_short():
     """All 65,536 envs of config 3 against the oracle for 30 steps."""
     cfg = O.multi_config(65536, 8, reset_mode=O.RESET_ON_DONE0, max_episode_steps=20, seed=9)
@@ -285,7 +314,7 @@ def test_single_rollout(f32):
 def test_single_1000_step_rollout():
     """BASELINE config 2 (single UAV, B=65,536) for 1,000 steps; oracle follows a 4,096-env window."""
     G = _b200()
-    B, W, START = 65536, 4096, 12345
+    B, W, START = 65536, 65536, 0  # BASELINE config 2, the whole batch
     kw = dict(reset_mode=O.RESET_ON_ANY_DONE, seed=77)
     env = G.BatchedUAVWorld2D(B, **kw)
     orc = O.Oracle(O.single_config(W, env_index_base=START, **kw), nthreads=8)
