@@ -296,3 +296,15 @@ def test_fused_policy_accepts_a_td3_style_deterministic_actor():
         ref = actor(obs)
     a0, a1 = f.act(obs).clone(), f.act(obs).clone()
     assert (a0 - ref).abs().max().item() < 5e-3 and (a0 - a1).abs().max().item() < 1e-6  # deterministic up to e^-20 noise
+
+
+def test_rollout_example_runs():
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "rollout_sac_multi.py")
+    spec = importlib.util.spec_from_file_location("rollout_sac_multi", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sr, cr, episodes = mod.main(["--envs", "256", "--agents", "10", "--steps", "30", "--warmup-steps", "5", "--eval-envs", "64"])
+    assert episodes >= 64 and 0.0 <= sr <= 1.0 and cr >= 0.0
