@@ -76,7 +76,10 @@ __device__ __forceinline__ Uav load_uav(const StateView& s, const Lane& L) {
     u.flags = ld_stream(s.flags + L.m);
     u.px = p.x; u.py = p.y; u.vx = v.x; u.vy = v.y; u.tx = t.x; u.ty = t.y;
   } else {
-    u.px = u.py = u.tx = u.ty = 0.f; u.init = u.prev = 1.f; u.vx = u.vy = 0.0; u.flags = 0u;
+    // idle lanes (32 is not a multiple of N, or the ragged end of a shard) carry a harmless UAV in ordinary flight:
+    // moving, 8 m from its target, inside the box.  A zero state would sit exactly on its target with zero velocity
+    // and drag the whole warp through the rare paths (double-precision angles, finish()) on every step.
+    u.px = u.py = u.ty = 0.f; u.tx = 8.f; u.init = u.prev = 8.f; u.vx = 1.0; u.vy = 0.0; u.flags = 0u;
   }
   return u;
 }
