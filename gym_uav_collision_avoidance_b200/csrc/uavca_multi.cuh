@@ -438,7 +438,7 @@ __device__ __forceinline__ void reset_multi(const KernelArgs& a, const Lane& L, 
 // ================================================================================================================
 
 // UAVAgent.finish (uav_agent.py:38-42): park at 1 mm/s along the current heading (NaN -> 0 for a zero velocity)
-static __device__ __noinline__ double2 finish_velocity(double vx, double vy, double vsq) {
+static __device__ __forceinline__ double2 finish_velocity(double vx, double vy, double vsq) {
   const double nv = sqrt(vsq);
   double fx = __dmul_rn(__ddiv_rn(vx, nv), 0.001), fy = __dmul_rn(__ddiv_rn(vy, nv), 0.001);
   if ((fx != fx) | (fy != fy)) { fx = 0.0; fy = 0.0; }
