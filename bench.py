@@ -374,8 +374,9 @@ def run_ours(args, wl, rank, world, local_rank):
                        "single_stream_us_per_step": serial_us},
             "e2e": {"value": e2e_value, "unit": "UAV env-steps/s", "h2d_bytes_per_step": units_per_step * 8,
                     "d2h_bytes_per_step": units_per_step * (D * 4 + 4 + 1), "steps": e2e_steps,
-                    "path": ("uavca_step_host, pinned host buffers: " + ("staged chunked H2D/step/D2H pipeline" if os.environ.get("UAVCA_HOST_PATH") == "staged"
-                                                                          else "zero-copy (the step kernel reads actions and writes obs/reward/done through PCIe, mapped host memory)"))},
+                    "path": "uavca_step_host, pinned host buffers: outputs >= 256 MB leave by DMA (chunked H2D/step/D2H pipeline over two "
+                            "streams), smaller batches are zero-copy (the kernel reads/writes mapped host memory through PCIe)"
+                            + (f" [forced: {os.environ['UAVCA_HOST_PATH']}]" if os.environ.get("UAVCA_HOST_PATH") else "")},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_unit": alg,

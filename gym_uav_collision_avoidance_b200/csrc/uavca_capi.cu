@@ -25,6 +25,7 @@ int fail_cuda(const char* what, cudaError_t e) {
 }
 
 constexpr size_t kAlign = 256;
+constexpr size_t kDmaThresholdBytes = 256u << 20;  // uavca_step_host: outputs at least this large leave by DMA (measured: 23 MB zero-copy 1.05e9 vs DMA 0.93e9 UAV-steps/s; 1.5 GB 1.12e9 vs 1.16e9)
 size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 void compute_layout(int B, int N, uavca_layout* L) {
@@ -162,7 +163,9 @@ struct uavca_handle {
   int path = UAVCA_PATH_LANES;  // UAVCA_STEP_PATH=tma in the environment selects the bulk (TMA) kernel for whole tiles (A/B measurements)
   // end-to-end (host buffer) path, created lazily
   static constexpr int kHostStreams = 3;
+  static constexpr int kChunks = 8;
   cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_done[kChunks] = {};
   float* d_action = nullptr;
   float* d_obs = nullptr;
   float* d_reward = nullptr;
@@ -282,6 +285,7 @@ int uavca_destroy(uavca_handle* h) {
   DeviceGuard g(h->device);
   if (h->ring) cudaFree(h->ring);
   for (auto& s : h->hs) if (s) cudaStreamDestroy(s);
+  for (auto& ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
   if (h->d_action) cudaFree(h->d_action);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_reward) cudaFree(h->d_reward);
@@ -438,11 +442,19 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
   };
-  const char* hp = std::getenv("UAVCA_HOST_PATH");
+  const char* hp = std::getenv("UAVCA_HOST_PATH");  // zerocopy | dma | staged: force one path (A/B measurements)
   const bool want_staged = hp && std::strcmp(hp, "staged") == 0;
   void *m_act = nullptr, *m_obs = nullptr, *m_rew = nullptr, *m_done = nullptr;
   if (!want_staged) { m_act = mapped(host_action); m_obs = mapped(host_obs); m_rew = mapped(host_reward); m_done = mapped(host_done); }
-  if (m_act && m_obs && m_rew && m_done) {
+  const bool pinned = m_act && m_obs && m_rew && m_done;
+  // Very large pinned batches: the copy engines stream hundreds of MB slightly faster (56 GB/s) than SM stores through
+  // PCIe (47-50 GB/s), so the outputs go to device staging and leave by DMA, chunked so that H2D(k+1), step(k) and
+  // D2H(k-1) overlap.  Everything smaller stays zero-copy: no copy-engine latency, no per-chunk overhead.
+  const size_t out_bytes = M * ((size_t)D * sizeof(float) + sizeof(float) + 1);
+  bool use_dma = pinned && out_bytes >= kDmaThresholdBytes;
+  if (hp && std::strcmp(hp, "dma") == 0) use_dma = pinned;
+  if (hp && std::strcmp(hp, "zerocopy") == 0) use_dma = false;
+  if (pinned && !use_dma) {
     KernelArgs a = make_args(h, state);
     a.io.action = reinterpret_cast<const float2*>(m_act);
     a.io.obs = reinterpret_cast<float*>(m_obs); a.io.reward = reinterpret_cast<float*>(m_rew);
@@ -456,14 +468,49 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail_cuda("stream synchronize", e);
     return 0;
   }
-  // Staged path (pageable host memory): chunk the env range so that H2D of chunk k+1, the step of chunk k and D2H of
-  // chunk k-1 overlap
   if (!h->d_action) {
     if ((e = cudaMalloc(&h->d_action, M * 2 * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_obs, M * D * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_reward, M * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_done, M)) != cudaSuccess) return fail_cuda("cudaMalloc", e);
+    for (auto& ev : h->chunk_done)
+      if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return fail_cuda("event create", e);
   }
+  if (use_dma) {
+    // stream 0: H2D(actions k) -> step(k) -> event k;  stream 1: wait event k -> D2H(obs k);  reward/done leave whole
+    constexpr int chunks = uavca_handle::kChunks;
+    long long per = ((long long)B + chunks - 1) / chunks;
+    per = (per + 63) / 64 * 64;  // keeps every chunk's rows 16-byte aligned for any N
+    cudaStream_t s_in = h->hs[0], s_out = h->hs[1];
+    int k = 0;
+    for (long long env0 = 0; env0 < B; env0 += per, ++k) {
+      const long long nb = (env0 + per <= B) ? per : (B - env0);
+      const size_t m0 = (size_t)env0 * N, mc = (size_t)nb * N;
+      if ((e = cudaMemcpyAsync(h->d_action + m0 * 2, host_action + m0 * 2, mc * 2 * sizeof(float), cudaMemcpyHostToDevice, s_in)) != cudaSuccess)
+        return fail_cuda("H2D action", e);
+      KernelArgs a = make_args(h, state);
+      a.s = offset_view(a.s, env0, N);
+      a.c.env_base += env0;
+      a.B = (int)nb;
+      a.io.action = reinterpret_cast<const float2*>(h->d_action + m0 * 2);
+      a.io.obs = h->d_obs + m0 * D; a.io.reward = h->d_reward + m0; a.io.done = h->d_done + m0;
+      a.io.action_mode = action_mode; a.io.evaluate = evaluate;
+      int launched = 1;
+      e = h->cfg.kind == UAVCA_KIND_SINGLE ? launch_step_single(a, s_in) : launch_step_multi(a, s_in, &launched, h->path);
+      h->launches += launched;
+      if (e != cudaSuccess) return fail_cuda("uavca_step_host launch", e);
+      if ((e = cudaEventRecord(h->chunk_done[k], s_in)) != cudaSuccess) return fail_cuda("event record", e);
+      if ((e = cudaStreamWaitEvent(s_out, h->chunk_done[k], 0)) != cudaSuccess) return fail_cuda("stream wait", e);
+      if ((e = cudaMemcpyAsync(host_obs + m0 * D, h->d_obs + m0 * D, mc * D * sizeof(float), cudaMemcpyDeviceToHost, s_out)) != cudaSuccess)
+        return fail_cuda("D2H obs", e);
+    }
+    if ((e = cudaMemcpyAsync(host_reward, h->d_reward, M * sizeof(float), cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) return fail_cuda("D2H reward", e);
+    if ((e = cudaMemcpyAsync(host_done, h->d_done, M, cudaMemcpyDeviceToHost, s_out)) != cudaSuccess) return fail_cuda("D2H done", e);
+    if ((e = cudaStreamSynchronize(s_out)) != cudaSuccess) return fail_cuda("stream synchronize", e);
+    return 0;
+  }
+  // Staged path (pageable host memory): chunk the env range so that H2D of chunk k+1, the step of chunk k and D2H of
+  // chunk k-1 overlap
   int chunks = 8;
   long long per = ((long long)B + chunks - 1) / chunks;
   per = (per + 63) / 64 * 64;  // keeps every chunk's rows 16-byte aligned for any N

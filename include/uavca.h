@@ -150,8 +150,9 @@ int uavca_stats(uavca_handle* h, const void* state, int64_t* out8, void* stream)
 
 /* End-to-end form with HOST buffers; returns when the outputs are in host memory.  `state` stays on the
  * device.  Pinned (page-locked) buffers take the zero-copy path: one launch whose loads/stores go through
- * PCIe directly (mapped host memory).  Pageable buffers are staged: H2D actions, step, D2H obs/reward/done,
- * pipelined in chunks over internal streams.  Works for both kinds (obs_dim from the config). */
+ * PCIe directly (mapped host memory); outputs of 256 MB and more leave by DMA instead (chunked pipeline).
+ * Pageable buffers are staged: H2D actions, step, D2H obs/reward/done, pipelined in chunks over internal
+ * streams.  Works for both kinds (obs_dim from the config). */
 int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int action_mode, int evaluate,
                     float* host_obs, float* host_reward, uint8_t* host_done);
 
