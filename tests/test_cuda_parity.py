@@ -575,11 +575,14 @@ def test_action_modes(mode):
         assert np.allclose(orc.map_action(an, O.ACTION_POLAR if mode == "polar" else O.ACTION_SCALED), ref, rtol=1e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("pinned", [True, False, "dma"])
 @pytest.mark.parametrize("kind", ["multi", "single"])
-def test_step_host_matches_device_step(kind, pinned):
+def test_step_host_matches_device_step(kind, pinned, monkeypatch):
     """Host-buffer step: pinned buffers take the zero-copy path (the kernel reads/writes mapped host memory through
-    PCIe), pageable buffers the staged chunked-copy pipeline; both must equal the device-resident step."""
+    PCIe) or, for very large outputs (forced here), the DMA pipeline; pageable buffers the staged chunked-copy
+    pipeline; all must equal the device-resident step."""
+    if pinned == "dma":
+        monkeypatch.setenv("UAVCA_HOST_PATH", "dma")
     G = _b200()
     B = 5000
     pin = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
