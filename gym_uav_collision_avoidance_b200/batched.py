@@ -184,6 +184,19 @@ class _BatchedBase:
         return dict(episodes=v[0], reach=v[1], collisions=v[2], steps=v[3], live_reach=v[4], live_collisions=v[5],
                     live_steps=v[6], num_envs=v[7])
 
+    # the counters the reference keeps on the env object (multi_uav_world_2d.py:166-168), one value per env
+    @property
+    def steps(self) -> torch.Tensor:
+        return self.state.steps
+
+    @property
+    def target_reach_count(self) -> torch.Tensor:
+        return self.state.reach
+
+    @property
+    def collision_count(self) -> torch.Tensor:
+        return self.state.coll
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.uavca_launch_count(self._h))
