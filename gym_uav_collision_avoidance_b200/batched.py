@@ -207,7 +207,10 @@ class _BatchedBase:
             action = action.to(device=self.device, dtype=torch.float32)
         if action.numel() != B * N * 2:
             raise ValueError(f"action must hold {B}x{N}x2 values, got shape {tuple(action.shape)}")
-        return action.contiguous()
+        action = action.contiguous()
+        if action.data_ptr() % 16:  # a view into a larger buffer: the kernels read float2 / 16-byte units
+            action = action.clone()
+        return action
 
     def step_host(self, action: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor,
                   action_mode="cartesian", evaluate: bool = False):

@@ -198,6 +198,14 @@ KernelArgs make_args(const uavca_handle* h, void* state) {
 
 int check_handle(const uavca_handle* h) { return h ? 0 : fail(-1, "null handle"); }
 
+// the kernels move float2 / float4 / double2 units: reject pointers that would fault instead of launching
+bool misaligned(const void* p, uintptr_t a) { return p != nullptr && (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
+int check_step_alignment(const void* state, const void* action, const void* obs, const void* reward, const void* final_obs) {
+  if (misaligned(state, 16) || misaligned(action, 8) || misaligned(obs, 16) || misaligned(reward, 4) || misaligned(final_obs, 16))
+    return fail(-1, "misaligned buffer: state / obs / final_obs need 16-byte, action 8-byte, reward 4-byte alignment");
+  return 0;
+}
+
 int validate_config(const uavca_config& g) {
   if (g.kind != UAVCA_KIND_MULTI && g.kind != UAVCA_KIND_SINGLE) return fail(-1, "config.kind must be UAVCA_KIND_MULTI or UAVCA_KIND_SINGLE");
   if (g.num_envs <= 0) return fail(-1, "config.num_envs must be positive");
@@ -359,6 +367,7 @@ int uavca_step_multi(uavca_handle* h, void* state, const float* action, int acti
   if (int rc = check_handle(h)) return rc;
   if (h->cfg.kind != UAVCA_KIND_MULTI) return fail(-1, "uavca_step_multi on a single-UAV handle");
   if (!state || !action || !obs || !reward || !done) return fail(-1, "null argument");
+  if (int rc = check_step_alignment(state, action, obs, reward, final_obs)) return rc;
   if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
   if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
   DeviceGuard g(h->device);
@@ -378,6 +387,7 @@ int uavca_step_single(uavca_handle* h, void* state, const float* action, int act
   if (int rc = check_handle(h)) return rc;
   if (h->cfg.kind != UAVCA_KIND_SINGLE) return fail(-1, "uavca_step_single on a multi-UAV handle");
   if (!state || !action || !obs || !reward || !done) return fail(-1, "null argument");
+  if (int rc = check_step_alignment(state, action, obs, reward, final_obs)) return rc;
   if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
   if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
   DeviceGuard g(h->device);

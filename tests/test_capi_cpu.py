@@ -88,3 +88,11 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_misaligned_buffers_are_rejected_before_any_launch(capi):
+    """The argument checks of the step entry points run before the device is touched (a fake non-null handle would be
+    dereferenced, so this goes through null-handle / null-argument ordering only): null handle first."""
+    lib = capi.load()
+    assert lib.uavca_step_multi(None, 16, 16, 0, 0, 16, 16, 16, None, None, None) == -1
+    assert "null handle" in capi.last_error()

@@ -678,6 +678,21 @@ def test_step_in_cuda_graph():
     assert torch.equal(eager.state.blob, graphed.state.blob) and torch.equal(eager.obs, graphed.obs)
 
 
+def test_misaligned_tensors_are_rejected():
+    G = _b200()
+    from gym_uav_collision_avoidance_b200 import _capi
+
+    env = G.BatchedMultiUAVWorld2D(64, num_agents=5)
+    env.reset()
+    a = torch.zeros(64 * 5 * 2 + 1, device="cuda")[1:].view(64, 5, 2)  # 4-byte aligned only
+    assert a.data_ptr() % 8 == 4
+    rc = env._lib.uavca_step_multi(env._h, env.state.blob.data_ptr(), a.data_ptr(), 0, 0, env.obs.data_ptr(), env.reward.data_ptr(),
+                                   env.done.data_ptr(), None, None, None)
+    assert rc == -1 and "misaligned" in _capi.last_error()
+    env.step(a)  # ... while the class realigns such a view by copying it
+    assert env.steps.min().item() == 1
+
+
 def test_errors_are_loud():
     G = _b200()
     with pytest.raises(G.UavcaError):
