@@ -101,7 +101,7 @@ __device__ __forceinline__ void store_uav(const StateView& s, const Lane& L, con
 // Lane i reads slot i+k for k = 1..N-1, i.e. its ring neighbour j = (i+k) mod N, and receives as "a" exactly the
 // position the reference's sequential sweep would see — OLD for j > i (not moved yet), NEW for j < i — and as "n"
 // the NEW position, with no index arithmetic, no compare and no select.  A slot is laid out (a.x, n.x, a.y, n.y)
-// so that both squared distances come out of four packed FP32 instructions (FADD2/FMUL2) and two scalar adds.
+// so that both squared distances come out of five packed FP32 instructions (2 FADD2, 2 FFMA2 with a +0 addend, FADD2).
 struct WarpScratch {
   float4* ring;  // [64] per-env doubled rings, env e at offset 2*e*N
   float* th;     // [64] heading / pi, doubled the same way
