@@ -308,3 +308,38 @@ def test_rollout_example_runs():
     spec.loader.exec_module(mod)
     sr, cr, episodes = mod.main(["--envs", "256", "--agents", "10", "--steps", "30", "--warmup-steps", "5", "--eval-envs", "64"])
     assert episodes >= 64 and 0.0 <= sr <= 1.0 and cr >= 0.0
+
+
+def test_config5_rollout_env_parity_under_policy_actions():
+    """BASELINE config 5's shape (B=16,384 x N=10, actions from a PyTorch GaussianPolicy through the polar map, reset on
+    dones[0]): the env under policy-shaped actions against the oracle.  The polar map runs once on the device
+    (`map_action`); both sides then step on the same cartesian actions, so flags and state must be bit-exact; the
+    fused polar step must equal map + cartesian step bit for bit."""
+    import gym_uav_collision_avoidance_b200 as G
+    from oracle import oracle as O
+    from test_cuda_parity import assert_outputs, assert_state_equal
+
+    torch.manual_seed(4)
+    B, N = 16384, 10
+    kw = dict(reset_mode=O.RESET_ON_DONE0, max_episode_steps=120, seed=55)
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=N, **kw)
+    fused = G.BatchedMultiUAVWorld2D(B, num_agents=N, **kw)
+    orc = O.Oracle(O.multi_config(B, N, **kw), nthreads=O.max_threads())
+    policy = G.GaussianPolicy(10, 2).cuda()
+    obs = env.reset()
+    fused.reset()
+    orc.reset()
+    for t in range(200):
+        with torch.no_grad():
+            a = policy.act(obs.view(-1, 10)).view(B, N, 2).contiguous()
+        mapped = env.map_action(a, "polar")
+        obs, rew, done, info = env.step(mapped)
+        fused.step(a, action_mode="polar")
+        out = orc.step(mapped.cpu().numpy())
+        assert np.array_equal(done.cpu().numpy(), out["done"]), f"done flags differ at step {t}"
+        assert np.array_equal(info["reset_mask"].cpu().numpy(), out["reset_mask"]), f"reset mask differs at step {t}"
+        if t % 20 == 19:
+            assert_outputs(env, out, f"(config 5, step {t})")
+            assert_state_equal(env, orc.state, f"(config 5, step {t})")
+            assert torch.equal(fused.state.blob, env.state.blob) and torch.equal(fused.obs, env.obs)
+    assert env.stats()["episodes"] == int(orc.state.stats[0]) > B
