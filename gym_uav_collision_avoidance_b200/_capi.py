@@ -70,7 +70,12 @@ SYMBOLS = {
     "uavca_step_single": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "uavca_map_action": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "uavca_stats": (C.c_int, [_VP, _VP, _VP, _VP]),
-    "uavca_step_host": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP]),
+    "uavca_step_host": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
+    "uavca_rollout": (C.c_int, [_VP, _VP, C.c_int32, _VP, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _VP, _VP, _VP, _VP, _VP,
+                                _VP, _VP, _VP]),
+    "uavca_sample_actions": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, _VP]),
+    "uavca_replay_push_dev": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP,
+                                        C.c_int64, _VP, _VP]),
     "uavca_replay_push": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP,
                                     C.c_int64, C.c_int64, _VP]),
     "uavca_policy_act": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, C.c_uint64, C.c_uint64, _VP, _VP, _VP, _VP]),

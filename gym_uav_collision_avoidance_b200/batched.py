@@ -220,8 +220,63 @@ class _BatchedBase:
                 raise ValueError("step_host takes contiguous CPU tensors")
         _capi.check(self._lib.uavca_step_host(self._h, self.state.blob.data_ptr(), action.data_ptr(),
                                               _ACTION_MODES[action_mode], int(evaluate), obs.data_ptr(),
-                                              reward.data_ptr(), done.data_ptr()), "uavca_step_host")
+                                              reward.data_ptr(), done.data_ptr(), self._stream()), "uavca_step_host")
         return obs, reward, done
+
+    # -- K steps per launch ------------------------------------------------------------------------------------------
+    def sample_actions(self, step: int, action_seed: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The policy-space actions in [-1, 1)^2 that `rollout(actions=None)` draws at global step `step`
+        (`env.action_space.sample()` for every UAV, as a counter-based Philox stream)."""
+        if out is None:
+            out = torch.empty((self.num_envs, self.num_agents, 2), dtype=torch.float32, device=self.device)
+        ops.sample_actions(self._h, int(action_seed), int(step), out)
+        return out
+
+    def rollout(self, steps: int, actions: Optional[torch.Tensor] = None, action_mode="cartesian", evaluate: bool = False,
+                action_seed: int = 0, step0: int = 0, out: Optional[dict] = None, want_actions: bool = False,
+                want_final_obs: bool = False, want_reset_mask: bool = False, sync_last: bool = True) -> dict:
+        """`steps` consecutive env steps in ONE kernel launch — the reference's random-action driver loops
+        (run.py:10-16, run_multi.py:10-16: `env.step(env.action_space.sample())`, reset on done) or an open-loop
+        action block.  The env state stays in registers between the steps; only the per-step outputs stream out.
+
+        actions: [K, B, N, 2] float32 CUDA tensor in `action_mode`, or None: every UAV then draws uniform actions from
+        the Philox stream keyed by (action_seed, global env index, UAV, step0 + k); `action_mode="cartesian"` then spans
+        the whole action box (a * max_speed).  Returns a dict of [K, ...] tensors: obs, reward, done (+ actions,
+        final_obs, reset_mask, distance on request).  Pass the dict back as `out=` to reuse the buffers (CUDA graphs).
+        `self.obs` / `self.reward` / `self.done` receive the last step (`sync_last`).  Bit-identical to `steps` calls of
+        `step()` fed the same actions."""
+        K, B, N, D = int(steps), self.num_envs, self.num_agents, self.obs_dim
+        if K < 1:
+            raise ValueError("rollout needs steps >= 1")
+        if actions is not None:
+            if actions.device != self.device or actions.dtype != torch.float32:
+                actions = actions.to(device=self.device, dtype=torch.float32)
+            if actions.numel() != K * B * N * 2:
+                raise ValueError(f"actions must hold {K}x{B}x{N}x2 values, got shape {tuple(actions.shape)}")
+            actions = actions.contiguous()
+        if out is None:
+            kw = dict(device=self.device)
+            out = dict(obs=torch.empty((K, B, N, D), dtype=torch.float32, **kw),
+                       reward=torch.empty((K, B, N), dtype=torch.float32, **kw),
+                       done=torch.empty((K, B, N), dtype=torch.uint8, **kw))
+            if want_actions and actions is None:
+                out["actions"] = torch.empty((K, B, N, 2), dtype=torch.float32, **kw)
+            if want_final_obs:
+                out["final_obs"] = torch.empty((K, B, N, D), dtype=torch.float32, **kw)
+            if want_reset_mask:
+                out["reset_mask"] = torch.empty((K, B), dtype=torch.uint8, **kw)
+            if self.kind == KIND_SINGLE:
+                out["distance"] = torch.empty((K, B), dtype=torch.float32, **kw)
+        if out["obs"].shape[0] != K:
+            raise ValueError("the `out` buffers were made for a different number of steps")
+        ops.rollout(self._h, self.state.blob, K, actions, _ACTION_MODES[action_mode], bool(evaluate), int(action_seed),
+                    int(step0), out["obs"], out["reward"], out["done"], out.get("actions") if actions is None else None,
+                    out.get("final_obs"), out.get("reset_mask"), out.get("distance"))
+        if sync_last:  # keep the env object coherent: env.obs is what a policy acts on next
+            self.obs.copy_(out["obs"][-1])
+            self.reward.copy_(out["reward"][-1])
+            self.done.copy_(out["done"][-1])
+        return out
 
 
 class BatchedMultiUAVWorld2D(_BatchedBase):

@@ -139,6 +139,17 @@ Consts derive_consts(const uavca_config& g) {
   c.rs_all_off = (g.reset_mode & UAVCA_RESET_ON_ALL_DONE) ? 0u : 1u;
   c.steps_limit = g.max_episode_steps > 0 ? g.max_episode_steps : 0x7fffffff;
   c.key_mask = ~31;
+  {
+    // Pass A tests UAV j > i at its OLD position; a UAV moves at most ||(vmax, vmax)|| * tau per step (plus the float32
+    // rounding of its position), so only a UAV within `near` of lane i at the NEW positions can be within collision
+    // reach at the old one.  Keys at or below near_key mark such UAVs (conservative: margins of 1 % + 2 cm).
+    const double reach = std::sqrt((double)std::fmax(c.s_coll_le, c.s_hard_le));
+    const double near = (reach + c.vm2 * g.tau) * 1.01 + 0.02;
+    const float s = (float)(near * near);
+    int bits;
+    std::memcpy(&bits, &s, sizeof(bits));
+    c.near_key = bits | 31;
+  }
   c.reset_source = g.reset_source;
   c.circular = g.circular;
   c.single_f32_first_step = g.single_f32_first_step;
@@ -166,6 +177,7 @@ struct uavca_handle {
   static constexpr int kChunks = 8;
   cudaStream_t hs[kHostStreams] = {nullptr, nullptr, nullptr};
   cudaEvent_t chunk_done[kChunks] = {};
+  cudaEvent_t fork = nullptr;  // uavca_step_host: orders the internal streams after the caller's stream
   float* d_action = nullptr;
   float* d_obs = nullptr;
   float* d_reward = nullptr;
@@ -294,6 +306,7 @@ int uavca_destroy(uavca_handle* h) {
   if (h->ring) cudaFree(h->ring);
   for (auto& s : h->hs) if (s) cudaStreamDestroy(s);
   for (auto& ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
+  if (h->fork) cudaEventDestroy(h->fork);
   if (h->d_action) cudaFree(h->d_action);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_reward) cudaFree(h->d_reward);
@@ -425,7 +438,7 @@ int uavca_stats(uavca_handle* h, const void* state, int64_t* out8, void* stream)
 }
 
 int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int action_mode, int evaluate,
-                    float* host_obs, float* host_reward, uint8_t* host_done) {
+                    float* host_obs, float* host_reward, uint8_t* host_done, void* stream) {
   if (int rc = check_handle(h)) return rc;
   if (!state || !host_action || !host_obs || !host_reward || !host_done) return fail(-1, "null argument");
   if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
@@ -441,8 +454,12 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
       if (e != cudaSuccess) return fail_cuda("stream create", e);
     }
   }
-  // the caller's earlier work on `state` (any stream) must be visible before the internal streams touch it
-  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail_cuda("device synchronize", e);
+  // The call is ordered after the caller's earlier work on `stream` (like every other entry point): the zero-copy
+  // launch goes onto that stream itself, the copy pipelines fork their internal streams from an event recorded on it.
+  cudaStream_t caller = (cudaStream_t)stream;
+  if (!h->fork) {
+    if ((e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming)) != cudaSuccess) return fail_cuda("event create", e);
+  }
   // Zero-copy path: when all four host buffers are pinned (page-locked, hence mapped into the device's address
   // space under UVA) the step kernel reads the actions and writes obs/reward/done THROUGH PCIe itself — one launch,
   // no staging copies, the stores stream out as posted writes while the SMs work on the next warps.
@@ -470,7 +487,7 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
     a.io.obs = reinterpret_cast<float*>(m_obs); a.io.reward = reinterpret_cast<float*>(m_rew);
     a.io.done = reinterpret_cast<uint8_t*>(m_done);
     a.io.action_mode = action_mode; a.io.evaluate = evaluate;
-    cudaStream_t st = h->hs[0];
+    cudaStream_t st = caller;
     int launched = 1;
     e = h->cfg.kind == UAVCA_KIND_SINGLE ? launch_step_single(a, st) : launch_step_multi(a, st, &launched, h->path);
     h->launches += launched;
@@ -478,6 +495,9 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail_cuda("stream synchronize", e);
     return 0;
   }
+  if ((e = cudaEventRecord(h->fork, caller)) != cudaSuccess) return fail_cuda("event record", e);
+  for (auto& s_ : h->hs)
+    if ((e = cudaStreamWaitEvent(s_, h->fork, 0)) != cudaSuccess) return fail_cuda("stream wait", e);
   if (!h->d_action) {
     if ((e = cudaMalloc(&h->d_action, M * 2 * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
     if ((e = cudaMalloc(&h->d_obs, M * D * sizeof(float))) != cudaSuccess) return fail_cuda("cudaMalloc", e);
@@ -554,18 +574,89 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
   return 0;
 }
 
-int uavca_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs, const uint8_t* done,
-                      int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs, float* ring_action, float* ring_reward,
-                      float* ring_next_obs, float* ring_mask, int64_t capacity, int64_t head, void* stream) {
+int uavca_rollout(uavca_handle* h, void* state, int32_t K, const float* action_block, int action_mode, int evaluate,
+                  uint64_t action_seed, uint64_t step0, float* obs, float* reward, uint8_t* done, float* action_out,
+                  float* final_obs, uint8_t* reset_mask, float* distance, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!state || !obs || !reward || !done) return fail(-1, "null argument");
+  if (K < 0) return fail(-1, "uavca_rollout: K must be >= 0");
+  if (int rc = check_step_alignment(state, action_block, obs, reward, final_obs)) return rc;
+  if (misaligned(action_out, 8)) return fail(-1, "misaligned buffer: action_out needs 8-byte alignment");
+  if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
+  if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
+  const bool single = h->cfg.kind == UAVCA_KIND_SINGLE;
+  const long long M = (long long)h->cfg.num_envs * h->cfg.num_agents;
+  // the [K][...] blocks must keep every step's rows aligned for the 16-byte observation stores
+  if (!single && (M * UAVCA_OBS_DIM_MULTI * sizeof(float)) % 16 != 0 && K > 1)
+    return fail(-1, "uavca_rollout: num_envs * num_agents * 10 floats must be a multiple of 16 bytes for K > 1");
+  DeviceGuard g(h->device);
+  KernelArgs a = make_args(h, state);
+  a.io.obs = obs; a.io.reward = reward; a.io.done = done; a.io.final_obs = final_obs; a.io.reset_mask = reset_mask;
+  a.io.distance = single ? distance : nullptr;
+  a.io.evaluate = evaluate;
+  // Philox actions are drawn in policy space [-1, 1)^2: "cartesian" then means the whole action box, a * max_speed
+  a.io.action_mode = (action_block == nullptr && action_mode == UAVCA_ACTION_CARTESIAN) ? UAVCA_ACTION_SCALED : action_mode;
+  RolloutArgs r{};
+  r.K = K;
+  r.action_block = reinterpret_cast<const float2*>(action_block);
+  r.action_out = reinterpret_cast<float2*>(action_out);
+  r.seed_lo = (unsigned)(action_seed & 0xffffffffull);
+  r.seed_hi = (unsigned)(action_seed >> 32);
+  r.step0 = step0;
+  r.M = M;
+  r.B = h->cfg.num_envs;
+  cudaError_t e = single ? launch_rollout_single(a, r, (cudaStream_t)stream) : launch_rollout_multi(a, r, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_rollout", e);
+  if (K > 0) h->launches += 1;
+  return 0;
+}
+
+int uavca_sample_actions(uavca_handle* h, uint64_t action_seed, uint64_t step, float* out, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!out) return fail(-1, "null argument");
+  if (misaligned(out, 8)) return fail(-1, "misaligned buffer: out needs 8-byte alignment");
+  DeviceGuard g(h->device);
+  cudaError_t e = launch_sample_actions(h->consts, out, h->cfg.num_envs, h->cfg.num_agents, action_seed, step, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_sample_actions", e);
+  h->launches += 1;
+  return 0;
+}
+
+static int replay_push_impl(const float* obs, const float* action, const float* reward, const float* next_obs, const uint8_t* done,
+                            int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs, float* ring_action, float* ring_reward,
+                            float* ring_next_obs, float* ring_mask, int64_t capacity, int64_t head, int64_t* meta, void* stream) {
   if (!obs || !action || !reward || !next_obs || !done || !ring_obs || !ring_action || !ring_reward || !ring_next_obs || !ring_mask)
     return fail(-1, "null argument");
   if (M < 0 || obs_dim <= 0 || act_dim <= 0 || capacity <= 0) return fail(-1, "bad sizes");
   if (M > capacity) return fail(-1, "uavca_replay_push: M exceeds the ring capacity");
   if (head < 0 || head >= capacity) return fail(-1, "uavca_replay_push: head out of range");
+  // the pointers decide the device (no handle here): launch where the ring lives, whatever the current device is
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, ring_obs) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return fail(-1, "uavca_replay_push: ring_obs is not a device pointer");
+  }
+  DeviceGuard g(at.device);
   cudaError_t e = launch_replay_push(obs, action, reward, next_obs, done, M, obs_dim, act_dim, ring_obs, ring_action,
-                                     ring_reward, ring_next_obs, ring_mask, capacity, head, (cudaStream_t)stream);
+                                     ring_reward, ring_next_obs, ring_mask, capacity, head,
+                                     reinterpret_cast<long long*>(meta), (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("uavca_replay_push", e);
   return 0;
+}
+
+int uavca_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs, const uint8_t* done,
+                      int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs, float* ring_action, float* ring_reward,
+                      float* ring_next_obs, float* ring_mask, int64_t capacity, int64_t head, void* stream) {
+  return replay_push_impl(obs, action, reward, next_obs, done, M, obs_dim, act_dim, ring_obs, ring_action, ring_reward,
+                          ring_next_obs, ring_mask, capacity, head, nullptr, stream);
+}
+
+int uavca_replay_push_dev(const float* obs, const float* action, const float* reward, const float* next_obs, const uint8_t* done,
+                          int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs, float* ring_action, float* ring_reward,
+                          float* ring_next_obs, float* ring_mask, int64_t capacity, int64_t* ring_meta, void* stream) {
+  if (!ring_meta) return fail(-1, "null argument");
+  return replay_push_impl(obs, action, reward, next_obs, done, M, obs_dim, act_dim, ring_obs, ring_action, ring_reward,
+                          ring_next_obs, ring_mask, capacity, 0, ring_meta, stream);
 }
 
 int uavca_policy_act(const float* obs, int64_t M, const void* w1, const void* w2, const void* w2b, const void* w3,
@@ -577,6 +668,12 @@ int uavca_policy_act(const float* obs, int64_t M, const void* w1, const void* w2
   if (!a16(w1) || !a16(w2) || !a16(w2b) || !a16(w3) || !a16(w3b) || (reinterpret_cast<uintptr_t>(obs) & 7u) ||
       (reinterpret_cast<uintptr_t>(action) & 7u) || (head && !a16(head)) || (noise && (reinterpret_cast<uintptr_t>(noise) & 7u)))
     return fail(-1, "uavca_policy_act: misaligned buffer (weights/head 16 bytes, obs/action/noise 8 bytes)");
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, obs) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return fail(-1, "uavca_policy_act: obs is not a device pointer");
+  }
+  DeviceGuard g(at.device);  // no handle here: the launch goes where the buffers live
   cudaError_t e = launch_policy_act(obs, M, w1, w2, w2b, w3, w3b, noise, seed, counter,
                                     reinterpret_cast<const unsigned long long*>(counter_dev), action, head, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail_cuda("uavca_policy_act", e);

@@ -26,7 +26,7 @@ constexpr int kMinBlocksPerSM = UAVCA_MINB;  // step kernel: caps registers per 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned kMaxResetAttempts = 4096u;  // the reference would loop forever in an over-crowded box
 
-enum : int { kStreamPos = 0, kStreamTgt = 1, kStreamVel = 2 };
+enum : int { kStreamPos = 0, kStreamTgt = 1, kStreamVel = 2, kStreamAct = 3 };
 
 // Constants derived once on the host from uavca_config (capi.cu: derive_consts).
 struct Consts {
@@ -55,6 +55,7 @@ struct Consts {
   unsigned rs_any_mask, rs_all_off;  // reset_mode as masks over an env's done bits (step_core)
   int steps_limit;                   // max_steps, or INT_MAX when there is no limit
   int key_mask;                      // ~31: distance-bits mask of the neighbour keys (pair_scan)
+  int near_key;                      // greatest key of a neighbour that may be within collision reach of pass A (neighbours())
   unsigned seed_lo, seed_hi;
   long long env_base;
 };
@@ -94,6 +95,18 @@ struct KernelArgs {
   const float4* ring;  // circular reset table [N]: (pos.x, pos.y, tgt.x, tgt.y), nullable
   StepIO io;
   int B, N;
+};
+
+// K steps in one launch (uavca_rollout): per-step outputs are [K][...] blocks, actions come from a [K][M][2] block or
+// from the counter-based Philox stream (run.py:10-16 / run_multi.py:10-16: env.step(env.action_space.sample())).
+struct RolloutArgs {
+  int K;
+  const float2* action_block;  // [K][M] or nullptr: Philox actions
+  float2* action_out;          // nullable [K][M]: the actions taken (policy space, before the action mapping)
+  unsigned seed_lo, seed_hi;   // Philox key of the action stream
+  unsigned long long step0;    // global index of step k = 0 (Philox counter word; the caller advances it by K)
+  long long M;                 // B * N of this launch (stride of one step in the blocks)
+  int B;
 };
 
 // ---- exact float32 / float64 primitives ------------------------------------------------------------------
@@ -299,6 +312,18 @@ __device__ __forceinline__ float2 draw_pair(const Consts& c, long long env_globa
   float x = __double2float_rn(__dadd_rn(lox, __dmul_rn(__dsub_rn(hix, lox), ux)));
   float y = __double2float_rn(__dadd_rn(loy, __dmul_rn(__dsub_rn(hiy, loy), uy)));
   return make_float2(x, y);
+}
+
+// Uniform random action in [-1, 1)^2 for (global env, UAV, global step t): one Philox call serves steps 2q and 2q+1.
+__device__ __forceinline__ uint4 action_words(unsigned seed_lo, unsigned seed_hi, long long env_global, int uav,
+                                              unsigned long long t) {
+  return philox4x32_10((uint32_t)env_global, (uint32_t)(t >> 1), ((uint32_t)kStreamAct << 16) | (uint32_t)uav,
+                       (uint32_t)(t >> 33), seed_lo, seed_hi);
+}
+__device__ __forceinline__ float2 action_from_words(const uint4& w, unsigned long long t) {
+  const uint32_t a = (t & 1ull) ? w.z : w.x, b = (t & 1ull) ? w.w : w.y;
+  // 24-bit uniforms in [0, 1): exact in float32, then one FMA to [-1, 1)
+  return make_float2(__fmaf_rn((float)(a >> 8), 2.0f / 16777216.0f, -1.0f), __fmaf_rn((float)(b >> 8), 2.0f / 16777216.0f, -1.0f));
 }
 
 // ---- streaming loads / stores ----------------------------------------------------------------------------------

@@ -11,6 +11,10 @@ namespace uavca {
 // ragged rest; UAVCA_PATH_LANES: per-lane kernel only).  *launched receives the number of kernels launched.
 enum : int { UAVCA_PATH_AUTO = 0, UAVCA_PATH_LANES = 1 };
 cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path);
+cudaError_t launch_rollout_multi(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st);
+cudaError_t launch_rollout_single(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st);
+cudaError_t launch_sample_actions(const Consts& c, float* out, int B, int N, unsigned long long seed, unsigned long long t,
+                                  cudaStream_t st);
 cudaError_t launch_reset_multi(const KernelArgs& a, const uint8_t* mask, cudaStream_t st);
 cudaError_t launch_observe_multi(const KernelArgs& a, cudaStream_t st);
 cudaError_t launch_step_single(const KernelArgs& a, cudaStream_t st);
@@ -21,7 +25,7 @@ cudaError_t launch_stats(const StateView& s, int B, long long* out8, cudaStream_
 cudaError_t launch_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs,
                                const uint8_t* done, long long M, int obs_dim, int act_dim, float* r_obs, float* r_act,
                                float* r_rew, float* r_next, float* r_mask, long long capacity, long long head,
-                               cudaStream_t st);
+                               long long* meta, cudaStream_t st);
 
 cudaError_t launch_policy_act(const float* obs, long long M, const void* w1, const void* w2, const void* w2b, const void* w3,
                               const void* w3b, const float* noise, unsigned long long seed, unsigned long long counter,

@@ -52,7 +52,12 @@ struct GlobalIO {
     st_stream(a.s.tgt + L.m, make_float2(u.tx, u.ty));
     st_stream(a.s.init + L.m, u.init);
   }
-  __device__ __forceinline__ void store_steps(int v) const { a.s.steps[L.env] = v; }
+  __device__ __forceinline__ void store_steps(int v, bool leader) const {
+    if (leader) a.s.steps[L.env] = v;
+  }
+  __device__ __forceinline__ void store_reset(bool rs) const {
+    if (a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
+  }
 };
 
 template <int NT>
@@ -74,6 +79,101 @@ __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_kernel(c
     GlobalIO io{a, L, ws.stage};
     step_core<NT>(a, ws, L, io);
   }
+}
+
+
+// ---- K steps per launch -------------------------------------------------------------------------------------------
+// I/O policy of step_core for uavca_rollout: the state of the warp's UAVs stays in REGISTERS for all K steps (loaded
+// once, stored once), only the per-step outputs stream out, as [K][...] blocks.  Removes the launch, ramp-up and tail
+// of K-1 dependent launches and 66 of the 107 algorithmic bytes per UAV-step (the state round trip and, with Philox
+// actions, the action read).  Runs the very same step_core as the one-step kernel, so the results are bit-identical
+// to K single steps.
+struct RolloutIO {
+  const KernelArgs& a;
+  const RolloutArgs& r;
+  const Lane& L;
+  float* stage;
+  Uav cur;
+  float2 act;
+  int steps;
+  int k;
+  __device__ __forceinline__ Uav load_uav() const { return cur; }
+  __device__ __forceinline__ float2 load_action() const { return act; }
+  __device__ __forceinline__ int load_steps() const { return steps; }
+  __device__ __forceinline__ void loads_done() const {}
+  __device__ __forceinline__ void store_reward_done(float rw, bool done) const {
+    if (L.valid) {
+      st_stream(a.io.reward + (size_t)k * r.M + L.m, rw);
+      st_stream(a.io.done + (size_t)k * r.M + L.m, (uint8_t)done);
+    }
+  }
+  __device__ __forceinline__ bool wants_final() const { return a.io.final_obs != nullptr; }
+  __device__ __forceinline__ void put_own(float2 o01, float2 o23) const { stage_own(stage, L.lane, o01, o23); }
+  __device__ __forceinline__ void put_neighbours(const ObsTail& n) const { stage_neighbours(stage, L.lane, n); }
+  __device__ __forceinline__ void commit(float* g) const {
+    __syncwarp();
+    flush_rows(stage, g + (size_t)k * r.M * UAVCA_OBS_DIM_MULTI, L);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void commit_obs() const { commit(a.io.obs); }
+  __device__ __forceinline__ void commit_final() const { commit(a.io.final_obs); }
+  __device__ __forceinline__ void store_state(const Uav& u) { cur = u; }
+  __device__ __forceinline__ void store_target(const Uav&) const {}  // store_state carried the new target already
+  __device__ __forceinline__ void store_steps(int v, bool) { steps = v; }
+  __device__ __forceinline__ void store_reset(bool rs) const {
+    if (a.io.reset_mask) a.io.reset_mask[(size_t)k * r.B + L.env] = (uint8_t)rs;
+  }
+};
+
+template <int NT, bool FULL>
+__device__ __forceinline__ void rollout_multi_body(const KernelArgs& a, const RolloutArgs& r, const WarpScratch& ws,
+                                                   int warp_global) {
+  const Lane L = make_lane<NT, FULL>(a.B, a.N, warp_global);
+  RolloutIO io{a, r, L, ws.stage, load_uav(a.s, L), make_float2(0.f, 0.f), L.valid ? a.s.steps[L.env] : 0, 0};
+  cudaTriggerProgrammaticLaunchCompletion();
+  const long long env_global = a.c.env_base + L.env;
+  uint4 words = make_uint4(0u, 0u, 0u, 0u);
+  for (int k = 0; k < r.K; ++k) {
+    io.k = k;
+    if (r.action_block != nullptr) {
+      io.act = L.valid ? ld_stream(r.action_block + (size_t)k * r.M + L.m) : make_float2(0.f, 0.f);
+    } else {
+      const unsigned long long t = r.step0 + (unsigned long long)k;
+      if (k == 0 || (t & 1ull) == 0ull) words = action_words(r.seed_lo, r.seed_hi, env_global, L.i, t);
+      io.act = action_from_words(words, t);
+      if (r.action_out != nullptr && L.valid) st_stream(r.action_out + (size_t)k * r.M + L.m, io.act);
+    }
+    step_core<NT>(a, ws, L, io);
+  }
+  store_uav(a.s, L, io.cur, true);
+  if (L.valid & (L.i == 0)) a.s.steps[L.env] = io.steps;
+}
+
+// No load latency to hide inside the K-step loop: fewer resident CTAs, more registers (the env state lives in them).
+#ifndef UAVCA_ROLLOUT_MINB
+#define UAVCA_ROLLOUT_MINB 6
+#endif
+template <int NT>
+__global__ void __launch_bounds__(kThreads, UAVCA_ROLLOUT_MINB) rollout_multi_kernel(const __grid_constant__ KernelArgs a,
+                                                                                  const __grid_constant__ RolloutArgs r) {
+  __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
+  const WarpScratch ws = warp_scratch(smem);
+  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int N = NT > 0 ? NT : a.N;
+  const bool full = uavs_left(a.B, N, warp_global) >= (32 / N) * N;  // warp-uniform
+  cudaGridDependencySynchronize();
+  if (full) rollout_multi_body<NT, true>(a, r, ws, warp_global);
+  else rollout_multi_body<NT, false>(a, r, ws, warp_global);
+}
+
+// The action stream of uavca_rollout on its own, one step: out[m] = the policy-space action of global step t.
+__global__ void __launch_bounds__(kThreads) sample_actions_kernel(const __grid_constant__ Consts c, float2* out, int B, int N,
+                                                                  unsigned seed_lo, unsigned seed_hi, unsigned long long t) {
+  const long long m = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (m >= (long long)B * N) return;
+  const long long env = m / N;
+  const int i = (int)(m - env * N);
+  out[m] = action_from_words(action_words(seed_lo, seed_hi, c.env_base + env, i, t), t);
 }
 
 template <int NT>
@@ -98,14 +198,13 @@ __global__ void __launch_bounds__(kThreads) reset_multi_kernel(const __grid_cons
     a.s.episode[L.env] = episode + 1u;
   }
   reset_multi(a, L, rs, episode, u);
-  float o[10];
-  observe_state<NT>(a.c, ws, L, u, o);
+  const ObsRow o = observe_state<NT>(a.c, ws, L, u);
   if (a.io.obs) {
     if (mask == nullptr) {
       store_obs_rows(ws.stage, a.io.obs, L, o);
     } else if (rs) {  // rows of other envs stay untouched
-#pragma unroll
-      for (int k = 0; k < 10; ++k) a.io.obs[(size_t)L.m * 10 + k] = o[k];
+      float2* row = reinterpret_cast<float2*>(a.io.obs + (size_t)L.m * 10);
+      row[0] = o.o01; row[1] = o.o23; row[2] = o.n.a; row[3] = o.n.b; row[4] = o.n.c;
     }
   }
   if (rs) store_uav(a.s, L, u, true);
@@ -117,9 +216,7 @@ __global__ void __launch_bounds__(kThreads) observe_multi_kernel(const __grid_co
   const WarpScratch ws = warp_scratch(smem);
   const Lane L = make_lane<NT>(a.B, a.N);
   const Uav u = load_uav(a.s, L);
-  float o[10];
-  observe_state<NT>(a.c, ws, L, u, o);
-  store_obs_rows(ws.stage, a.io.obs, L, o);
+  store_obs_rows(ws.stage, a.io.obs, L, observe_state<NT>(a.c, ws, L, u));
 }
 
 // ================================================================================================================
@@ -193,12 +290,11 @@ __device__ __forceinline__ void fold_single(const KernelArgs& a, long long b, un
   a.s.episode[b] = episode + 1u;
 }
 
-__global__ void __launch_bounds__(kThreads) step_single_kernel(const __grid_constant__ KernelArgs a) {
+// One UAVWorld2D.step of env b held in registers (uav_world_2d.py:137-173); outputs go to row `o` of the output
+// tensors (o = b for one step per launch, k * B + b inside a rollout).  Returns true when the env auto-reset.
+__device__ __forceinline__ bool step_single_core(const KernelArgs& a, long long b, long long o, SingleEnv& e, float2 act_raw) {
   const Consts& c = a.c;
-  const long long b = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (b >= a.B) return;
-  SingleEnv e = load_single(a.s, b);
-  const float2 act = map_action(ld_stream(a.io.action + b), a.io.action_mode, c);
+  const float2 act = map_action(act_raw, a.io.action_mode, c);
 
   // UAVWorld2D.step (uav_world_2d.py:142-147)
   if (c.single_f32_first_step && e.steps == 0) {
@@ -228,25 +324,57 @@ __global__ void __launch_bounds__(kThreads) step_single_kernel(const __grid_cons
   e.prev = dist;                                                                  // :172
   if (reached) a.s.reach[b] += 1;
 
-  float o[4];
-  obs_single(c, e, false, o);
-  st_stream(a.io.reward + b, r);
-  st_stream(a.io.done + b, (uint8_t)done);
-  if (a.io.distance) st_stream(a.io.distance + b, dist);                          // info["distance"] :169
-  if (a.io.final_obs) st_stream(reinterpret_cast<float4*>(a.io.final_obs) + b, make_float4(o[0], o[1], o[2], o[3]));
+  float ob[4];
+  obs_single(c, e, false, ob);
+  st_stream(a.io.reward + o, r);
+  st_stream(a.io.done + o, (uint8_t)done);
+  if (a.io.distance) st_stream(a.io.distance + o, dist);                          // info["distance"] :169
+  if (a.io.final_obs) st_stream(reinterpret_cast<float4*>(a.io.final_obs) + o, make_float4(ob[0], ob[1], ob[2], ob[3]));
 
   bool rs = false;
   if (c.reset_mode & (UAVCA_RESET_ON_DONE0 | UAVCA_RESET_ON_ALL_DONE | UAVCA_RESET_ON_ANY_DONE)) rs |= done;
   if (c.max_steps > 0) rs |= e.steps >= c.max_steps;
-  if (a.io.reset_mask) a.io.reset_mask[b] = (uint8_t)rs;
+  if (a.io.reset_mask) a.io.reset_mask[o] = (uint8_t)rs;
   if (rs) {
     const unsigned episode = a.s.episode[b];
     fold_single(a, b, episode, e.steps);
     reset_single(a, b, episode, e);
-    obs_single(c, e, true, o);
+    obs_single(c, e, true, ob);
   }
-  st_stream(reinterpret_cast<float4*>(a.io.obs) + b, make_float4(o[0], o[1], o[2], o[3]));
+  st_stream(reinterpret_cast<float4*>(a.io.obs) + o, make_float4(ob[0], ob[1], ob[2], ob[3]));
+  return rs;
+}
+
+__global__ void __launch_bounds__(kThreads) step_single_kernel(const __grid_constant__ KernelArgs a) {
+  const long long b = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (b >= a.B) return;
+  SingleEnv e = load_single(a.s, b);
+  const bool rs = step_single_core(a, b, b, e, ld_stream(a.io.action + b));
   store_single(a.s, b, e, rs);
+}
+
+// K steps of UAVWorld2D per launch, the env in registers throughout (see RolloutIO above).
+__global__ void __launch_bounds__(kThreads) rollout_single_kernel(const __grid_constant__ KernelArgs a,
+                                                                  const __grid_constant__ RolloutArgs r) {
+  const long long b = (long long)blockIdx.x * kThreads + threadIdx.x;
+  cudaGridDependencySynchronize();
+  if (b >= a.B) return;
+  SingleEnv e = load_single(a.s, b);
+  cudaTriggerProgrammaticLaunchCompletion();
+  uint4 words = make_uint4(0u, 0u, 0u, 0u);
+  for (int k = 0; k < r.K; ++k) {
+    float2 act;
+    if (r.action_block != nullptr) {
+      act = ld_stream(r.action_block + (size_t)k * r.M + b);
+    } else {
+      const unsigned long long t = r.step0 + (unsigned long long)k;
+      if (k == 0 || (t & 1ull) == 0ull) words = action_words(r.seed_lo, r.seed_hi, a.c.env_base + b, 0, t);
+      act = action_from_words(words, t);
+      if (r.action_out != nullptr) st_stream(r.action_out + (size_t)k * r.M + b, act);
+    }
+    step_single_core(a, b, (long long)k * r.M + b, e, act);
+  }
+  store_single(a.s, b, e, true);
 }
 
 __global__ void __launch_bounds__(kThreads) reset_single_kernel(const __grid_constant__ KernelArgs a, const uint8_t* mask) {
@@ -313,7 +441,11 @@ template <typename V>
 __global__ void __launch_bounds__(kThreads) replay_push_kernel(const V* obs, const V* act, const float* rew, const V* nxt,
                                                                const uint8_t* done, long long M, long long od, long long ad,
                                                                V* r_obs, V* r_act, float* r_rew, V* r_nxt, float* r_mask,
-                                                               long long cap, long long head) {
+                                                               long long cap, long long head, long long* meta) {
+  // meta (nullable, device): [0] ring head, [1] block ticket, [2] transitions held.  With it the head lives on the
+  // device, so a CUDA-graph replay of the push appends where the previous replay stopped; the last block to finish
+  // (every block has read the head by then) advances it.
+  if (meta != nullptr) head = meta[0];
   const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (j < M * od) {
     long long d = head * od + j;
@@ -331,6 +463,20 @@ __global__ void __launch_bounds__(kThreads) replay_push_kernel(const V* obs, con
     if (d >= cap) d -= cap;
     r_rew[d] = ld_stream(rew + j);
     r_mask[d] = done[j] ? 0.0f : 1.0f;
+  }
+  if (meta != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(meta + 1), 1ull);
+      if (t == (unsigned long long)gridDim.x - 1ull) {
+        long long nh = head + M;
+        meta[0] = nh >= cap ? nh - cap : nh;
+        const long long held = meta[2] + M;
+        meta[2] = held > cap ? cap : held;
+        meta[1] = 0;
+      }
+    }
   }
 }
 
@@ -487,6 +633,44 @@ cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launche
   return cudaGetLastError();
 }
 
+template <typename Kernel>
+static cudaError_t launch_pdl2(Kernel kernel, int grid, cudaStream_t st, const KernelArgs& a, const RolloutArgs& r) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, a, r);
+}
+
+cudaError_t launch_rollout_multi(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st) {
+  if (a.B <= 0 || r.K <= 0) return cudaSuccess;
+  cudaError_t e = cudaSuccess;
+  const int grid = multi_grid(a.B, a.N);
+  UAVCA_DISPATCH_N(a.N, (e = launch_pdl2(rollout_multi_kernel<NT>, grid, st, a, r)));
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t launch_rollout_single(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st) {
+  if (a.B <= 0 || r.K <= 0) return cudaSuccess;
+  const cudaError_t e = launch_pdl2(rollout_single_kernel, flat_grid(a.B), st, a, r);
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t launch_sample_actions(const Consts& c, float* out, int B, int N, unsigned long long seed, unsigned long long t,
+                                  cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  sample_actions_kernel<<<flat_grid((long long)B * N), kThreads, 0, st>>>(c, reinterpret_cast<float2*>(out), B, N,
+                                                                          (unsigned)(seed & 0xffffffffull),
+                                                                          (unsigned)(seed >> 32), t);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_reset_multi(const KernelArgs& a, const uint8_t* mask, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
   const int grid = multi_grid(a.B, a.N);
@@ -529,7 +713,7 @@ cudaError_t launch_map_action(const Consts& c, const float* in, float* out, long
 cudaError_t launch_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs,
                                const uint8_t* done, long long M, int obs_dim, int act_dim, float* r_obs, float* r_act,
                                float* r_rew, float* r_next, float* r_mask, long long capacity, long long head,
-                               cudaStream_t st) {
+                               long long* meta, cudaStream_t st) {
   if (M <= 0) return cudaSuccess;
   auto a8 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; };
   const bool wide = (obs_dim % 2 == 0) && (act_dim % 2 == 0) && a8(obs) && a8(action) && a8(next_obs) && a8(r_obs) &&
@@ -540,11 +724,11 @@ cudaError_t launch_replay_push(const float* obs, const float* action, const floa
     replay_push_kernel<float2><<<flat_grid(n), kThreads, 0, st>>>(
         reinterpret_cast<const float2*>(obs), reinterpret_cast<const float2*>(action), reward,
         reinterpret_cast<const float2*>(next_obs), done, M, obs_dim / 2, act_dim / 2, reinterpret_cast<float2*>(r_obs),
-        reinterpret_cast<float2*>(r_act), r_rew, reinterpret_cast<float2*>(r_next), r_mask, capacity, head);
+        reinterpret_cast<float2*>(r_act), r_rew, reinterpret_cast<float2*>(r_next), r_mask, capacity, head, meta);
   } else {
     const long long n = M * (widest > 1 ? widest : 1);
     replay_push_kernel<float><<<flat_grid(n), kThreads, 0, st>>>(obs, action, reward, next_obs, done, M, obs_dim, act_dim,
-                                                                  r_obs, r_act, r_rew, r_next, r_mask, capacity, head);
+                                                                  r_obs, r_act, r_rew, r_next, r_mask, capacity, head, meta);
   }
   return cudaGetLastError();
 }

@@ -17,6 +17,7 @@ struct Lane {
   int lane;
   int i;            // UAV index inside its env
   int base;         // first lane of this lane's env
+  int ring;         // float4 offset of this env's ring in WarpScratch::pairs
   unsigned envmask; // N low bits
   int env;          // env index inside the shard
   int m;            // flat UAV index env*N + i  (B*N < 2^31 is checked at uavca_create)
@@ -40,6 +41,7 @@ __device__ __forceinline__ Lane make_lane(int B, int Nrt, int warp_global) {
   const int e_local = L.lane / L.N;
   L.i = L.lane - e_local * L.N;
   L.base = e_local * L.N;
+  L.ring = e_local * (L.N + 1);
   L.envmask = L.N >= 32 ? 0xffffffffu : ((1u << L.N) - 1u);
   L.env = warp_global * epw + e_local;
   L.warp_m0 = warp_global * L.lanes_used;
@@ -51,7 +53,7 @@ __device__ __forceinline__ Lane make_lane(int B, int Nrt, int warp_global) {
   }
   L.valid = L.lane < L.valid_lanes;
   L.m = L.warp_m0 + L.lane;
-  if (!L.valid) { L.base = 0; L.i = 0; }  // idle lanes shadow UAV 0 of the warp's first env and never store
+  if (!L.valid) { L.base = 0; L.ring = 0; L.i = 0; }  // idle lanes shadow UAV 0 of the warp's first env and never store
   return L;
 }
 template <int NT>
@@ -96,31 +98,37 @@ __device__ __forceinline__ void store_uav(const StateView& s, const Lane& L, con
   }
 }
 
-// Per-warp shared-memory scratch.  Neighbour data never goes to global memory.  Each env owns a DOUBLED ring of
-// 2N slots: slot m < N holds UAV m's (old position, new position), slot N+m holds (new, new) and its heading.
-// Lane i reads slot i+k for k = 1..N-1, i.e. its ring neighbour j = (i+k) mod N, and receives as "a" exactly the
-// position the reference's sequential sweep would see — OLD for j > i (not moved yet), NEW for j < i — and as "n"
-// the NEW position, with no index arithmetic, no compare and no select.  A slot is laid out (a.x, n.x, a.y, n.y)
-// so that both squared distances come out of five packed FP32 instructions (2 FADD2, 2 FFMA2 with a +0 addend, FADD2).
+// Per-warp shared-memory scratch.  Neighbour data never goes to global memory.
+//   pairs  per env a DOUBLED ring of the NEW positions, two ring slots per float4: element q of an env's ring holds
+//          (x[2q], x[2q+1], y[2q], y[2q+1]) with slot s < N = UAV s and slot N+s = UAV s again.  Lane i sweeps the slots
+//          from its own even-aligned start, so one LDS.128 brings TWO neighbours laid out for packed FP32 (both
+//          squared distances of the pair come out of 2 FADD2 + 2 FFMA2 with a +0 addend + 1 FADD2) and ring
+//          neighbour i+k needs no index arithmetic, compare or select.
+//   cand   per UAV (new.x, new.y, old.x, old.y): what the few selected neighbours are looked up in afterwards
+//   th     per UAV heading / pi
 struct WarpScratch {
-  float4* ring;  // [64] per-env doubled rings, env e at offset 2*e*N
-  float* th;     // [64] heading / pi, doubled the same way
-  float* stage;  // [320] observation rows of the warp
+  float4* pairs;  // [48]  env e_local at float4 offset e_local * (N + 1)
+  float4* cand;   // [32]  by lane of the UAV
+  float* th;      // [32]  by lane of the UAV
+  float* stage;   // [320] observation rows of the warp
 };
-constexpr int kScratchFloats = 64 * 4 + 64 + 32 * 10;
+constexpr int kRingFloats = 48 * 4 + 32 * 4 + 32;
+constexpr int kScratchFloats = kRingFloats + 32 * 10;
 
 __device__ __forceinline__ WarpScratch warp_scratch(float* block_smem) {
   float* w = block_smem + (threadIdx.x >> 5) * kScratchFloats;
-  return WarpScratch{reinterpret_cast<float4*>(w), w + 256, w + 320};
+  return WarpScratch{reinterpret_cast<float4*>(w), reinterpret_cast<float4*>(w + 192), w + 320, w + kRingFloats};
 }
 
 __device__ __forceinline__ void publish(const WarpScratch& ws, const Lane& L, float nx, float ny, float ox, float oy, float th_u) {
   if (L.valid) {
-    const int slot = 2 * L.base + L.i;
-    ws.ring[slot] = make_float4(ox, nx, oy, ny);
-    ws.ring[slot + L.N] = make_float4(nx, nx, ny, ny);
-    ws.th[slot] = th_u;
-    ws.th[slot + L.N] = th_u;
+    float* ring = reinterpret_cast<float*>(ws.pairs + L.ring);
+    const int s0 = L.i, s1 = L.i + L.N;
+    const int a0 = ((s0 >> 1) << 2) + (s0 & 1), a1 = ((s1 >> 1) << 2) + (s1 & 1);
+    ring[a0] = nx; ring[a0 + 2] = ny;
+    ring[a1] = nx; ring[a1 + 2] = ny;
+    ws.cand[L.lane] = make_float4(nx, ny, ox, oy);
+    ws.th[L.lane] = th_u;
   }
   __syncwarp();
 }
@@ -129,17 +137,21 @@ __device__ __forceinline__ void publish(const WarpScratch& ws, const Lane& L, fl
 // The two nearest other UAVs of the env, ordered by (squared float32 distance, ring offset) — the order of
 // `relative_distances.argsort()` (uav_agent.py:62) with the lowest ring offset first among exactly equal distances
 // (the reference's own order of exact ties is undefined).  Results are ring offsets k (neighbour
-// slot = own slot + k); 0 = none.
+// j = (i + k) mod N); 0 = none.
+
+constexpr int kInfBits = 0x7f800000;
 
 // Exact reference selection: branch-free insertion on the float32 squared distances themselves.  Out of line: it
 // only runs for the rare lanes whose fast selection below is ambiguous.
-static __device__ __noinline__ int nearest2_exact(const float4* row, float px, float py, int N) {
-  const float inf = __int_as_float(0x7f800000);
+static __device__ __noinline__ int nearest2_exact(const float4* cand, int i, int N, float px, float py) {
+  const float inf = __int_as_float(kInfBits);
   float s1 = inf, s2 = inf;
   int j1 = 0, j2 = 0;
   for (int k = 1; k < N; ++k) {
-    const float4 q = row[k];
-    const float s = sq32(__fsub_rn(q.y, px), __fsub_rn(q.w, py));
+    int j = i + k;
+    j -= j >= N ? N : 0;
+    const float4 q = cand[j];
+    const float s = sq32(__fsub_rn(q.x, px), __fsub_rn(q.y, py));
     const bool p1 = s < s1, p2 = s < s2;
     j2 = p1 ? j1 : (p2 ? k : j2);
     s2 = p1 ? s1 : (p2 ? s : s2);
@@ -149,91 +161,136 @@ static __device__ __noinline__ int nearest2_exact(const float4* row, float px, f
   return j1 | (j2 << 8);
 }
 
-// One sweep over the env's other UAVs serving both pairwise passes of MultiUAVWorld2D.step:
-//   pass A (multi_uav_world_2d.py:198-210): nearest neighbour with j<i at the NEW position and j>i at the OLD one
-//                                           (the reference moves and tests the UAVs one after the other) -> smin;
-//   pass B (:75 via _get_obs):              the two nearest neighbours with every UAV at its NEW position -> j1, j2.
-// Pass B keeps the THREE smallest integer keys (distance bits with the low 5 bits replaced by the ring offset):
-// integer min/max only, two neighbours merged per step with the k-th-smallest-of-two-sorted-lists identities
+// Pass A of MultiUAVWorld2D.step in full (multi_uav_world_2d.py:198-210): the squared distance to the nearest other
+// UAV with j < i at its NEW position and j > i at its OLD one (the reference moves and tests the UAVs one after the
+// other).  Out of line: only lanes with three or more UAVs within collision reach need the whole sweep.
+static __device__ __noinline__ float nearest_mixed_exact(const float4* cand, int i, int N, float px, float py) {
+  float smin = __int_as_float(kInfBits);
+  for (int j = 0; j < N; ++j) {
+    if (j == i) continue;
+    const float4 q = cand[j];
+    const float s = j < i ? sq32(__fsub_rn(q.x, px), __fsub_rn(q.y, py)) : sq32(__fsub_rn(q.z, px), __fsub_rn(q.w, py));
+    smin = fminf(smin, s);
+  }
+  return smin;
+}
+
+// One sweep over the env's other UAVs at their NEW positions (what _get_obs sees, multi_uav_world_2d.py:75), two
+// neighbours per step.  It keeps the THREE smallest integer keys (distance bits with the low 5 bits replaced by the
+// element number of the sweep): integer min/max only, two neighbours merged per step with the
+// k-th-smallest-of-two-sorted-lists identities
 //   t1' = min(t1, a)   t2' = min(t2, max(t1, a), b)   t3' = min(t3, max(t2, a), max(t1, b))       (a <= b).
-// A key orders like (distance truncated to 19 mantissa bits, offset).  If the truncated distances of the three
+// A key orders like (distance truncated to 19 mantissa bits, ring offset).  If the truncated distances of the three
 // smallest keys are pairwise different, truncation cannot have reordered anything and t1, t2 are exactly the
 // reference's two nearest; otherwise (two of them within 2^-18 relative, ~1e-4 of the lanes at N=32) the lane
-// re-runs the exact selection.
+// re-runs the exact selection.  t3 — a lower bound of the third-smallest distance — also tells the caller whether
+// anybody besides the two nearest can be within collision reach.
+//
+// Lane i starts at the even slot s0 = i + (i & 1); element e of its sweep is ring offset k = (i & 1) + e.  Offsets
+// 0 and N (the lane's own two ring slots) and anything beyond are masked with "none" keys.
 template <int NT>
 __device__ __forceinline__ void pair_scan(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
-                                          float& smin, int& j1, int& j2) {
+                                          int& k1, int& k2, int& t3_out) {
   const int N = NT > 0 ? NT : L.N;
-  const float4* row = ws.ring + 2 * L.base + L.i;
+  const int k0 = L.i & 1;
+  const float4* row = ws.pairs + L.ring + ((L.i + 1) >> 1);
   const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py), zero = make_float2(0.f, 0.f);
-  // (a.x - p.x, n.x - p.x), (a.y - p.y, n.y - p.y); squares and sum rounded separately, exactly as sq32().  The
-  // squares are FFMA2 with a +0 addend: a plain mul.rn.f32x2 feeding add.rn.f32x2 is contracted into one FFMA2 by
-  // ptxas 12.9 (even under -fmad=false), which would break the unfused np.linalg.norm order.
-  auto dist2 = [&](int k) {
-    const float4 q = row[k];
+  // squares and sum rounded separately, exactly as sq32().  The squares are FFMA2 with a +0 addend: a plain
+  // mul.rn.f32x2 feeding add.rn.f32x2 is contracted into one FFMA2 by ptxas 12.9 (even under -fmad=false), which
+  // would break the unfused np.linalg.norm order.
+  auto dist2 = [&](int p) {
+    const float4 q = row[p];
     const float2 dx = __fadd2_rn(make_float2(q.x, q.y), npx), dy = __fadd2_rn(make_float2(q.z, q.w), npy);
     return __fadd2_rn(__ffma2_rn(dx, dx, zero), __ffma2_rn(dy, dy, zero));
   };
-  // the mask (~31) comes from the constant bank on purpose: with an opaque mask and an immediate offset the key is
-  // ONE LOP3 ((s & mask) | k); as two literals it would be two
+  // the mask (~31) comes from the constant bank on purpose: with an opaque mask and an immediate element number the
+  // key is ONE LOP3 ((s & mask) | e); as two literals it would be two
   const int mask = c.key_mask;
-  auto key = [mask](float sq, int k) { return (__float_as_int(sq) & mask) | k; };
-  smin = __int_as_float(0x7f800000);
-  int t1 = 0x7f800000, t2 = 0x7f800020, t3 = 0x7f800040;  // "none": above every real key, pairwise unambiguous
-  int k = 1;
-#pragma unroll
-  for (; k + 1 < N; k += 2) {
-    const float2 s0 = dist2(k), s1 = dist2(k + 1);
-    smin = fminf(smin, fminf(s0.x, s1.x));
-    const int ka = key(s0.y, k), kb = key(s1.y, k + 1);
+  auto key = [&](float sq, int e) {
+    int kk = (__float_as_int(sq) & mask) | e;
+    // valid iff 1 <= k0 + e <= N - 1; "none" keys lie above every real key and are pairwise unambiguous
+    if (e >= N) return kInfBits + 5 * 32;
+    if (e == 0) kk = k0 ? kk : kInfBits + 3 * 32;
+    if (e == N - 1) kk = k0 ? kInfBits + 4 * 32 : kk;
+    return kk;
+  };
+  int t1 = kInfBits, t2 = kInfBits + 32, t3 = kInfBits + 64;
+  auto merge = [&](int ka, int kb) {
     const int a = min(ka, kb), b = max(ka, kb);
     const int m1a = max(t1, a), m2a = max(t2, a), m1b = max(t1, b);
     t3 = __vimin3_s32(t3, m2a, m1b);
     t2 = __vimin3_s32(t2, m1a, b);
     t1 = min(t1, a);
+  };
+  if (N > 1) {
+    const int P = (N + 1) >> 1;
+    if (NT > 0) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const float2 s = dist2(p);
+        merge(key(s.x, 2 * p), key(s.y, 2 * p + 1));
+      }
+    } else {
+      for (int p = 0; p < P; ++p) {
+        const float2 s = dist2(p);
+        merge(key(s.x, 2 * p), key(s.y, 2 * p + 1));
+      }
+    }
   }
-  if (k < N) {
-    const float2 s0 = dist2(k);
-    smin = fminf(smin, s0.x);
-    const int a = key(s0.y, k);
-    t3 = min(t3, max(t2, a));
-    t2 = min(t2, max(t1, a));
-    t1 = min(t1, a);
-  }
-  j1 = t1 & 31;
-  j2 = t2 & 31;
+  k1 = t1 < kInfBits ? k0 + (t1 & 31) : 0;
+  k2 = t2 < kInfBits ? k0 + (t2 & 31) : 0;
+  t3_out = t3;
   if (((unsigned)(t1 ^ t2) < 32u) | ((unsigned)(t2 ^ t3) < 32u)) {
-    const int e = nearest2_exact(row, px, py, N);
-    j1 = e & 0xff;
-    j2 = e >> 8;
+    const int e = nearest2_exact(ws.cand + L.base, L.i, N, px, py);
+    k1 = e & 0xff;
+    k2 = e >> 8;
   }
 }
 
-// MultiUAVWorld2D._get_obs (multi_uav_world_2d.py:60-109) for this lane's UAV, neighbour half: features 4..9.
+// The two selected neighbours, looked up by ring offset: observation features 4..9 (MultiUAVWorld2D._get_obs,
+// multi_uav_world_2d.py:75-95) and, for the step, the collision distance of pass A.
 // Neighbour bearings/headings are differences of float32 angles (absolute error ~2e-7 of a half-turn).
 struct ObsTail {
   float2 a, b, c;  // (o4, o5) (o6, o7) (o8, o9)
 };
-__device__ __forceinline__ ObsTail obs_neighbours(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
-                                                  float th_u, int j1, int j2) {
-  const int slot = 2 * L.base + L.i;
-  const float4 q1 = ws.ring[slot + j1], q2 = ws.ring[slot + j2];
-  const float h1 = ws.th[slot + j1], h2 = ws.th[slot + j2];
-  const float dx1 = __fsub_rn(q1.y, px), dy1 = __fsub_rn(q1.w, py), dx2 = __fsub_rn(q2.y, px), dy2 = __fsub_rn(q2.w, py);
+// smin (WANT_A): squared distance to the nearest other UAV as the reference's sequential sweep sees it — j < i at the
+// NEW position, j > i at the OLD one (multi_uav_world_2d.py:181-210).  Only a UAV within `near` of the new position
+// can be within collision reach of the old one (a UAV moves at most sqrt(2) v_max tau per step; Consts::near_key),
+// so unless the third-smallest key is that close the two nearest are the only candidates.
+template <int NT, bool WANT_A>
+__device__ __forceinline__ ObsTail neighbours(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
+                                              float th_u, int k1, int k2, int t3, float& smin) {
+  const int N = NT > 0 ? NT : L.N;
+  int j1 = L.i + k1, j2 = L.i + k2;
+  const bool w1 = j1 >= N, w2 = j2 >= N;  // wrapped: j < i
+  j1 -= w1 ? N : 0;
+  j2 -= w2 ? N : 0;
+  const float4 q1 = ws.cand[L.base + j1], q2 = ws.cand[L.base + j2];
+  const float h1 = ws.th[L.base + j1], h2 = ws.th[L.base + j2];
+  const float dx1 = __fsub_rn(q1.x, px), dy1 = __fsub_rn(q1.y, py), dx2 = __fsub_rn(q2.x, px), dy2 = __fsub_rn(q2.y, py);
   const float s1 = sq32(dx1, dy1), s2 = sq32(dx2, dy2);  // the exact squared distances of the two winners
-  const bool have1 = (j1 != 0) & (s1 < c.s_dsense_lt);  // uav_agent.py:52 strict <
-  const bool have2 = have1 & (j2 != 0) & (s2 < c.s_dsense_lt);
+  if (WANT_A) {
+    const float inf = __int_as_float(kInfBits);
+    float a1 = w1 ? s1 : sq32(__fsub_rn(q1.z, px), __fsub_rn(q1.w, py));
+    float a2 = w2 ? s2 : sq32(__fsub_rn(q2.z, px), __fsub_rn(q2.w, py));
+    a1 = k1 != 0 ? a1 : inf;
+    a2 = k2 != 0 ? a2 : inf;
+    smin = fminf(a1, a2);
+    if (t3 <= c.near_key) smin = nearest_mixed_exact(ws.cand + L.base, L.i, N, px, py);
+  }
+  const bool have1 = (k1 != 0) & (s1 < c.s_dsense_lt);  // uav_agent.py:52 strict <
+  const bool have2 = have1 & (k2 != 0) & (s2 < c.s_dsense_lt);
   const float2 b = fast_atan2_pair(dy1, dx1, dy2, dx2);
   const float2 nth = make_float2(-th_u, -th_u);
-  const float2 w1 = wrap_units2(__ffma2_rn(b, make_float2(c.inv_pi, c.inv_pi), nth));  // bearings relative to the heading
-  const float2 w2 = wrap_units2(__fadd2_rn(make_float2(h1, h2), nth));                 // neighbour headings, relative
+  const float2 v1 = wrap_units2(__ffma2_rn(b, make_float2(c.inv_pi, c.inv_pi), nth));  // bearings relative to the heading
+  const float2 v2 = wrap_units2(__fadd2_rn(make_float2(h1, h2), nth));                 // neighbour headings, relative
   ObsTail o;
   o.a.x = have1 ? sqrt_approx(s1) * c.inv_dsense : 1.0f;  // :77
-  o.a.y = have1 ? w1.x : 1.0f;                            // :78-81 (no neighbour: bearing pi)
-  o.b.x = have1 ? w2.x : 0.0f;                            // :82-85
+  o.a.y = have1 ? v1.x : 1.0f;                            // :78-81 (no neighbour: bearing pi)
+  o.b.x = have1 ? v2.x : 0.0f;                            // :82-85
   o.b.y = have2 ? sqrt_approx(s2) * c.inv_dsense : 1.0f;  // :87
-  o.c.x = have2 ? w1.y : 1.0f;                            // :88-91
-  o.c.y = have2 ? w2.y : 0.0f;                            // :92-95
+  o.c.x = have2 ? v1.y : 1.0f;                            // :88-91
+  o.c.y = have2 ? v2.y : 0.0f;                            // :92-95
   return o;
 }
 
@@ -279,19 +336,22 @@ __device__ __forceinline__ void obs_own(const Consts& c, const Own& w, double vs
 }
 
 // Observation of a state at rest (reset / observe kernels): publish, scan, build.  All lanes must call.
+struct ObsRow {
+  float2 o01, o23;
+  ObsTail n;
+};
 template <int NT>
-__device__ __forceinline__ void observe_state(const Consts& c, const WarpScratch& ws, const Lane& L, const Uav& u, float o[10]) {
+__device__ __forceinline__ ObsRow observe_state(const Consts& c, const WarpScratch& ws, const Lane& L, const Uav& u) {
   const Own w = own_features(c, u.px, u.py, u.tx, u.ty, u.vx, u.vy);
   __syncwarp();
   publish(ws, L, u.px, u.py, u.px, u.py, w.th_u);
-  float smin;
-  int j1, j2;
-  pair_scan<NT>(c, ws, L, u.px, u.py, smin, j1, j2);
-  float2 o01, o23;
-  obs_own(c, w, w.vsq, o01, o23);
-  const ObsTail n = obs_neighbours(c, ws, L, u.px, u.py, w.th_u, j1, j2);
-  o[0] = o01.x; o[1] = o01.y; o[2] = o23.x; o[3] = o23.y;
-  o[4] = n.a.x; o[5] = n.a.y; o[6] = n.b.x; o[7] = n.b.y; o[8] = n.c.x; o[9] = n.c.y;
+  int k1, k2, t3;
+  pair_scan<NT>(c, ws, L, u.px, u.py, k1, k2, t3);
+  ObsRow r;
+  obs_own(c, w, w.vsq, r.o01, r.o23);
+  float unused;
+  r.n = neighbours<NT, false>(c, ws, L, u.px, u.py, w.th_u, k1, k2, t3, unused);
+  return r;
 }
 
 // The warp's observation rows go out as one contiguous run of 16-byte stores, staged through shared memory (a
@@ -328,11 +388,10 @@ __device__ __forceinline__ void flush_rows(const float* stage, float* gobs, cons
     }
   }
 }
-__device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const Lane& L, const float o[10]) {
+__device__ __forceinline__ void store_obs_rows(float* stage, float* gobs, const Lane& L, const ObsRow& o) {
   __syncwarp();
-  float2* st2 = reinterpret_cast<float2*>(stage) + L.lane * 5;
-#pragma unroll
-  for (int k = 0; k < 5; ++k) st2[k] = make_float2(o[2 * k], o[2 * k + 1]);
+  stage_own(stage, L.lane, o.o01, o.o23);
+  stage_neighbours(stage, L.lane, o.n);
   __syncwarp();
   flush_rows(stage, gobs, L);
 }
@@ -433,7 +492,8 @@ __device__ __forceinline__ void reset_multi(const KernelArgs& a, const Lane& L, 
 //   void  commit_obs();  void commit_final();                          (all lanes; rows -> obs / final_obs)
 //   void  store_state(const Uav&);        pos, vel, prev, flags
 //   void  store_target(const Uav&);       tgt, init (reset lanes only)
-//   void  store_steps(int);               (env leader lanes only)
+//   void  store_steps(int, bool leader);  (every valid lane; the leader lane writes the env's counter)
+//   void  store_reset(bool);              (env leader lanes only: the env auto-reset this step)
 //   bool  wants_final();
 // ================================================================================================================
 
@@ -482,10 +542,12 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
     r = fmaf(-0.01f * 3.14159274101257324f, fabsf(w.dth_u), r);
   }
 
-  // ---- both pairwise passes in one sweep over the env's UAVs
+  // ---- both pairwise passes: one sweep at the NEW positions for the two nearest (observation), from which the
+  // collision distance of the sequential pass follows (neighbours())
   float smin;
-  int j1, j2;
-  pair_scan<NT>(c, ws, L, u.px, u.py, smin, j1, j2);
+  int k1, k2, t3;
+  pair_scan<NT>(c, ws, L, u.px, u.py, k1, k2, t3);
+  const ObsTail tail = neighbours<NT, true>(c, ws, L, u.px, u.py, w.th_u, k1, k2, t3, smin);
 
   // ---- collisions (:199-210), decided in squared-distance space (the thresholds already include "in sensing range")
   const bool collision = smin <= c.s_coll_le;
@@ -513,21 +575,22 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
     float2 o01, o23;
     obs_own(c, w, vsq_obs, o01, o23);
     io.put_own(o01, o23);
-    io.put_neighbours(obs_neighbours(c, ws, L, u.px, u.py, w.th_u, j1, j2));
+    io.put_neighbours(tail);
   }
   io.store_reward_done(r, done);
 
   // ---- per-env bookkeeping: reset decision, counters
   // reset triggers as two masks derived on the host: any done flag under rs_any_mask (bit 0 for dones[0], all
   // bits for any(dones)); every flag of the env set (rs_all_off = 0) for all(dones); the step limit (INT_MAX = none)
-  const unsigned done_env = __ballot_sync(kFull, done) >> L.base;
-  const bool rs = (((done_env & c.rs_any_mask) != 0u) | ((((done_env & L.envmask) ^ L.envmask) | c.rs_all_off) == 0u) |
+  // (masked to the env's own lanes: with several envs per warp the shifted ballot still carries the envs above it)
+  const unsigned done_env = (__ballot_sync(kFull, done) >> L.base) & L.envmask;
+  const bool rs = (((done_env & c.rs_any_mask) != 0u) | (((done_env ^ L.envmask) | c.rs_all_off) == 0u) |
                    (steps_new >= c.steps_limit)) & L.valid;
   const bool leader = L.valid & (L.i == 0);
-  if (leader && a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
+  if (leader) io.store_reset(rs);
 
   if (!__any_sync(kFull, rs | newly_reached | hard)) {  // nothing to count, nobody resets: the common case
-    if (leader) io.store_steps(steps_new);
+    io.store_steps(steps_new, leader);
     io.commit_obs();
     if (io.wants_final()) io.commit_final();
     io.store_state(u);
@@ -539,8 +602,8 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
   const int reach_inc = __popc((ev_reach >> L.base) & L.envmask), coll_inc = __popc((ev_coll >> L.base) & L.envmask);
   if (io.wants_final()) io.commit_final();
   if (!__any_sync(kFull, rs)) {
+    io.store_steps(steps_new, leader);
     if (leader) {
-      io.store_steps(steps_new);
       if (reach_inc) a.s.reach[L.env] += reach_inc;  // :221
       if (coll_inc) a.s.coll[L.env] += coll_inc;     // :209
     }
@@ -559,23 +622,21 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
         atomicAdd(a.s.stats + 2, (unsigned long long)(a.s.coll[L.env] + coll_inc));
         atomicAdd(a.s.stats + 3, (unsigned long long)steps_new);
       }
-      io.store_steps(0);
       a.s.reach[L.env] = 0; a.s.coll[L.env] = 0;  // :166-168
       a.s.episode[L.env] = episode + 1u;
     } else {
-      io.store_steps(steps_new);
       if (reach_inc) a.s.reach[L.env] += reach_inc;
       if (coll_inc) a.s.coll[L.env] += coll_inc;
     }
   }
+  io.store_steps(rs ? 0 : steps_new, leader);
   Uav nu = u;
   reset_multi(a, L, rs, episode, nu);
-  float no[10];
-  observe_state<NT>(c, ws, L, nu, no);
+  const ObsRow no = observe_state<NT>(c, ws, L, nu);
   if (rs) {
     u = nu;
-    io.put_own(make_float2(no[0], no[1]), make_float2(no[2], no[3]));
-    io.put_neighbours(ObsTail{make_float2(no[4], no[5]), make_float2(no[6], no[7]), make_float2(no[8], no[9])});
+    io.put_own(no.o01, no.o23);
+    io.put_neighbours(no.n);
   }
   io.commit_obs();
   io.store_state(u);

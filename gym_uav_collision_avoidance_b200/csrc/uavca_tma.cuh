@@ -57,7 +57,7 @@ struct TmaGeom {
   static constexpr int STEPS = DONE + T;
   static constexpr int STAGE_BYTES = (STEPS + E * 4 + 127) / 128 * 128;
   static constexpr unsigned BYTES_IN = T * (8 + 16 + 8 + 8 + 4 + 4 + 1) + E * 4;
-  static constexpr int RING_FLOATS = 64 * 4 + 64;  // per compute warp: doubled position ring + headings
+  static constexpr int RING_FLOATS = kRingFloats;  // per compute warp: position rings, candidates, headings
   static constexpr int SMEM_BYTES = S * STAGE_BYTES + W * RING_FLOATS * 4 + 2 * S * 8;
 };
 
@@ -113,6 +113,7 @@ struct SmemIO {
   int u;              // UAV slot inside the tile
   int e;              // env slot inside the tile
   int m;              // flat UAV index in the shard (rare direct global stores)
+  int env;            // env index in the shard
   bool valid;
   template <typename T>
   __device__ __forceinline__ T* at(int off) const { return reinterpret_cast<T*>(st + off); }
@@ -171,7 +172,12 @@ struct SmemIO {
     a.s.tgt[m] = make_float2(s.tx, s.ty);
     a.s.init[m] = s.init;
   }
-  __device__ __forceinline__ void store_steps(int v) const { at<int>(G::STEPS)[e] = v; }
+  __device__ __forceinline__ void store_steps(int v, bool leader) const {
+    if (leader) at<int>(G::STEPS)[e] = v;
+  }
+  __device__ __forceinline__ void store_reset(bool rs) const {  // straight to global: one byte per env
+    if (a.io.reset_mask) a.io.reset_mask[env] = (uint8_t)rs;
+  }
 };
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
@@ -264,11 +270,12 @@ __global__ void __launch_bounds__(TmaGeom<NT, FINAL>::THREADS, TmaGeom<NT, FINAL
   const int e_local = L.valid ? lane / NT : 0;
   L.i = L.valid ? lane - e_local * NT : 0;  // idle lanes shadow UAV 0 of the warp's first env and never store
   L.base = e_local * NT;
+  L.ring = e_local * (NT + 1);
   L.envmask = NT >= 32 ? 0xffffffffu : ((1u << NT) - 1u);
   const int u_slot = warp * G::LANES + (L.valid ? lane : 0);
   const int e_slot = warp * G::EPW + e_local;
   float* const ring = rings + warp * G::RING_FLOATS;
-  const WarpScratch ws{reinterpret_cast<float4*>(ring), ring + 256, nullptr};
+  const WarpScratch ws{reinterpret_cast<float4*>(ring), reinterpret_cast<float4*>(ring + 192), ring + 320, nullptr};
 
   for (int j = 0; j < n_my; ++j) {
     const int s = j % S;
@@ -277,7 +284,7 @@ __global__ void __launch_bounds__(TmaGeom<NT, FINAL>::THREADS, TmaGeom<NT, FINAL
     L.m = L.warp_m0 + (L.valid ? lane : 0);
     L.env = tile * G::E + e_slot;
     mbar_wait(bar0 + 8 * s, (unsigned)(j / S) & 1u);  // the tile's inputs have landed in stage s
-    SmemIO<G, FINAL> io{a, stages + s * G::STAGE_BYTES, u_slot, e_slot, L.m, L.valid};
+    SmemIO<G, FINAL> io{a, stages + s * G::STAGE_BYTES, u_slot, e_slot, L.m, L.env, L.valid};
     step_core<NT>(a, ws, L, io);
     fence_proxy_async();
     __syncwarp();

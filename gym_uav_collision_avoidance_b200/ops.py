@@ -53,6 +53,28 @@ def step_single(handle: int, state: torch.Tensor, action: torch.Tensor, action_m
                                                _ptr(reset_mask), _stream(state)), "uavca_step_single")
 
 
+@torch.library.custom_op("uavca::rollout", mutates_args=("state", "obs", "reward", "done", "action_out", "final_obs",
+                                                        "reset_mask", "distance"))
+def rollout(handle: int, state: torch.Tensor, steps: int, action_block: Optional[torch.Tensor], action_mode: int,
+            evaluate: bool, action_seed: int, step0: int, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor,
+            action_out: Optional[torch.Tensor], final_obs: Optional[torch.Tensor], reset_mask: Optional[torch.Tensor],
+            distance: Optional[torch.Tensor]) -> None:
+    """K = `steps` consecutive env steps in one launch (run.py:10-16 / run_multi.py:10-16); outputs are [K, ...] blocks."""
+    _need_cuda(state, action_block, obs, reward, done, action_out, final_obs, reset_mask, distance)
+    _capi.check(_capi.load().uavca_rollout(handle, state.data_ptr(), steps, _ptr(action_block), action_mode, int(evaluate),
+                                           action_seed, step0, obs.data_ptr(), reward.data_ptr(), done.data_ptr(),
+                                           _ptr(action_out), _ptr(final_obs), _ptr(reset_mask), _ptr(distance),
+                                           _stream(state)), "uavca_rollout")
+
+
+@torch.library.custom_op("uavca::sample_actions", mutates_args=("out",))
+def sample_actions(handle: int, action_seed: int, step: int, out: torch.Tensor) -> None:
+    """The policy-space actions uavca::rollout draws at global step `step` (env.action_space.sample() for every UAV)."""
+    _need_cuda(out)
+    _capi.check(_capi.load().uavca_sample_actions(handle, action_seed, step, out.data_ptr(), _stream(out)),
+                "uavca_sample_actions")
+
+
 @torch.library.custom_op("uavca::reset", mutates_args=("state", "obs"))
 def reset(handle: int, state: torch.Tensor, mask: Optional[torch.Tensor], obs: torch.Tensor) -> None:
     """reset() of all (mask=None) or the masked envs (multi_uav_world_2d.py:116-175, uav_world_2d.py:119-135)."""
@@ -97,6 +119,22 @@ def replay_push(obs: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, n
                                                ring_obs.data_ptr(), ring_action.data_ptr(), ring_reward.data_ptr(),
                                                ring_next_obs.data_ptr(), ring_mask.data_ptr(), ring_reward.numel(), head,
                                                _stream(obs)), "uavca_replay_push")
+
+
+@torch.library.custom_op("uavca::replay_push_dev",
+                         mutates_args=("ring_obs", "ring_action", "ring_reward", "ring_next_obs", "ring_mask", "ring_meta"))
+def replay_push_dev(obs: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, next_obs: torch.Tensor, done: torch.Tensor,
+                    ring_obs: torch.Tensor, ring_action: torch.Tensor, ring_reward: torch.Tensor, ring_next_obs: torch.Tensor,
+                    ring_mask: torch.Tensor, ring_meta: torch.Tensor) -> None:
+    """The same append with the ring head on the device (`ring_meta` int64[4]: head, scratch, size): safe to replay from
+    a CUDA graph, every replay appends where the previous one stopped."""
+    _need_cuda(obs, action, reward, next_obs, done, ring_obs, ring_action, ring_reward, ring_next_obs, ring_mask, ring_meta)
+    M = reward.numel()
+    _capi.check(_capi.load().uavca_replay_push_dev(obs.data_ptr(), action.data_ptr(), reward.data_ptr(), next_obs.data_ptr(),
+                                                   done.data_ptr(), M, obs.numel() // max(M, 1), action.numel() // max(M, 1),
+                                                   ring_obs.data_ptr(), ring_action.data_ptr(), ring_reward.data_ptr(),
+                                                   ring_next_obs.data_ptr(), ring_mask.data_ptr(), ring_reward.numel(),
+                                                   ring_meta.data_ptr(), _stream(obs)), "uavca_replay_push_dev")
 
 
 @torch.library.custom_op("uavca::policy_act", mutates_args=("action", "head"))

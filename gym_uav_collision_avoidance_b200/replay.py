@@ -27,11 +27,21 @@ class DeviceReplay:
         self.reward = torch.zeros(capacity, **kw)
         self.next_state = torch.zeros((capacity, obs_dim), **kw)
         self.mask = torch.zeros(capacity, **kw)
-        self.position = 0  # next slot to write (ReplayMemory.position)
-        self.size = 0
+        # ring head and fill level live ON THE DEVICE (int64: head, scratch, size, spare): the append kernel reads and
+        # advances them itself, so an acting step captured in a CUDA graph appends where the previous replay stopped
+        self.meta = torch.zeros(4, dtype=torch.int64, device=self.device)
         self.gen = torch.Generator(device=self.device)
         if seed is not None:
             self.gen.manual_seed(seed)
+
+    @property
+    def position(self) -> int:
+        """Next slot to write (ReplayMemory.position); reading it synchronises with the device."""
+        return int(self.meta[0].item())
+
+    @property
+    def size(self) -> int:
+        return int(self.meta[2].item())
 
     def __len__(self) -> int:
         return self.size
@@ -47,22 +57,21 @@ class DeviceReplay:
             raise ValueError("transition tensors disagree on the number of transitions")
         if done.dtype == torch.bool:
             done = done.view(torch.uint8)
-        ops.replay_push(state.contiguous(), action.contiguous(), reward.contiguous(), next_state.contiguous(),
-                        done.contiguous(), self.state, self.action, self.reward, self.next_state, self.mask, self.position)
-        self.position = (self.position + M) % self.capacity
-        self.size = min(self.capacity, self.size + M)
+        ops.replay_push_dev(state.contiguous(), action.contiguous(), reward.contiguous(), next_state.contiguous(),
+                            done.contiguous(), self.state, self.action, self.reward, self.next_state, self.mask, self.meta)
 
     def sample(self, batch_size: int, recency_weighted: bool = False):
         """-> (state [b,obs], action [b,act], reward [b], next_state [b,obs], mask [b]) as `memory.sample` returns them
         (pytorch_sac_temp/sac.py:48).  Uniform with replacement, or with probability rising linearly with recency
         (the `unbalance_p` scheme of pytorch_ddpg/buffer_tensor.py:78-87: p_i ~ i + 1/2 over insertion order)."""
-        if self.size == 0:
+        head, size = (int(v) for v in self.meta[[0, 2]].tolist())
+        if size == 0:
             raise ValueError("empty replay buffer")
         if recency_weighted:
             u = torch.rand(batch_size, generator=self.gen, device=self.device)
-            age = (u.sqrt() * self.size).long().clamp_(max=self.size - 1)  # inverse CDF of p_i ~ i + 1/2
-            oldest = self.position if self.size == self.capacity else 0
+            age = (u.sqrt() * size).long().clamp_(max=size - 1)  # inverse CDF of p_i ~ i + 1/2
+            oldest = head if size == self.capacity else 0
             idx = (age + oldest) % self.capacity
         else:
-            idx = torch.randint(0, self.size, (batch_size,), generator=self.gen, device=self.device)
+            idx = torch.randint(0, size, (batch_size,), generator=self.gen, device=self.device)
         return self.state[idx], self.action[idx], self.reward[idx], self.next_state[idx], self.mask[idx]

@@ -11,6 +11,7 @@
  *   uavca_reset        <- MultiUAVWorld2D.reset :116-175 / UAVWorld2D.reset uav_world_2d.py:119-135
  *   uavca_observe      <- MultiUAVWorld2D._get_obs :60-109 / UAVWorld2D._get_obs uav_world_2d.py:77-112
  *   uavca_map_action   <- caller-side action mapping      test_sac_multi.py:77-80, test_pytorch_multi.py:80
+ *   uavca_rollout      <- the random-action driver loops    run.py:10-16, run_multi.py:10-16 (K x env.step per call)
  *   uavca_stats        <- env.steps / target_reach_count / collision_count  multi_uav_world_2d.py:166-168,209,221,238
  *   uavca_config       <- constructor kwargs              multi_uav_world_2d.py:13-28, uav_world_2d.py:14-26
  *
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define UAVCA_VERSION 100
+#define UAVCA_VERSION 200
 
 /* world kinds */
 #define UAVCA_KIND_MULTI 0  /* MultiUAVWorld2D: N UAVs per env, 10-feature observation */
@@ -148,13 +149,30 @@ int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* o
  * same three counters summed over the episodes in flight (reach, collisions, steps) and B. */
 int uavca_stats(uavca_handle* h, const void* state, int64_t* out8, void* stream);
 
-/* End-to-end form with HOST buffers; returns when the outputs are in host memory.  `state` stays on the
- * device.  Pinned (page-locked) buffers take the zero-copy path: one launch whose loads/stores go through
- * PCIe directly (mapped host memory); outputs of 256 MB and more leave by DMA instead (chunked pipeline).
- * Pageable buffers are staged: H2D actions, step, D2H obs/reward/done, pipelined in chunks over internal
- * streams.  Works for both kinds (obs_dim from the config). */
+/* End-to-end form with HOST buffers; ordered after the work already queued on `stream`, returns when the
+ * outputs are in host memory.  `state` stays on the device.  Pinned (page-locked) buffers take the zero-copy
+ * path: one launch on `stream` whose loads/stores go through PCIe directly (mapped host memory); outputs of
+ * 256 MB and more leave by DMA instead (chunked pipeline).  Pageable buffers are staged: H2D actions, step,
+ * D2H obs/reward/done, pipelined in chunks over internal streams forked from `stream`.  Works for both kinds
+ * (obs_dim from the config). */
 int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int action_mode, int evaluate,
-                    float* host_obs, float* host_reward, uint8_t* host_done);
+                    float* host_obs, float* host_reward, uint8_t* host_done, void* stream);
+
+/* K consecutive steps in ONE launch (the loops of run.py:10-16 / run_multi.py:10-16).  The state stays in
+ * registers for the K steps; per-step outputs are [K][...] blocks:
+ *   obs float [K][B][N][obs_dim]; reward float [K][B][N]; done uint8 [K][B][N];
+ *   final_obs (nullable) like obs; reset_mask (nullable) uint8 [K][B]; distance (nullable, single world) float [K][B].
+ * Actions: action_block float [K][B][N][2] in `action_mode`, or NULL — then every UAV draws uniform policy-space
+ * actions in [-1,1)^2 from Philox4x32-10 keyed by (action_seed, global env index, UAV, step0 + k) and mapped by
+ * `action_mode` (UAVCA_ACTION_CARTESIAN then means a * max_speed: action_space.sample()); action_out (nullable)
+ * float [K][B][N][2] receives the draws.  Results are bit-identical to K calls of uavca_step_* fed the same actions
+ * (uavca_sample_actions reproduces the draws of one step).  K > 1 needs B*N*obs_dim*4 to be a multiple of 16. */
+int uavca_rollout(uavca_handle* h, void* state, int32_t K, const float* action_block, int action_mode, int evaluate,
+                  uint64_t action_seed, uint64_t step0, float* obs, float* reward, uint8_t* done, float* action_out,
+                  float* final_obs, uint8_t* reset_mask, float* distance, void* stream);
+
+/* out float [B][N][2]: the policy-space actions uavca_rollout draws at global step `step`. */
+int uavca_sample_actions(uavca_handle* h, uint64_t action_seed, uint64_t step, float* out, void* stream);
 
 /* Device-resident replay ring, the hand-off to the learner side ("next" row; replaces ReplayMemory.push,
  * pytorch_sac_temp/replay_memory.py:15-19, and ReplayBuffer.append, pytorch_ddpg/buffer_tensor.py:40-59).
@@ -166,6 +184,15 @@ int uavca_replay_push(const float* obs, const float* action, const float* reward
                       const uint8_t* done, int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs,
                       float* ring_action, float* ring_reward, float* ring_next_obs, float* ring_mask,
                       int64_t capacity, int64_t head, void* stream);
+
+/* The same append with the ring head kept ON THE DEVICE: ring_meta int64[4] (device, zero-initialised by the caller)
+ * holds [0] the slot the next append starts at, [1] scratch, [2] the number of transitions held (<= capacity).  The
+ * call reads the head from ring_meta and advances it itself, so a CUDA-graph replay of an acting step appends where
+ * the previous replay stopped. */
+int uavca_replay_push_dev(const float* obs, const float* action, const float* reward, const float* next_obs,
+                          const uint8_t* done, int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs,
+                          float* ring_action, float* ring_reward, float* ring_next_obs, float* ring_mask,
+                          int64_t capacity, int64_t* ring_meta, void* stream);
 
 /* Fused acting path of the shared SAC policy ("next" row; replaces the per-UAV SAC.select_action round trips,
  * pytorch_sac_temp/sac.py:38-44, with GaussianPolicy.forward/sample, pytorch_sac_temp/model.py:74-101, for all

@@ -99,7 +99,7 @@ def lib():
         build()
         _lib = C.CDLL(_LIB_PATH)
         for name in ("uavo_reset", "uavo_observe", "uavo_step_multi", "uavo_step_single", "uavo_map_action",
-                     "uavo_max_threads"):
+                     "uavo_max_threads", "uavo_sample_actions"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -190,6 +190,12 @@ class Oracle:
         a = np.ascontiguousarray(action, dtype=np.float32).reshape(self.B, self.N, 2)
         out = np.empty_like(a)
         lib().uavo_map_action(C.byref(self.cfg), _ptr(a), C.c_int(action_mode), _ptr(out))
+        return out
+
+    def sample_actions(self, step: int, seed: int = 0):
+        """Policy-space actions in [-1, 1)^2 of global step `step` (the rollout's Philox action stream)."""
+        out = np.empty((self.B, self.N, 2), np.float32)
+        lib().uavo_sample_actions(C.byref(self.cfg), C.c_uint64(seed), C.c_uint64(step), _ptr(out))
         return out
 
     def step(self, action, action_mode=ACTION_CARTESIAN, evaluate=False, want_final_obs=False):

@@ -7,8 +7,10 @@ a record.  This module registers minimal stand-ins in ``sys.mod
     gym_uav_collision_avoidance.envs.UAVWorld2D        (uav_world_2d.py:11)
     gym_uav_collision_avoidance.envs.MultiUAVWorld2D   (multi_uav_world_2d.py:10)
 
-from ``/root/reference`` untouched.  It exists only where ``/root/reference`` exists (the build container):
-it validates oracle/uav_oracle.c and generates tests/golden/.  Nothing that runs on the GPU box imports it.
+from ``/root/reference`` untouched — or, on the GPU box where that checkout does not exist, from the unmodified
+copies of the five env-core files that oracle/build_ref.py leaves under ``oracle/_ref/`` (git-ignored).  In the
+build container it validates oracle/uav_oracle.c and generates tests/golden/; on the GPU box it only serves
+bench.py's literal-reference CPU legs.
 """
 from __future__ import annotations
 
@@ -19,10 +21,24 @@ import types
 import numpy as np
 
 REFERENCE_ROOT = os.environ.get("UAVCA_REFERENCE_ROOT", "/root/reference")
+_TRAVELLING_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # made by oracle/build_ref.py
+
+
+def _has_envs(root: str) -> bool:
+    return os.path.isdir(os.path.join(root, "gym_uav_collision_avoidance", "envs"))
+
+
+if not _has_envs(REFERENCE_ROOT) and _has_envs(_TRAVELLING_COPY):
+    REFERENCE_ROOT = _TRAVELLING_COPY  # the GPU box: unmodified copies of the five env-core files
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "gym_uav_collision_avoidance", "envs"))
+    return _has_envs(REFERENCE_ROOT)
+
+
+def reference_is_checkout() -> bool:
+    """True when the reference is the original checkout (the build container), not the travelling copy."""
+    return reference_available() and REFERENCE_ROOT != _TRAVELLING_COPY
 
 
 class _Box:

@@ -94,7 +94,7 @@ static inline double u53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
-enum { STREAM_POS = 0, STREAM_TGT = 1, STREAM_VEL = 2 };
+enum { STREAM_POS = 0, STREAM_TGT = 1, STREAM_VEL = 2, STREAM_ACT = 3 };
 
 /* One draw of np.random.uniform(low, high, size=(2,)).astype(float32): low + (high-low)*u per component. */
 static inline void draw_pair(const uavca_config* c, int64_t env_global, uint32_t episode, int stream, int uav,
@@ -206,11 +206,11 @@ static void reset_env_multi(const uavca_config* c, uavo_state* s, const uavo_sta
   const uint32_t ep = s->episode[b];
 
   /* fold the finished episode into the running totals */
-  if (s->stats && ep > 0) {
-    s->stats[0] += 1;
-    s->stats[1] += (uint64_t)s->reach[b];
-    s->stats[2] += (uint64_t)s->coll[b];
-    s->stats[3] += (uint64_t)s->steps[b];
+  if (s->stats && ep > 0) { /* atomic: the auto-reset pass runs on the thread pool */
+    __atomic_fetch_add(&s->stats[0], 1, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[1], (uint64_t)s->reach[b], __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[2], (uint64_t)s->coll[b], __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[3], (uint64_t)s->steps[b], __ATOMIC_RELAXED);
   }
 
   if (c->reset_source == UAVCA_SOURCE_POOL && pool && pool_envs > 0) {
@@ -274,11 +274,11 @@ static void reset_env_single(const uavca_config* c, uavo_state* s, const uavo_st
   float* tgt = s->tgt + (size_t)b * 2;
   const int64_t env_global = c->env_index_base + b;
   const uint32_t ep = s->episode[b];
-  if (s->stats && ep > 0) {
-    s->stats[0] += 1;
-    s->stats[1] += (uint64_t)s->reach[b];
-    s->stats[2] += (uint64_t)s->coll[b];
-    s->stats[3] += (uint64_t)s->steps[b];
+  if (s->stats && ep > 0) { /* atomic: the auto-reset pass runs on the thread pool */
+    __atomic_fetch_add(&s->stats[0], 1, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[1], (uint64_t)s->reach[b], __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[2], (uint64_t)s->coll[b], __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[3], (uint64_t)s->steps[b], __ATOMIC_RELAXED);
   }
   if (c->reset_source == UAVCA_SOURCE_POOL && pool && pool_envs > 0) {
     const size_t p = (size_t)((env_global + (int64_t)ep) % pool_envs);
@@ -448,27 +448,79 @@ static void step_env_single(const uavca_config* c, uavo_state* s, int b, const f
   *done = (uint8_t)d;
 }
 
-/* ---- minimal pthread parallel-for over environments -------------------------------------------------- */
+/* ---- persistent pthread pool: parallel-for over environments ----------------------------------------
+ * Workers are created once and parked on a condition variable; a job hands out chunks of envs through an
+ * atomic counter (dynamic schedule: episodes that reset cost more than ones that do not), the calling
+ * thread works too.  No thread is created or joined per step, so the all-cores CPU arm of bench.py measures
+ * the step itself. */
 
 typedef void (*env_fn)(void* ctx, int b);
-typedef struct { env_fn fn; void* ctx; int lo, hi; } pf_job;
-static void* pf_run(void* p) {
-  pf_job* j = (pf_job*)p;
-  for (int b = j->lo; b < j->hi; ++b) j->fn(j->ctx, b);
+#define POOL_MAX 64
+static struct {
+  pthread_t th[POOL_MAX];
+  int nthreads; /* workers created so far */
+  pthread_mutex_t mu;
+  pthread_cond_t cv_start, cv_done;
+  unsigned long gen; /* job generation */
+  int want;          /* workers that take part in the current job */
+  int running;       /* workers still inside the current job */
+  env_fn fn;
+  void* ctx;
+  int B, chunk;
+  int next; /* atomic: first env of the next chunk */
+} g_pool = {.mu = PTHREAD_MUTEX_INITIALIZER, .cv_start = PTHREAD_COND_INITIALIZER, .cv_done = PTHREAD_COND_INITIALIZER};
+
+static void pool_drain(void) {
+  for (;;) {
+    int lo = __atomic_fetch_add(&g_pool.next, g_pool.chunk, __ATOMIC_RELAXED);
+    if (lo >= g_pool.B) return;
+    int hi = lo + g_pool.chunk;
+    if (hi > g_pool.B) hi = g_pool.B;
+    for (int b = lo; b < hi; ++b) g_pool.fn(g_pool.ctx, b);
+  }
+}
+static void* pool_worker(void* arg) {
+  const int id = (int)(intptr_t)arg;
+  unsigned long seen = 0;
+  pthread_mutex_lock(&g_pool.mu);
+  for (;;) {
+    while (g_pool.gen == seen) pthread_cond_wait(&g_pool.cv_start, &g_pool.mu);
+    seen = g_pool.gen;
+    if (id >= g_pool.want) continue;
+    pthread_mutex_unlock(&g_pool.mu);
+    pool_drain();
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.running == 0) pthread_cond_signal(&g_pool.cv_done);
+  }
   return 0;
 }
 static void parallel_for(env_fn fn, void* ctx, int B, int nthreads) {
-  if (nthreads > 64) nthreads = 64;
-  if (nthreads <= 1 || B < 2 * nthreads) { pf_job j = {fn, ctx, 0, B}; pf_run(&j); return; }
-  pthread_t th[64];
-  pf_job jobs[64];
-  int per = (B + nthreads - 1) / nthreads;
-  for (int t = 0; t < nthreads; ++t) {
-    int lo = t * per, hi = lo + per; if (lo > B) lo = B; if (hi > B) hi = B;
-    jobs[t] = (pf_job){fn, ctx, lo, hi};
-    pthread_create(&th[t], 0, pf_run, &jobs[t]);
+  if (nthreads > POOL_MAX) nthreads = POOL_MAX;
+  if (nthreads <= 1 || B < 2 * nthreads) {
+    for (int b = 0; b < B; ++b) fn(ctx, b);
+    return;
   }
-  for (int t = 0; t < nthreads; ++t) pthread_join(th[t], 0);
+  const int helpers = nthreads - 1; /* the caller is the last worker */
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.nthreads < helpers) {
+    pthread_attr_t at;
+    pthread_attr_init(&at);
+    pthread_attr_setdetachstate(&at, PTHREAD_CREATE_DETACHED);
+    if (pthread_create(&g_pool.th[g_pool.nthreads], &at, pool_worker, (void*)(intptr_t)g_pool.nthreads) != 0) break;
+    g_pool.nthreads += 1;
+  }
+  g_pool.fn = fn; g_pool.ctx = ctx; g_pool.B = B;
+  g_pool.chunk = B / (8 * nthreads) > 0 ? B / (8 * nthreads) : 1;
+  __atomic_store_n(&g_pool.next, 0, __ATOMIC_RELAXED);
+  g_pool.want = helpers < g_pool.nthreads ? helpers : g_pool.nthreads;
+  g_pool.running = g_pool.want;
+  g_pool.gen += 1;
+  pthread_cond_broadcast(&g_pool.cv_start);
+  pthread_mutex_unlock(&g_pool.mu);
+  pool_drain();
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.running > 0) pthread_cond_wait(&g_pool.cv_done, &g_pool.mu);
+  pthread_mutex_unlock(&g_pool.mu);
 }
 
 /* ---- batched entry points --------------------------------------------------------------------------- */
@@ -476,19 +528,38 @@ static void parallel_for(env_fn fn, void* ctx, int B, int nthreads) {
 typedef struct {
   const uavca_config* c; uavo_state* s; const float* action; int action_mode; int evaluate;
   double* obs; double* reward; uint8_t* done; float* distance; double* final_obs;
+  const uavo_state* pool; int pool_envs; uint8_t* reset_mask;
 } step_ctx;
+static int want_reset(const uavca_config* c, const uint8_t* done, int N, int steps);
 static void step_multi_body(void* p, int b) {
   step_ctx* x = (step_ctx*)p;
   const int N = x->c->num_agents;
   step_env_multi(x->c, x->s, b, x->action + (size_t)b * N * 2, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
                  x->reward + (size_t)b * N, x->done + (size_t)b * N);
   if (x->final_obs) memcpy(x->final_obs + (size_t)b * N * 10, x->obs + (size_t)b * N * 10, sizeof(double) * N * 10);
+  /* auto-reset in place (envs are independent; the shared totals are folded atomically) */
+  const int rs = want_reset(x->c, x->done + (size_t)b * N, N, x->s->steps[b]);
+  if (x->reset_mask) x->reset_mask[b] = (uint8_t)rs;
+  if (rs) {
+    uavo_state* s = x->s;
+    reset_env_multi(x->c, s, x->pool, x->pool_envs, b);
+    for (int i = 0; i < N; ++i)
+      obs_multi(x->c, s->pos + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt + (size_t)b * N * 2, N, i,
+                x->obs + ((size_t)b * N + i) * 10);
+  }
 }
 static void step_single_body(void* p, int b) {
   step_ctx* x = (step_ctx*)p;
   step_env_single(x->c, x->s, b, x->action + (size_t)b * 2, x->action_mode, x->obs + (size_t)b * 4, x->reward + b,
                   x->done + b, x->distance ? x->distance + b : 0);
   if (x->final_obs) memcpy(x->final_obs + (size_t)b * 4, x->obs + (size_t)b * 4, sizeof(double) * 4);
+  const int rs = want_reset(x->c, x->done + b, 1, x->s->steps[b]);
+  if (x->reset_mask) x->reset_mask[b] = (uint8_t)rs;
+  if (rs) {
+    uavo_state* s = x->s;
+    reset_env_single(x->c, s, x->pool, x->pool_envs, b);
+    obs_single(x->c, s->pos + (size_t)b * 2, s->vel + (size_t)b * 2, s->tgt + (size_t)b * 2, 1, x->obs + (size_t)b * 4);
+  }
 }
 
 static int want_reset(const uavca_config* c, const uint8_t* done, int N, int steps) {
@@ -537,19 +608,9 @@ int uavo_step_multi(const uavca_config* c, uavo_state* s, const uavo_state* pool
                     int action_mode, int evaluate, double* obs, double* reward, uint8_t* done, double* final_obs,
                     uint8_t* reset_mask, int nthreads) {
   const int N = c->num_agents, B = c->num_envs;
-  step_ctx ctx = {c, s, action, action_mode, evaluate, obs, reward, done, 0, final_obs};
-  parallel_for(step_multi_body, &ctx, B, nthreads);
-  /* auto-reset pass is serial because it folds into the shared totals */
-  for (int b = 0; b < B; ++b) {
-    int rs = want_reset(c, done + (size_t)b * N, N, s->steps[b]);
-    if (reset_mask) reset_mask[b] = (uint8_t)rs;
-    if (rs) {
-      reset_env_multi(c, s, pool, pool_envs, b);
-      for (int i = 0; i < N; ++i)
-        obs_multi(c, s->pos + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt + (size_t)b * N * 2, N, i,
-                  obs + ((size_t)b * N + i) * 10);
-    }
-  }
+  step_ctx ctx = {c, s, action, action_mode, evaluate, obs, reward, done, 0, final_obs, pool, pool_envs, reset_mask};
+  (void)N; (void)B;
+  parallel_for(step_multi_body, &ctx, c->num_envs, nthreads);
   return 0;
 }
 
@@ -557,22 +618,31 @@ int uavo_step_single(const uavca_config* c, uavo_state* s, const uavo_state* poo
                      int action_mode, double* obs, double* reward, uint8_t* done, float* distance, double* final_obs,
                      uint8_t* reset_mask, int nthreads) {
   const int B = c->num_envs;
-  step_ctx ctx = {c, s, action, action_mode, 0, obs, reward, done, distance, final_obs};
+  step_ctx ctx = {c, s, action, action_mode, 0, obs, reward, done, distance, final_obs, pool, pool_envs, reset_mask};
   parallel_for(step_single_body, &ctx, B, nthreads);
-  for (int b = 0; b < B; ++b) {
-    int rs = want_reset(c, done + b, 1, s->steps[b]);
-    if (reset_mask) reset_mask[b] = (uint8_t)rs;
-    if (rs) {
-      reset_env_single(c, s, pool, pool_envs, b);
-      obs_single(c, s->pos + (size_t)b * 2, s->vel + (size_t)b * 2, s->tgt + (size_t)b * 2, 1, obs + (size_t)b * 4);
-    }
-  }
   return 0;
 }
 
 int uavo_map_action(const uavca_config* c, const float* in, int action_mode, float* out) {
   const size_t M = (size_t)c->num_envs * c->num_agents;
   for (size_t m = 0; m < M; ++m) map_action(c, action_mode, in[2 * m], in[2 * m + 1], out + 2 * m, out + 2 * m + 1);
+  return 0;
+}
+
+/* The random-action stream of the driver loops (run.py:10-16, run_multi.py:10-16: env.action_space.sample()) as a
+ * counter-based draw: uniform in [-1, 1)^2 per (global env, UAV, global step t); one Philox block serves steps 2q, 2q+1.
+ * 24-bit uniforms, so every value is exact in float32. */
+int uavo_sample_actions(const uavca_config* c, uint64_t seed, uint64_t t, float* out) {
+  const int N = c->num_agents;
+  for (int b = 0; b < c->num_envs; ++b)
+    for (int i = 0; i < N; ++i) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)(c->env_index_base + b), (uint32_t)(t >> 1), ((uint32_t)STREAM_ACT << 16) | (uint32_t)i,
+                    (uint32_t)(t >> 33), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+      const uint32_t wa = (t & 1) ? r[2] : r[0], wb = (t & 1) ? r[3] : r[1];
+      out[((size_t)b * N + i) * 2] = (float)((double)(wa >> 8) * (2.0 / 16777216.0) - 1.0);
+      out[((size_t)b * N + i) * 2 + 1] = (float)((double)(wb >> 8) * (2.0 / 16777216.0) - 1.0);
+    }
   return 0;
 }
 

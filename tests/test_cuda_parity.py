@@ -153,6 +153,20 @@ def test_multi_rollout_all_agent_counts(n):
     assert ev["resets"] > 0
 
 
+@pytest.mark.parametrize("n", [2, 5, 8, 16, 32])
+@pytest.mark.parametrize("mode", [O.RESET_ON_ANY_DONE, O.RESET_ON_ALL_DONE, O.RESET_ON_ANY_DONE | O.RESET_ON_DONE0])
+def test_multi_rollout_reset_modes(n, mode):
+    """any(dones) / all(dones) with several envs per warp: an env's reset decision must only see its own done bits
+    (reset_mask, episode and step counters bit-exact against the oracle's want_reset)."""
+    # a small box and random actions: UAVs leave it all the time (done = out of bounds), one by one
+    cfg = O.multi_config(515, n, reset_mode=mode, max_episode_steps=60, seed=300 + n, x_size=9.0, y_size=9.0,
+                         collider_radius=0.3, hard_collision_radius=0.15)
+    ev, orc = rollout_vs_oracle(cfg, steps=150, seed=40 + n)
+    assert ev["resets"] > 515 and ev["done"] > 0
+    if mode & O.RESET_ON_ANY_DONE:
+        assert int(orc.state.stats[3]) < 50 * int(orc.state.stats[0]), "most episodes should end before the step limit"
+
+
 def test_multi_rollout_crowded_collisions_and_reaches():
     cfg = O.multi_config(2048, 8, reset_mode=O.RESET_ON_ALL_DONE, max_episode_steps=300, seed=77, x_size=16.0, y_size=16.0)
     ev, orc = rollout_vs_oracle(cfg, steps=400, seed=3, crowd=1.2)
