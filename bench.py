@@ -1,27 +1,36 @@
 #!/usr/bin/env python
 """bench.py — UAV env-steps/s of the batched environment step on B200, next to the reference CPU step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c4s|...] [--impl ours|reference]
 
-A "step" is one pass of the hot path (one `uavca_step_*` launch) over one batch of B envs.  The default workload
-is BASELINE.json configs[2] — multi-UAV, N=8 UAVs per env, B=65,536 envs per GPU, random cartesian actions,
-auto-reset on dones[0] / 1,500 steps from the on-device Philox stream.  One batch is ~50 MB (L2-resident on a
-B200), so the bench cycles through a ring of independent batches whose combined footprint exceeds L2 several
-times over: every timed launch reads its state and actions from HBM.  Steps are replayed from a CUDA graph and
-timed with CUDA events; multi-GPU runs are one process per GPU (torchrun), envs sharded with no per-step
-collective, time = max over ranks.
+A "step" is one pass of the hot path (one `uavca_step_*` launch) over one batch of B envs.  Default workload:
+BASELINE.json configs[2] at N=1 GPU — multi-UAV, N=8 UAVs per env, B=65,536 envs, random cartesian actions, auto-reset
+on dones[0] / 1,500 steps from the on-device Philox stream — and configs[3] when `--gpus` > 1 — N=32, 1,048,576 envs
+IN TOTAL, sharded over the GPUs (`c4s`).  Small batches are L2-resident on a B200, so the bench cycles through a ring
+of independent batches whose combined footprint exceeds L2 several times over: every timed launch reads its state and
+actions from HBM.  Steps are replayed from a CUDA graph and timed with CUDA events: >= 5 repetitions of the K-step
+region, each bracketed by events; the line reports the MEDIAN repetition (`value`, `ms_per_step`) and the best one.
+Multi-GPU runs are one process per GPU (torchrun), envs sharded with no per-step collective, time = max over ranks.
 
-The JSON line carries `value` (device-resident throughput), `e2e` (same metric through `uavca_step_host` with
-pinned HOST buffers: H2D actions + step + D2H obs/reward/done inside the timed region), `roofline` (algorithmic
-bytes per launch / measured launch time against MEASURED_PEAKS.json) and `cpu_baseline` (the oracle port of the
-reference step timed on this host).  `--impl reference` times the reference's CPU algorithm (oracle port, the
-Python reference cannot travel to the GPU box) with all host threads.
+The JSON line carries
+  value        device-resident throughput, one launch per step (inputs resident in HBM);
+  e2e          the same metric through `uavca_step_host` with pinned HOST buffers: H2D actions + step + D2H
+               obs/reward/done inside the timed region, next to the PCIe copy ceiling measured on the same rank;
+  roofline     algorithmic bytes per launch / measured launch time against MEASURED_PEAKS.json (+ the same for one
+               dependent launch at a time, `frac_single_stream`);
+  rollout      K steps per launch (`uavca_rollout`: Philox actions / an action block), one stream;
+  cpu_baseline the oracle port of the reference step on one host thread, `cpu_baseline_literal` the LITERAL Python
+               reference (oracle/_ref, when it travelled) on one core.
+`--impl reference` times the reference's CPU algorithm (oracle port, all host threads) on the same workload.
+`--workload c1` is BASELINE configs[0] (single-UAV gym loop, 1,000 steps): the literal reference against the B=1
+drop-in class.  `--workload c5r` is configs[4]: policy inference + env step + replay append per acting step.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import sys
 import threading
 import time
@@ -31,21 +40,30 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: kind, N, B per GPU, algorithmic bytes per UAV-step (SURVEY.md §8d / DESIGN.md §5), default steps
+    # name: kind, N, B per GPU, default steps
+    "c1": dict(kind="single", N=1, B=1, desc="single-UAV gym loop, random actions, 1,000 steps (BASELINE configs[0])", steps=1000, loop=True),
     "c3": dict(kind="multi", N=8, B=65536, desc="multi-UAV N=8, B=65,536 envs/GPU (BASELINE configs[2])", steps=20000),
     "c2": dict(kind="single", N=1, B=65536, desc="single-UAV, B=65,536 envs/GPU (BASELINE configs[1])", steps=20000, streams=4),
     "c4": dict(kind="multi", N=32, B=1048576, desc="multi-UAV N=32, B=1,048,576 envs/GPU (BASELINE configs[3] shape)", steps=300),
     "c4s": dict(kind="multi", N=32, B=1048576, desc="multi-UAV N=32, B=1,048,576 envs IN TOTAL, sharded over the GPUs (BASELINE configs[3])",
-                steps=300, shard_total=True),
+                steps=600, shard_total=True),
     "c5": dict(kind="multi", N=10, B=16384, desc="multi-UAV N=10, B=16,384 envs/GPU (BASELINE configs[4] env part)", steps=20000, streams=4),
+    "c5r": dict(kind="multi", N=10, B=16384, desc="SAC-style acting step: policy 10-256-256-2 + env step (polar map fused) + replay append, "
+                                                   "N=10, B=16,384 envs/GPU (BASELINE configs[4])", steps=2000, acting=True),
 }
 L2_BYTES = 126e6
 GRAPH_STEPS = 200
+MIN_REPS, MAX_REPS, LOADED_MS = 5, 400, 60.0  # repetitions of the K-step region; enough of them to sample clocks under load
 
 
 def algorithmic_bytes_per_unit(kind: str, N: int) -> float:
     """multi 107 B per UAV-step + 24/N for the per-env counters; single 89 B per env-step."""
     return 89.0 if kind == "single" else 107.0 + 24.0 / N
+
+
+def rollout_bytes_per_unit(kind: str, N: int, block: bool) -> float:
+    """What a K-step rollout has to move per UAV-step (state stays in registers): obs + reward + done (+ the action)."""
+    return (16 if kind == "single" else 40) + 4 + 1 + (8 if block else 0)
 
 
 def footprint_bytes_per_unit(kind: str) -> float:
@@ -71,7 +89,7 @@ class ClockSampler:
         0x100: "display_clock_setting",
     }
 
-    def __init__(self, index: int, period_s: float = 0.01):
+    def __init__(self, index: int, period_s: float = 0.004):
         self.index, self.period = index, period_s
         self.sm, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
@@ -114,10 +132,11 @@ class ClockSampler:
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
         s = sorted(self.sm)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "sampled": "during the timed repetitions"}
 
 
-# ---- CPU side: the oracle port of the reference step ------------------------------------------------------------
+# ---- CPU side ---------------------------------------------------------------------------------------------------
 
 
 def time_oracle(kind: str, N: int, envs: int, steps: int, nthreads: int, seed: int = 0):
@@ -135,13 +154,43 @@ def time_oracle(kind: str, N: int, envs: int, steps: int, nthreads: int, seed: i
     orc = O.Oracle(cfg, nthreads=nthreads)
     orc.reset()
     rng = np.random.default_rng(seed)
-    acts = [rng.uniform(-amax, amax, size=(envs, N, 2)).astype(np.float32) for _ in range(8)]
+    acts = [rng.uniform(-amax, amax, size=(envs, N, 2)).astype(np.float32) for _ in range(4)]
     orc.step(acts[0])
     t0 = time.perf_counter()
     for k in range(steps):
-        orc.step(acts[k % 8])
+        orc.step(acts[k % 4])
     dt = time.perf_counter() - t0
     return envs * N * steps / dt, dt
+
+
+def time_literal(kind: str, N: int, steps: int, repeats: int = 3):
+    """The LITERAL Python reference on one core: the run.py / run_multi.py loop — random
+    actions, reset on done (dones[0] for the multi world), np.random.seed(0), best of `repeats`.  Returns
+    (UAV-steps/s, seconds of the best repeat) or None where neither /root/reference nor oracle/_ref exists."""
+    import numpy as np
+
+    from oracle import ref_loader as R
+
+    if not R.reference_available():
+        return None
+    UAVWorld2D, MultiUAVWorld2D = R.load_reference()
+    best = None
+    for _ in range(repeats):
+        np.random.seed(0)
+        env = UAVWorld2D() if kind == "single" else MultiUAVWorld2D(num_agents=N)
+        env.reset()
+        if kind == "single":
+            acts = [env.action_space.sample() for _ in range(steps)]
+        else:
+            acts = [[np.random.uniform(-10, 10, 2).astype(np.float32) for _ in range(N)] for _ in range(steps)]
+        t0 = time.perf_counter()
+        for a in acts:
+            _, _, done, _ = env.step(a)
+            if done if kind == "single" else done[0]:
+                env.reset()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return N * steps / best, best
 
 
 def cpu_model() -> str:
@@ -155,56 +204,167 @@ def cpu_model() -> str:
     return "unknown"
 
 
+def workload_config(args, wl, world, B_per_gpu):
+    """The part of `config` both arms share (the driver compares it)."""
+    return {"workload": wl["desc"], "uavs_per_env": wl["N"], "envs_per_gpu": B_per_gpu, "envs_total": B_per_gpu * world if not wl.get("shard_total") else wl["B"],
+            "actions": "uniform random cartesian", "auto_reset": "dones[0] or 1500 steps"}
+
+
+def shard_envs(wl, rank, world):
+    if wl.get("shard_total"):
+        from gym_uav_collision_avoidance_b200 import sharding as _sh
+
+        return _sh.shard_range(wl["B"], rank, world)[1]
+    return wl["B"]
+
+
+def literal_baseline(kind, N):
+    """cpu_baseline_literal: a bounded sample (~3-10 s) of the literal reference, or why it is absent."""
+    steps = 1000 if kind == "single" else max(20, int(4000 // (N * N // 8 + 1)))
+    try:
+        res = time_literal(kind, N, steps, repeats=2)
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"literal reference failed to run: {exc!r}"[:200]}
+    if res is None:
+        return {"unavailable": "oracle/_ref was not built (python -m oracle.build_ref needs /root/reference)"}
+    ups, dt = res
+    return {"value": ups, "unit": "UAV env-steps/s", "cores": 1, "kind": "reference",
+            "sample": f"1 env x {N} UAVs x {steps} steps, the run.py / run_multi.py loop on the unmodified reference env "
+                      f"(oracle/_ref), best of 2 ({dt:.2f} s)"}
+
+
 def run_reference(args, wl, rank, world):
-    """--impl reference: the reference's CPU algorithm for the path (oracle port; the Python reference itself
-    cannot travel to the GPU box), all host threads, bounded sample of the same workload per step."""
+    """--impl reference: the reference's CPU algorithm for the path on all host threads (oracle port: the Python
+    reference is single-threaded and ~300x slower; it is reported beside it as `cpu_baseline_literal`)."""
     if rank != 0:
         return
     from oracle import oracle as O
 
-    nthreads = O.max_threads()
-    envs = 8192 if wl["N"] <= 8 else 1024
-    envs = min(envs, wl["B"])
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    steps = min(steps, 400)  # bounded: a step here is one pass over `envs` envs
-    time_oracle(wl["kind"], wl["N"], envs, max(1, min(warm, 5)), nthreads)
-    ups, dt = time_oracle(wl["kind"], wl["N"], envs, steps, nthreads)
     unit = "UAV env-steps/s"
-    sample = f"{envs} envs x {wl['N']} UAVs x {steps} steps of the {args.workload} workload (oracle/uav_oracle.c, pthreads)"
+    if wl.get("loop"):  # c1: the literal reference itself, one core (it is single-threaded)
+        lit = time_literal("single", 1, steps if args.steps else 1000, repeats=3)
+        if lit is None:
+            emit({"impl": "reference", "unavailable": "oracle/_ref missing: the literal reference did not travel"})
+            return
+        ups, dt = lit
+        emit({"impl": "reference", "metric": "UAV env-steps/sec", "value": ups, "unit": unit, "n_gpus": args.gpus, "steps": steps,
+              "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": "f64/f32 mixed (as the reference)", "data": "synthetic",
+              "config": dict(workload_config(args, wl, 1, 1), host_cpu=cpu_model()),
+              "cpu_baseline": {"value": ups, "unit": unit, "cores": 1, "kind": "reference",
+                               "sample": f"UAVWorld2D, {steps} steps of the run.py loop, np.random.seed(0), best of 3"},
+              "e2e": {"value": ups, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+        return
+    nthreads = O.max_threads()
+    B = shard_envs(wl, 0, max(1, args.gpus))
+    envs = min(B, 131072 if wl["N"] >= 16 else B)  # the full per-GPU batch; N=32 is bounded to the 8-GPU shard size
+    steps = min(steps, 200)
+    time_oracle(wl["kind"], wl["N"], envs, max(1, min(warm, 3)), nthreads)
+    ups, dt = time_oracle(wl["kind"], wl["N"], envs, steps, nthreads)
+    sample = (f"{envs} envs x {wl['N']} UAVs x {steps} steps of the {args.workload} workload "
+              f"(oracle/uav_oracle.c, persistent pool of {nthreads} pthreads)")
     line = {
         "impl": "reference", "metric": "UAV env-steps/sec", "value": ups, "unit": unit, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 mixed (as the reference)", "data": "synthetic",
-        "config": {"workload": wl["desc"], "envs_per_step": envs, "uavs_per_env": wl["N"], "actions": "uniform random cartesian",
-                   "auto_reset": "dones[0] or 1500 steps", "host_cpu": cpu_model()},
+        "scaling": "strong" if wl.get("shard_total") else "weak", "vs_baseline": None, "dtype": "f64/f32 mixed (as the reference)", "data": "synthetic",
+        "config": dict(workload_config(args, wl, max(1, args.gpus), B), envs_per_step=envs, host_cpu=cpu_model(), host_threads=nthreads),
         "cpu_baseline": {"value": ups, "unit": unit, "cores": nthreads, "kind": "port", "sample": sample},
+        "cpu_baseline_literal": literal_baseline(wl["kind"], wl["N"]),
         "e2e": {"value": ups, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
 
 
+# ---- host topology (e2e) ------------------------------------------------------------------------------------------
+
+
+def gpu_numa_node(index: int):
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        for cand in (bus.lower(), bus.lower()[4:] if len(bus) > 12 else bus.lower()):
+            p = f"/sys/bus/pci/devices/{cand}/numa_node"
+            if os.path.exists(p):
+                return int(open(p).read().strip())
+    except Exception:
+        pass
+    return None
+
+
+def bind_to_gpu_numa_node(index: int) -> dict:
+    """Pin this rank to the CPUs of its GPU's NUMA node (pinned host buffers are then allocated next to the GPU's PCIe
+    root instead of all ranks sharing one socket's memory).  Best effort; reports what happened."""
+    info = {"gpu_numa_node": gpu_numa_node(index), "cpu_affinity_before": len(os.sched_getaffinity(0))}
+    node = info["gpu_numa_node"]
+    if node is None or node < 0:
+        info["bound"] = False
+        return info
+    try:
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        info["bound"] = True
+        info["cpus"] = len(cpus)
+    except Exception as exc:  # noqa: BLE001  (cpuset of the container may not include that node)
+        info["bound"] = False
+        info["why"] = repr(exc)[:120]
+    return info
+
+
 # ---- GPU side ---------------------------------------------------------------------------------------------------
+
+
+def timed_reps(torch, stream, replay_fn, est_ms, dev, barrier):
+    """>= MIN_REPS repetitions of `replay_fn` (one K-step region), each bracketed by CUDA events on `stream`; enough of
+    them to keep the GPU loaded for LOADED_MS so that the clock sampler sees the timed region.  Returns per-rep ms."""
+    reps = int(min(MAX_REPS, max(MIN_REPS, LOADED_MS / max(est_ms, 1e-3))))
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    barrier()
+    with torch.cuda.stream(stream):
+        evs[0].record(stream)
+        for i in range(reps):
+            replay_fn()
+            evs[i + 1].record(stream)
+    stream.synchronize()
+    barrier()
+    return [evs[i].elapsed_time(evs[i + 1]) for i in range(reps)]
 
 
 def run_ours(args, wl, rank, world, local_rank):
     import torch
 
     import gym_uav_collision_avoidance_b200 as G
+    from gym_uav_collision_avoidance_b200 import sharding
 
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    topo = bind_to_gpu_numa_node(local_rank) if not args.no_numa_bind else {"bound": False, "why": "--no-numa-bind"}
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
-    kind, N, B = wl["kind"], wl["N"], wl["B"]
-    if wl.get("shard_total"):  # strong scaling: the named total is cut into contiguous shards
-        from gym_uav_collision_avoidance_b200 import sharding as _sh
 
-        B = _sh.shard_range(wl["B"], rank, world)[1]
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    if wl.get("loop"):
+        return run_c1(args, wl, G, torch, dev)
+    if wl.get("acting"):
+        return run_acting(args, wl, G, torch, dev, rank, world, dist, barrier)
+
+    kind, N = wl["kind"], wl["N"]
+    B = shard_envs(wl, rank, world)
     K, W = args.steps, max(args.warmup, 3)
     units_per_step = B * N
     # ring of independent batches: combined footprint > 3x L2 so that every launch streams from HBM
@@ -230,16 +390,15 @@ def run_ours(args, wl, rank, world, local_rank):
     def one_step(k):
         envs[k % ring].step(actions[(k + k // ring) % n_act])
 
+    def launches():
+        return sum(e.launch_count for e in envs)
+
     # The batches of the ring are independent environments: like a double-buffered env pool they are pipelined over
     # `S` streams, so that one batch's ramp-up overlaps the previous batch's tail.  A batch always runs on the same
     # stream (its own steps stay ordered).  S=1 (--streams 1) serialises every launch behind the previous one.
-
-    # warm-up (eager), then capture graphs of GRAPH_STEPS steps and of the remainder
     for k in range(W):
         one_step(k)
     torch.cuda.synchronize(dev)
-    launches_before = sum(e.launch_count for e in envs)
-    q, rem = divmod(K, GRAPH_STEPS)
     stream = torch.cuda.Stream(device=dev)
 
     def capture(n, k0, n_streams):
@@ -260,59 +419,58 @@ def run_ours(args, wl, rank, world, local_rank):
                 stream.wait_event(join)
         return g
 
-    # the same steps once more on ONE stream (every launch waits for the previous one): reported beside the headline
-    serial_us = None
-    if S > 1 and q > 0:
-        l0 = sum(e.launch_count for e in envs)
-        g_ser = capture(GRAPH_STEPS, W, 1)
-        g_ser.replay()
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(1, min(q, 20))
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(reps):
-                g_ser.replay()
-            e1.record(stream)
-        stream.synchronize()
-        serial_us = e0.elapsed_time(e1) * 1e3 / (reps * GRAPH_STEPS)
-        del g_ser
-        launches_before += sum(e.launch_count for e in envs) - l0
-
-    g_main = capture(GRAPH_STEPS, W, S) if q > 0 else None
-    launches_per_graph = sum(e.launch_count for e in envs) - launches_before
-    g_rem = capture(rem, W + GRAPH_STEPS, S) if rem > 0 else None
-    launches_rem = sum(e.launch_count for e in envs) - launches_before - launches_per_graph
-    if g_main is not None:
-        g_main.replay()  # graph warm-up (upload)
-    if g_rem is not None:
-        g_rem.replay()
-    torch.cuda.synchronize(dev)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    def graphs_for(n_streams):
+        """Graphs replaying exactly K steps: q replays of a GRAPH_STEPS-step graph + one graph of the remainder."""
+        q, rem = divmod(K, GRAPH_STEPS)
+        g_main = capture(GRAPH_STEPS, W, n_streams) if q > 0 else None
+        g_rem = capture(rem, W + GRAPH_STEPS, n_streams) if rem > 0 else None
+        for g in (g_main, g_rem):
+            if g is not None:
+                g.replay()  # graph warm-up (upload)
         torch.cuda.synchronize(dev)
 
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with ClockSampler(local_rank) as clocks:
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
+        def replay():
             for _ in range(q):
                 g_main.replay()
             if g_rem is not None:
                 g_rem.replay()
-            ev1.record(stream)
-        stream.synchronize()
-        if K * 1 < 2000:  # short runs: keep sampling a little so that at least one clock sample lands
-            time.sleep(0.03)
-    barrier()
-    from gym_uav_collision_avoidance_b200 import sharding
+        return replay, (g_main, g_rem)
 
-    ms = sharding.max_over_ranks(ev0.elapsed_time(ev1), device=dev)  # device time, slowest rank
-    gpu_launches = q * launches_per_graph + launches_rem
-    value = world * units_per_step * K / (ms * 1e-3)
+    # launches of ours per K-step region: one kernel per step (a batch whose ragged rest needs its own launch has two)
+    l0 = launches()
+    one_step(0)
+    torch.cuda.synchronize(dev)
+    per_region_launches = (launches() - l0) * K
+    est_ms = units_per_step * algorithmic_bytes_per_unit(kind, N) / 3.5e12 * 1e3 * K  # rough, only sizes the repetition count
+
+    # one stream: every launch waits for the previous one (what a single env pool with a policy between steps sees)
+    replay1, keep1 = graphs_for(1)
+    with ClockSampler(local_rank) as clocks1:
+        t1 = timed_reps(torch, stream, replay1, est_ms, dev, barrier)
+    del keep1
+    # S streams: independent batches in flight
+    if S > 1:
+        replayS, keepS = graphs_for(S)
+        with ClockSampler(local_rank) as clocks:
+            tS = timed_reps(torch, stream, replayS, est_ms, dev, barrier)
+        del keepS
+    else:
+        tS, clocks = t1, clocks1
+
+    def reduce_reps(ts):
+        ts = [sharding.max_over_ranks(t, device=dev) for t in ts] if dist is not None else ts
+        return statistics.median(ts), min(ts), len(ts)
+
+    ms_med, ms_best, n_reps = reduce_reps(tS)
+    ms1_med, ms1_best, n_reps1 = reduce_reps(t1)
+    gpu_launches = per_region_launches * (n_reps + (n_reps1 if S > 1 else 0))
+    value = world * units_per_step * K / (ms_med * 1e-3)
+
+    # ---- K steps per launch (uavca_rollout), ONE stream: Philox actions (the run_multi.py loop) and an action block
+    rollout = None
+    if not args.no_rollout:
+        rollout = measure_rollout(torch, G, envs, ring, kind, N, B, amax, dev, stream, barrier, reduce_reps, world, args.rollout_k)
+        gpu_launches += rollout.pop("_launches")
 
     # ---- end to end through the host-buffer C-ABI call (uavca_step_host): pinned host buffers, H2D + step + D2H
     D = 4 if kind == "single" else 10
@@ -322,19 +480,25 @@ def run_ours(args, wl, rank, world, local_rank):
     h_obs = torch.empty((B, N, D), dtype=torch.float32).pin_memory()
     h_rew = torch.empty((B, N), dtype=torch.float32).pin_memory()
     h_done = torch.empty((B, N), dtype=torch.uint8).pin_memory()
-    e2e_steps = max(1, min(K, 200 if units_per_step < 4e6 else 10))
+    e2e_steps = max(1, min(K, 200 if units_per_step < 4e6 else 20))
     e2e_ring = min(ring, 4)  # PCIe-bound: L2 residency is irrelevant here; keep the lazily created staging small
     for k in range(2 * e2e_ring):
         envs[k % e2e_ring].step_host(h_act[k % 2], h_obs, h_rew, h_done)
-    barrier()
-    launches_e2e0 = sum(e.launch_count for e in envs)
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        envs[k % e2e_ring].step_host(h_act[k % 2], h_obs, h_rew, h_done)
-    torch.cuda.synchronize(dev)
-    e2e_s = sharding.max_over_ranks(time.perf_counter() - t0, device=dev)
+    l0 = launches()
+    e2e_times = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            envs[k % e2e_ring].step_host(h_act[k % 2], h_obs, h_rew, h_done)
+        torch.cuda.synchronize(dev)
+        e2e_times.append(sharding.max_over_ranks(time.perf_counter() - t0, device=dev))
+    e2e_s = statistics.median(e2e_times)
     e2e_value = world * units_per_step * e2e_steps / e2e_s
-    gpu_launches += sum(e.launch_count for e in envs) - launches_e2e0
+    gpu_launches += launches() - l0
+    # the PCIe ceiling of this rank, measured the same way: one pinned D2H copy of a step's outputs + the H2D of its actions
+    d2h_bytes, h2d_bytes = units_per_step * (D * 4 + 4 + 1), units_per_step * 8
+    pcie = measure_pcie(torch, dev, envs[0], h_obs, h_act[0], actions[0], barrier, sharding)
 
     # episode statistics: the only collective of the path (NCCL all-reduce of 4 counters, outside the timed region)
     local = dict.fromkeys(sharding.STAT_KEYS, 0)
@@ -343,51 +507,245 @@ def run_ours(args, wl, rank, world, local_rank):
         for k in sharding.STAT_KEYS:
             local[k] += s[k]
     stats = sharding.reduce_stats(local, device=dev)
+    topos = gather_objects(dist, topo, world)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         alg = algorithmic_bytes_per_unit(kind, N)
-        launch_s = ms * 1e-3 / K
+        launch_s = ms_med * 1e-3 / K
         achieved = units_per_step * alg / launch_s / 1e9
-        cpu = None
-        if not args.no_cpu_baseline and world == 1:  # a reported baseline, timed on rank 0 at N=1 only
+        serial_us = ms1_med / K * 1e3
+        cpu = lit = None
+        if not args.no_cpu_baseline and world == 1:  # reported baselines, timed on rank 0 at N=1 only
             c_envs = min(B, 4096 if N <= 8 else 512)
             c_steps = max(20, int(12e6 // (c_envs * N)))
             ups, dt = time_oracle(kind, N, c_envs, c_steps, 1)
             cpu = {"value": ups, "unit": "UAV env-steps/s", "cores": 1, "kind": "port",
                    "sample": f"{c_envs} envs x {N} UAVs x {c_steps} steps of the same workload, oracle/uav_oracle.c on 1 thread "
                              f"({dt:.1f} s; host: {cpu_model()}, {os.cpu_count()} logical cores)"}
+            lit = literal_baseline(kind, N)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get(args.workload)
+        e2e_bytes_s = e2e_value / world * (D * 4 + 4 + 1 + 8)
         line = {
             "metric": "UAV env-steps/sec", "value": value, "unit": "UAV env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if wl.get("shard_total") else "weak", "vs_baseline": None,
-            "dtype": "f64 velocity / f32 position+obs (as the reference)", "data": "synthetic",
-            "config": {"workload": wl["desc"], "envs_per_gpu": B, "uavs_per_env": N, "env_steps_per_s": value / N,
-                       "actions": "uniform random cartesian, resident in HBM", "auto_reset": "on-device Philox, dones[0] or 1500 steps",
-                       "l2": f"ring of {ring} independent batches ({ring * per_batch / 1e6:.0f} MB > L2) so every launch streams from HBM",
-                       "timing": f"CUDA events around CUDA-graph replays ({GRAPH_STEPS} steps per graph)", "parallelism": f"env-sharded x{world}, no per-step collective",
-                       "streams": S, "pipelining": (f"independent batches of the ring pipelined over {S} streams (a batch's own steps stay ordered)" if S > 1 else "none: every launch waits for the previous one"),
-                       "single_stream_us_per_step": serial_us},
-            "e2e": {"value": e2e_value, "unit": "UAV env-steps/s", "h2d_bytes_per_step": units_per_step * 8,
-                    "d2h_bytes_per_step": units_per_step * (D * 4 + 4 + 1), "steps": e2e_steps,
-                    "path": "uavca_step_host, pinned host buffers: outputs >= 256 MB leave by DMA (chunked H2D/step/D2H pipeline over two "
-                            "streams), smaller batches are zero-copy (the kernel reads/writes mapped host memory through PCIe)"
-                            + (f" [forced: {os.environ['UAVCA_HOST_PATH']}]" if os.environ.get("UAVCA_HOST_PATH") else "")},
+            "warmup": W, "ms_per_step": ms_med / K, "higher_is_better": True, "scaling": "strong" if wl.get("shard_total") else "weak",
+            "vs_baseline": None, "dtype": "f64 velocity / f32 position+obs (as the reference)", "data": "synthetic",
+            "config": dict(workload_config(args, wl, world, B), env_steps_per_s=value / N,
+                           actions_resident="in HBM", auto_reset_source="on-device Philox",
+                           l2=f"ring of {ring} independent batches ({ring * per_batch / 1e6:.0f} MB > L2) so every launch streams from HBM",
+                           timing=f"CUDA events around each of {n_reps} repetitions of the {K}-step region (CUDA-graph replays, "
+                                  f"{GRAPH_STEPS} steps per graph); value = median repetition",
+                           parallelism=f"env-sharded x{world}, no per-step collective", streams=S,
+                           pipelining=(f"independent batches of the ring pipelined over {S} streams (a batch's own steps stay ordered)"
+                                       if S > 1 else "none: every launch waits for the previous one"),
+                           best_rep_value=world * units_per_step * K / (ms_best * 1e-3), repetitions=n_reps,
+                           single_stream_us_per_step=serial_us, single_stream_value=world * units_per_step * K / (ms1_med * 1e-3)),
+            "e2e": {"value": e2e_value, "unit": "UAV env-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": e2e_steps, "host_gbs_per_gpu": e2e_bytes_s / 1e9, "pcie_ceiling": pcie,
+                    "frac_of_pcie_ceiling": (e2e_bytes_s / 1e9) / pcie["duplex_gbs"] if pcie and pcie.get("duplex_gbs") else None,
+                    "host_topology": topos,
+                    "path": "uavca_step_host on the caller's stream, pinned host buffers: outputs >= 256 MB leave by DMA (chunked "
+                            "H2D/step/D2H pipeline over two streams), smaller batches are zero-copy (the kernel reads/writes mapped host "
+                            "memory through PCIe)" + (f" [forced: {os.environ['UAVCA_HOST_PATH']}]" if os.environ.get("UAVCA_HOST_PATH") else "")},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_unit": alg,
                          "units_per_launch": units_per_step, "launch_us": launch_s * 1e6,
-                         "launch_us_is": "timed region / launches" + (f" ({S} independent launches in flight)" if S > 1 else ""),
-                         "frac_single_stream": (units_per_step * alg / (serial_us * 1e-6) / 1e9 / peak) if serial_us else None},
+                         "launch_us_is": "median repetition / launches" + (f" ({S} independent launches in flight)" if S > 1 else ""),
+                         "frac_best_rep": units_per_step * alg / (ms_best * 1e-3 / K) / 1e9 / peak,
+                         "frac_single_stream": units_per_step * alg / (serial_us * 1e-6) / 1e9 / peak},
+            "rollout": rollout,
             "cpu_baseline": cpu,
+            "cpu_baseline_literal": lit,
             "clocks": clocks.summary(),
             "episode_stats": stats,
         }
         emit(line)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def gather_objects(dist, obj, world):
+    if dist is None:
+        return [obj]
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def measure_pcie(torch, dev, env, h_obs, h_act, d_act, barrier, sharding):
+    """Pinned D2H of one step's observation block and pinned H2D of its actions, alone and together (GB/s, this rank,
+    max time over ranks: all ranks copy at once, as in the e2e leg)."""
+    try:
+        d_obs = env.obs
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        reps = max(3, int(2e9 // max(1, h_obs.numel() * 4)))
+        reps = min(reps, 200)
+
+        def run(d2h, h2d):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                if d2h:
+                    with torch.cuda.stream(s1):
+                        h_obs.copy_(d_obs, non_blocking=True)
+                if h2d:
+                    with torch.cuda.stream(s2):
+                        d_act.copy_(h_act, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            return sharding.max_over_ranks(time.perf_counter() - t0, device=dev) / reps
+
+        run(True, True)
+        t_d2h, t_h2d, t_both = run(True, False), run(False, True), run(True, True)
+        b_d2h, b_h2d = h_obs.numel() * 4, h_act.numel() * 4
+        return {"d2h_gbs": b_d2h / t_d2h / 1e9, "h2d_gbs": b_h2d / t_h2d / 1e9, "duplex_gbs": (b_d2h + b_h2d) / t_both / 1e9,
+                "how": f"cudaMemcpyAsync of one step's observations ({b_d2h / 1e6:.0f} MB, D2H) and actions ({b_h2d / 1e6:.0f} MB, H2D) "
+                       f"between pinned host memory and HBM, {reps} repetitions, every rank at once"}
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": repr(exc)[:160]}
+
+
+def measure_rollout(torch, G, envs, ring, kind, N, B, amax, dev, stream, barrier, reduce_reps, world, Kr):
+    """`uavca_rollout`: Kr steps per launch on ONE stream, the ring of batches cycled as in the main measurement (each
+    launch finds its state in HBM, not in L2); outputs go to one shared [Kr, ...] block per ring slot parity."""
+    M = B * N
+    if kind != "single" and (M * 10 * 4) % 16:
+        return {"unavailable": "B*N*40 bytes is not a multiple of 16", "_launches": 0}
+    # bound the output blocks to ~6 GB
+    out_bytes = M * ((4 if kind == "single" else 10) * 4 + 4 + 1)
+    Kr = int(max(2, min(Kr, 6e9 // (2 * out_bytes))))
+    res = {"steps_per_launch": Kr, "_launches": 0, "streams": 1}
+    outs = [envs[0].rollout(Kr, None, action_seed=1, step0=0, sync_last=False) for _ in range(2)]
+    n_blocks = int(max(1, min(4, 3e9 // (Kr * M * 8))))
+    gen = torch.Generator(device=dev).manual_seed(99)
+    blocks = [(torch.rand((Kr, B, N, 2), generator=gen, device=dev) * 2 - 1) * amax for _ in range(n_blocks)]
+    peak, _ = measured_peaks()
+    alg = algorithmic_bytes_per_unit(kind, N)
+    for name in ("philox", "block"):
+        launches_per_rep = max(ring, 4)
+        state = {"t": 0}
+
+        def rep(name=name):
+            for j in range(launches_per_rep):
+                e = envs[j % ring]
+                acts = None if name == "philox" else blocks[j % n_blocks]
+                e.rollout(Kr, acts, action_seed=1, step0=state["t"], out=outs[j % 2], sync_last=False)
+            state["t"] += Kr
+
+        with torch.cuda.stream(stream):
+            rep()
+        torch.cuda.synchronize(dev)
+        est_ms = launches_per_rep * Kr * M * 45 / 3.0e12 * 1e3
+        ts = timed_reps(torch, stream, rep, est_ms, dev, barrier)
+        med, best, n = reduce_reps(ts)
+        us_per_step = med * 1e3 / (launches_per_rep * Kr)
+        moved = rollout_bytes_per_unit(kind, N, name == "block")
+        res[name] = {"us_per_step": us_per_step, "value": world * M / us_per_step * 1e6, "best_us_per_step": best * 1e3 / (launches_per_rep * Kr),
+                     "frac": M * alg / (us_per_step * 1e-6) / 1e9 / peak,
+                     "frac_is": f"SURVEY 8d algorithmic bytes of a step ({alg:g} B/UAV-step) / time / peak, as for `roofline.frac`",
+                     "bytes_moved_per_unit": moved, "frac_of_bytes_moved": M * moved / (us_per_step * 1e-6) / 1e9 / peak,
+                     "repetitions": n}
+        res["_launches"] += launches_per_rep * (n + 1)
+    res["note"] = ("the env state stays in registers for the K steps of a launch, so only obs/reward/done (+ an action block) cross "
+                   "HBM: `frac` uses the per-step algorithmic bytes for comparability with `roofline.frac`, `frac_of_bytes_moved` "
+                   "what this mode really has to move; the kernel is instruction-issue bound here")
+    del outs, blocks
+    return res
+
+
+def run_c1(args, wl, G, torch, dev):
+    """BASELINE configs[0]: the run.py loop through the B=1 drop-in class (`compat.UAVWorld2D`): one env, one step per
+    call, python floats back on the host every step — latency, not throughput."""
+    import numpy as np
+
+    from gym_uav_collision_avoidance_b200 import compat
+
+    K = args.steps
+    best = None
+    launches = 0
+    for _ in range(3):
+        np.random.seed(0)
+        env = compat.UAVWorld2D()
+        env.reset()
+        acts = [env.action_space.sample() for _ in range(K)]
+        l0 = env._b.launch_count
+        t0 = time.perf_counter()
+        for a in acts:
+            _, _, done, _ = env.step(a)
+            if done:
+                env.reset()
+        dt = time.perf_counter() - t0
+        launches = env._b.launch_count - l0
+        best = dt if best is None else min(best, dt)
+    lit = literal_baseline("single", 1) if not args.no_cpu_baseline else None
+    emit({"metric": "UAV env-steps/sec", "value": K / best, "unit": "UAV env-steps/s", "n_gpus": 1, "steps": K, "warmup": args.warmup,
+          "ms_per_step": best / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f64 velocity / f32 position+obs (as the reference)", "data": "synthetic",
+          "config": dict(workload_config(args, wl, 1, 1), note="one env, one launch + one host read-back per step: launch/sync latency bound; "
+                         "the batched classes are the product, this row only shows the drop-in runs the reference's own loop"),
+          "e2e": {"value": K / best, "unit": "UAV env-steps/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 4 * 4 + 4 + 1},
+          "gpu_launches": int(launches), "roofline": None, "cpu_baseline": lit, "cpu_baseline_literal": lit})
+
+
+def run_acting(args, wl, G, torch, dev, rank, world, dist, barrier):
+    """BASELINE configs[4]: one acting step = policy forward over all B*N observations + env step (polar action map
+    fused) + append of the B*N transitions to the device replay ring.  Rows: eager fp32 (the reference's arithmetic),
+    TF32, and the fused tcgen05 acting kernel; value = the fp32 row unless --acting-precision says otherwise."""
+    from gym_uav_collision_avoidance_b200 import sharding
+
+    B, N = wl["B"], wl["N"]
+    K = args.steps
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rows = {}
+    stream = torch.cuda.Stream(device=dev)
+    total_launches = 0
+    for precision in ("fp32", "tf32", "fused"):
+        env = G.BatchedMultiUAVWorld2D(B, num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=1500, seed=0x5EED,
+                                       env_index_base=rank * B, device=dev)
+        policy = G.GaussianPolicy(10, 2).to(dev)
+        replay = G.DeviceReplay(min(B * N * 16, 4_000_000), 10, 2, device=dev)
+        ro = G.BatchedRollout(env, policy, replay, action_mode="polar", precision=precision)
+        ro.reset()
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                ro.step()
+        torch.cuda.synchronize(dev)
+        n_graph = min(K, 50)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for _ in range(n_graph):
+                ro.step()
+        g.replay()
+        torch.cuda.synchronize(dev)
+        q = max(1, K // n_graph)
+
+        def rep(g=g, q=q):
+            for _ in range(q):
+                g.replay()
+
+        ts = timed_reps(torch, stream, rep, 0.07 * q * n_graph if precision == "fused" else 1.0 * q * n_graph, dev, barrier)
+        ts = [sharding.max_over_ranks(t, device=dev) for t in ts] if dist is not None else ts
+        med = statistics.median(ts)
+        us = med * 1e3 / (q * n_graph)
+        rows[precision] = {"us_per_acting_step": us, "value": world * B * N / us * 1e6, "best_us": min(ts) * 1e3 / (q * n_graph),
+                           "repetitions": len(ts), "replay_size": len(replay)}
+        total_launches += env.launch_count
+        del g, ro, replay, env
+    head = args.acting_precision
+    if rank == 0:
+        us = rows[head]["us_per_acting_step"]
+        emit({"metric": "UAV env-steps/sec", "value": rows[head]["value"], "unit": "UAV env-steps/s", "n_gpus": world, "steps": K,
+              "warmup": max(args.warmup, 3), "ms_per_step": us / 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+              "dtype": f"env: f64 velocity / f32; policy: {head}", "data": "synthetic (random-init policy: the reference ships no weights)",
+              "config": dict(workload_config(args, wl, world, B), actions="policy samples mapped by the fused polar action map",
+                             headline_precision=head, rows=rows,
+                             timing="CUDA events around repetitions of CUDA-graph replays of the whole acting step (policy + step + replay append)"),
+              "e2e": None, "gpu_launches": int(total_launches), "roofline": None, "cpu_baseline": None})
     if dist is not None:
         dist.destroy_process_group()
 
@@ -416,13 +774,20 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=20)
-    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: c3 (BASELINE configs[2]) on one GPU, c4s (configs[3]: N=32, 1,048,576 envs sharded) with --gpus > 1")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--rollout-k", type=int, default=32, help="steps per launch of the rollout measurement")
+    ap.add_argument("--acting-precision", default="fp32", choices=["fp32", "tf32", "fused"])
     ap.add_argument("--streams", type=int, default=None,
                     help="streams the independent batches of the ring are pipelined over (default: 2; 4 for the small c2/c5 batches)")
     args = ap.parse_args()
     protect_stdout()
+    if args.workload is None:
+        args.workload = "c3" if args.gpus <= 1 else "c4s"
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -42,6 +42,8 @@ class Config(C.Structure):
         ("reach_distance", C.c_double),
         ("reach_speed", C.c_double),
         ("polar_scale", C.c_double),
+        ("track_scores", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -49,7 +51,7 @@ class Layout(C.Structure):
     """`uavca_layout`: byte offsets of the SoA fields inside a state blob."""
 
     _fields_ = [(n, C.c_size_t) for n in
-                ("total_bytes", "stats", "pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode")]
+                ("total_bytes", "stats", "pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score")]
 
 
 # every symbol include/uavca.h declares: name -> (restype, argtypes)

@@ -58,10 +58,12 @@ class StateBlob:
             off = getattr(layout, name)
             setattr(self, name, self.blob[off:off + num_envs * 4].view(dt))
         self.stats = self.blob[layout.stats:layout.stats + 64].view(torch.int64)
+        self.stats_f64 = self.blob[layout.stats:layout.stats + 64].view(torch.float64)  # slots 4, 5: score sums
+        self.score = self.blob[layout.score:layout.score + num_envs * 16].view(torch.float64).view(num_envs, 2)
         self.init.fill_(1.0)
         self.prev.fill_(1.0)
 
-    FIELDS = ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode")
+    FIELDS = ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score")
 
     def load_arrays(self, **arrays) -> None:
         """Overwrite fields from host arrays / tensors of the matching shape (parity runs, checkpoints)."""
@@ -181,8 +183,12 @@ class _BatchedBase:
         """Totals over finished episodes plus the counters of the episodes in flight."""
         ops.stats(self._h, self.state.blob, self._stats)
         v = self._stats.cpu().tolist()
+        sf = self.state.stats_f64[4:6].cpu().tolist()
         return dict(episodes=v[0], reach=v[1], collisions=v[2], steps=v[3], live_reach=v[4], live_collisions=v[5],
-                    live_steps=v[6], num_envs=v[7])
+                    live_steps=v[6], num_envs=v[7],
+                    # over finished episodes, with track_scores=True: sum of rewards[0] (test_sac_multi.py:105) and of
+                    # rewards[i] * (1 - dones[i]) over all UAVs (:152-156); UAV-steps whose reward / position was not finite
+                    score0_sum=sf[0], score_live_sum=sf[1], nonfinite=int(self.state.stats[6].item()))
 
     # the counters the reference keeps on the env object (multi_uav_world_2d.py:166-168), one value per env
     @property
@@ -196,6 +202,57 @@ class _BatchedBase:
     @property
     def collision_count(self) -> torch.Tensor:
         return self.state.coll
+
+    @property
+    def score(self) -> torch.Tensor:
+        """[B, 2] float64, the episode in flight (needs track_scores=True): column 0 the running `score += rewards[0]`
+        of the training loops (test_sac_multi.py:105, test_sac_multi_score.py:54), column 1 the running
+        `total_score += rewards[i] * (1 - dones[i])` of the evaluation loop (test_sac_multi.py:152-156)."""
+        return self.state.score
+
+    def export_trajectory(self, env_slice, steps: int, actions=None, policy=None, action_mode="cartesian",
+                          evaluate: bool = False) -> dict:
+        """Host-side trajectory of a slice of the envs — what the reference draws with pygame (`render()`,
+        multi_uav_world_2d.py:243-331) or collects by hand for plotting (test_sac_multi_plot_trajectory.py:46-68:
+        every UAV's `location` per step, the targets, and the step at which it was done).
+
+        Steps ALL envs `steps` times (actions: a [steps, B, N, 2] tensor, a callable `policy(obs) -> action`, or None
+        for the Philox random stream) and returns NumPy arrays for `env_slice` (an int, slice or index tensor):
+        pos [steps+1, E, N, 2] (row 0 = before the first step), target [steps+1, E, N, 2], velocity [steps+1, E, N, 2],
+        done / reward [steps, E, N], reset [steps, E] (an auto-reset happened: the trajectory jumps), parked / collided
+        [steps+1, E, N] and `done_step` [E, N] (first step each UAV reported done, -1 if never)."""
+        import numpy as np
+
+        idx = torch.arange(self.num_envs, device=self.device)[env_slice].reshape(-1)
+        st = self.state
+        rec = dict(pos=[st.pos[idx].cpu()], target=[st.tgt[idx].cpu()], velocity=[st.vel[idx].cpu()], flags=[st.flags[idx].cpu()],
+                   done=[], reward=[], reset=[])
+        for k in range(int(steps)):
+            if actions is not None:
+                a = actions[k]
+            elif policy is not None:
+                a = policy(self.obs)
+            else:
+                a = self.sample_actions(k)
+                if action_mode == "cartesian":
+                    a = a * float(self.max_speed[0])
+            if self.kind == KIND_SINGLE:
+                _, r, d, info = self.step(a, action_mode=action_mode)
+            else:
+                _, r, d, info = self.step(a, evaluate=evaluate, action_mode=action_mode)
+            rec["pos"].append(st.pos[idx].cpu()); rec["target"].append(st.tgt[idx].cpu())
+            rec["velocity"].append(st.vel[idx].cpu()); rec["flags"].append(st.flags[idx].cpu())
+            rec["done"].append(d[idx].cpu()); rec["reward"].append(r[idx].cpu()); rec["reset"].append(info["reset_mask"][idx].cpu())
+        out = {k: torch.stack(v).numpy() for k, v in rec.items()}
+        flags = out.pop("flags")
+        out["parked"], out["collided"] = (flags & 1).astype(bool), (flags & 2).astype(bool)
+        done = out["done"].astype(bool)
+        out["done"] = done
+        out["reset"] = out["reset"].astype(bool)
+        first = np.where(done.any(axis=0), done.argmax(axis=0), -1)
+        out["done_step"] = first
+        out["env_index"] = idx.cpu().numpy()
+        return out
 
     @property
     def launch_count(self) -> int:
@@ -286,8 +343,10 @@ class BatchedMultiUAVWorld2D(_BatchedBase):
 
     def __init__(self, num_envs: int, x_size=50.0, y_size=50.0, max_speed=10.0, max_acceleration=5.0, num_agents=4,
                  collider_radius=1.0, d_sense=15, *, device=None, seed=0, reset_mode=0, max_episode_steps=0,
-                 reset_source=SOURCE_PHILOX, circular=False, env_index_base=0, hard_collision_radius=0.5):
+                 reset_source=SOURCE_PHILOX, circular=False, env_index_base=0, hard_collision_radius=0.5,
+                 track_scores=False):
         cfg = _capi.default_config(KIND_MULTI)
+        cfg.track_scores = int(bool(track_scores))
         cfg.num_envs, cfg.num_agents = num_envs, num_agents
         cfg.x_size, cfg.y_size, cfg.max_speed, cfg.max_acceleration = x_size, y_size, max_speed, max_acceleration
         cfg.collider_radius, cfg.d_sense, cfg.hard_collision_radius = collider_radius, d_sense, hard_collision_radius
@@ -335,8 +394,9 @@ class BatchedUAVWorld2D(_BatchedBase):
 
     def __init__(self, num_envs: int, x_size=100.0, y_size=100.0, agent_num=4, max_speed=12.0, max_acceleration=5.0, *,
                  device=None, seed=0, reset_mode=0, max_episode_steps=0, reset_source=SOURCE_PHILOX, env_index_base=0,
-                 float32_first_step=False):
+                 float32_first_step=False, track_scores=False):
         cfg = _capi.default_config(KIND_SINGLE)
+        cfg.track_scores = int(bool(track_scores))
         cfg.num_envs, cfg.num_agents = num_envs, 1
         cfg.x_size, cfg.y_size, cfg.max_speed, cfg.max_acceleration = x_size, y_size, max_speed, max_acceleration
         cfg.seed, cfg.reset_mode, cfg.max_episode_steps = seed, reset_mode, max_episode_steps

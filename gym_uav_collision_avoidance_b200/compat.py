@@ -98,6 +98,7 @@ class MultiUAVWorld2D:
             r, g, b = colorsys.hsv_to_rgb(i / num_agents, 1.0, 1.0)
             self.agent_list.append(_AgentView(self, i, (int(255 * r), int(255 * g), int(255 * b))))
         self.window = self.clock = None
+        self.trajectory = []  # frames recorded by render()
 
     # counters live in the device state (multi_uav_world_2d.py:166-168)
     def _counter(name):
@@ -142,7 +143,21 @@ class MultiUAVWorld2D:
         return (self._obs_list(obs), [float(x) for x in r], [bool(x) for x in d], {"distance": 0})
 
     def render(self, mode="human"):
+        """No window: the reference's pygame drawing (multi_uav_world_2d.py:243-331) is replaced by a trajectory tap.
+        Every call appends the current locations / targets / done latches to `self.trajectory` (a list of dicts of
+        NumPy arrays), which is what the reference's plotting script collects by hand
+        (test_sac_multi_plot_trajectory.py:46-68); `export_trajectory()` stacks it."""
+        st = self._b.state
+        self.trajectory.append(dict(pos=st.pos[0].cpu().numpy(), target=st.tgt[0].cpu().numpy(),
+                                    done=(st.flags[0].cpu().numpy() & 1).astype(bool), step=self.steps))
         return None
+
+    def export_trajectory(self) -> dict:
+        """pos [T, N, 2], target [T, N, 2], done [T, N], step [T] of the frames recorded by render()."""
+        if not self.trajectory:
+            return dict(pos=np.zeros((0, self.num_agents, 2), np.float32), target=np.zeros((0, self.num_agents, 2), np.float32),
+                        done=np.zeros((0, self.num_agents), bool), step=np.zeros(0, np.int64))
+        return {k: np.stack([f[k] for f in self.trajectory]) for k in ("pos", "target", "done", "step")}
 
     def close(self):
         self._b.close()

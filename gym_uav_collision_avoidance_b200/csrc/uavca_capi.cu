@@ -43,6 +43,7 @@ void compute_layout(int B, int N, uavca_layout* L) {
   L->reach = take((size_t)B * sizeof(int32_t));
   L->coll = take((size_t)B * sizeof(int32_t));
   L->episode = take((size_t)B * sizeof(uint32_t));
+  L->score = take((size_t)B * 2 * sizeof(double));
   L->total_bytes = off;
 }
 
@@ -61,6 +62,7 @@ StateView view_of(void* blob, const uavca_layout& L) {
   v.reach = reinterpret_cast<int*>(p + L.reach);
   v.coll = reinterpret_cast<int*>(p + L.coll);
   v.episode = reinterpret_cast<unsigned*>(p + L.episode);
+  v.score = reinterpret_cast<double2*>(p + L.score);
   return v;
 }
 
@@ -153,6 +155,7 @@ Consts derive_consts(const uavca_config& g) {
   c.reset_source = g.reset_source;
   c.circular = g.circular;
   c.single_f32_first_step = g.single_f32_first_step;
+  c.track_scores = g.track_scores;
   c.seed_lo = (unsigned)(g.seed & 0xffffffffull);
   c.seed_hi = (unsigned)(g.seed >> 32);
   c.env_base = g.env_index_base;
@@ -280,7 +283,11 @@ int uavca_create(const uavca_config* cfg, int device, uavca_handle** out) {
   h->consts = derive_consts(*cfg);
   h->device = device;
   compute_layout(cfg->num_envs, cfg->num_agents, &h->layout);
-  if (const char* p = std::getenv("UAVCA_STEP_PATH")) h->path = std::strcmp(p, "tma") == 0 ? UAVCA_PATH_AUTO : UAVCA_PATH_LANES;
+  if (const char* p = std::getenv("UAVCA_STEP_PATH")) {  // A/B measurements: tma | prefetch (always) | plain (never prefetch)
+    h->path = std::strcmp(p, "tma") == 0 ? UAVCA_PATH_AUTO
+              : std::strcmp(p, "prefetch") == 0 ? UAVCA_PATH_PREFETCH
+              : std::strcmp(p, "plain") == 0 ? UAVCA_PATH_PLAIN : UAVCA_PATH_LANES;
+  }
   if (cfg->kind == UAVCA_KIND_MULTI && cfg->circular) {
     // multi_uav_world_2d.py:157-163, computed with the host libm and rounded to the float32 state
     DeviceGuard g(device);

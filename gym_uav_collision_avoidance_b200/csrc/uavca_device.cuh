@@ -51,7 +51,7 @@ struct Consts {
   float inv_diag, inv_vm2_f, inv_vmax_f, inv_pi;
   float polar_scale, vmax_f, tau_f;
   // episode control
-  int reset_mode, max_steps, reset_source, circular, single_f32_first_step;
+  int reset_mode, max_steps, reset_source, circular, single_f32_first_step, track_scores;
   unsigned rs_any_mask, rs_all_off;  // reset_mode as masks over an env's done bits (step_core)
   int steps_limit;                   // max_steps, or INT_MAX when there is no limit
   int key_mask;                      // ~31: distance-bits mask of the neighbour keys (pair_scan)
@@ -72,6 +72,7 @@ struct StateView {
   int* reach;
   int* coll;
   unsigned* episode;
+  double2* score;  // per env: (sum of rewards[0], sum_i rewards[i] * (1 - dones[i])) of the episode in flight
   unsigned long long* stats;
 };
 

@@ -9,7 +9,7 @@ namespace uavca {
 
 // path: which kernel(s) may run the step (UAVCA_PATH_AUTO: TMA bulk kernel for whole tiles + per-lane kernel for the
 // ragged rest; UAVCA_PATH_LANES: per-lane kernel only).  *launched receives the number of kernels launched.
-enum : int { UAVCA_PATH_AUTO = 0, UAVCA_PATH_LANES = 1 };
+enum : int { UAVCA_PATH_AUTO = 0, UAVCA_PATH_LANES = 1, UAVCA_PATH_PREFETCH = 2, UAVCA_PATH_PLAIN = 3 };
 cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path);
 cudaError_t launch_rollout_multi(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st);
 cudaError_t launch_rollout_single(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st);
@@ -36,7 +36,7 @@ inline StateView offset_view(const StateView& v, long long env0, int N) {
   StateView o = v;
   const long long m0 = env0 * N;
   o.pos += m0; o.vel += m0; o.tgt += m0; o.init += m0; o.prev += m0; o.flags += m0;
-  o.steps += env0; o.reach += env0; o.coll += env0; o.episode += env0;
+  o.steps += env0; o.reach += env0; o.coll += env0; o.episode += env0; o.score += env0;
   return o;
 }
 

@@ -9,6 +9,9 @@
 // streaming accesses; neighbour interaction stays on chip (per-warp shared-memory ring, uavca_multi.cuh).  No tensor
 // cores: there is no dense contraction anywhere in the step.  (The fused policy kernel, which is GEMM-shaped, lives
 // in uavca_policy.cu.)
+#include <cmath>
+#include <cstdlib>
+
 #include "uavca_host.h"
 #include "uavca_multi.cuh"
 #include "uavca_tma.cuh"
@@ -133,10 +136,13 @@ __device__ __forceinline__ void rollout_multi_body(const KernelArgs& a, const Ro
   cudaTriggerProgrammaticLaunchCompletion();
   const long long env_global = a.c.env_base + L.env;
   uint4 words = make_uint4(0u, 0u, 0u, 0u);
+  float2 next_act = make_float2(0.f, 0.f);  // action block: the load of step k+1 is in flight while step k is computed
+  if (r.action_block != nullptr && L.valid) next_act = ld_stream(r.action_block + L.m);
   for (int k = 0; k < r.K; ++k) {
     io.k = k;
     if (r.action_block != nullptr) {
-      io.act = L.valid ? ld_stream(r.action_block + (size_t)k * r.M + L.m) : make_float2(0.f, 0.f);
+      io.act = next_act;
+      if (k + 1 < r.K && L.valid) next_act = ld_stream(r.action_block + (size_t)(k + 1) * r.M + L.m);
     } else {
       const unsigned long long t = r.step0 + (unsigned long long)k;
       if (k == 0 || (t & 1ull) == 0ull) words = action_words(r.seed_lo, r.seed_hi, env_global, L.i, t);
@@ -149,9 +155,10 @@ __device__ __forceinline__ void rollout_multi_body(const KernelArgs& a, const Ro
   if (L.valid & (L.i == 0)) a.s.steps[L.env] = io.steps;
 }
 
-// No load latency to hide inside the K-step loop: fewer resident CTAs, more registers (the env state lives in them).
+// Resident CTAs per SM of the rollout kernel (measured on B200, profiles/r2_rollout_minb.md: 8 CTAs x 64 registers beats
+// 6 x 80 and 5 x 96 at N = 16 / 32 and with action blocks, and ties at N = 8 with Philox actions).
 #ifndef UAVCA_ROLLOUT_MINB
-#define UAVCA_ROLLOUT_MINB 6
+#define UAVCA_ROLLOUT_MINB 8
 #endif
 template <int NT>
 __global__ void __launch_bounds__(kThreads, UAVCA_ROLLOUT_MINB) rollout_multi_kernel(const __grid_constant__ KernelArgs a,
@@ -176,6 +183,107 @@ __global__ void __launch_bounds__(kThreads) sample_actions_kernel(const __grid_c
   out[m] = action_from_words(action_words(seed_lo, seed_hi, c.env_base + env, i, t), t);
 }
 
+// ---- persistent variant with cp.async input prefetch (large batches) ----------------------------------------------------
+// ncu on step_multi_kernel<32> (profiles/r2_full_c4_step_multi_n32.md): a fifth of the warp-time is spent waiting for
+// the warp's own state to arrive (long scoreboard on the first use of the loads).  Here every warp walks warp-tiles
+// w, w + G, w + 2G, ...; while it computes one tile, the next tile's state and actions are already on their way INTO
+// SHARED MEMORY (cp.async / LDGSTS: no registers held, unlike a register prefetch).  Same step_core, same outputs.
+// MEASURED (profiles/r2_prefetch_variant.md): the long-scoreboard stall disappears (2.05 -> 0.16 warps per issue cycle)
+// but issue utilisation does not rise (76.5 % -> 72.5 %): the idle issue slots come from the dependent integer min/max
+// chains and ALU-pipe contention, not from load latency, and the hardware CTA scheduler already overlaps one CTA's loads
+// with its neighbours' compute.  151.6 vs 132.3 us at N=32, B=131,072 — slower everywhere, hence opt-in only
+// (UAVCA_STEP_PATH=prefetch), parity-tested.
+constexpr int kPfStageBytes = 32 * (16 + 8 + 8 + 8 + 4 + 4);  // vel, pos, tgt, action, init, prev of one warp-tile
+
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc, int bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+  else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct PfStage {
+  double2* vel;
+  float2 *pos, *tgt, *act;
+  float *init, *prev;
+};
+__device__ __forceinline__ PfStage pf_stage(unsigned char* base) {
+  PfStage st;
+  st.vel = reinterpret_cast<double2*>(base);
+  st.pos = reinterpret_cast<float2*>(base + 32 * 16);
+  st.tgt = st.pos + 32;
+  st.act = st.tgt + 32;
+  st.init = reinterpret_cast<float*>(st.act + 32);
+  st.prev = st.init + 32;
+  return st;
+}
+
+struct PfIO : GlobalIO {
+  Uav pre;
+  float2 act;
+  int steps;
+  __device__ __forceinline__ Uav load_uav() const { return pre; }
+  __device__ __forceinline__ float2 load_action() const { return act; }
+  __device__ __forceinline__ int load_steps() const { return steps; }
+  __device__ __forceinline__ void loads_done() const {}
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_pf_kernel(const __grid_constant__ KernelArgs a,
+                                                                                  const int num_tiles) {
+  __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
+  __shared__ __align__(16) unsigned char stage_mem[kWarpsPerBlock * kPfStageBytes];
+  const WarpScratch ws = warp_scratch(smem);
+  const PfStage st = pf_stage(stage_mem + (threadIdx.x >> 5) * kPfStageBytes);
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * kWarpsPerBlock;
+  int wt = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  cudaGridDependencySynchronize();
+  if (wt >= num_tiles) return;
+  // every tile of this kernel is a FULL warp-tile (the launcher hands the ragged rest to the per-lane kernel)
+  unsigned nflags = 0u;
+  int nsteps = 0;
+  auto prefetch = [&](int tile) {
+    const Lane P = make_lane<NT, true>(a.B, a.N, tile);
+    if (P.valid) {
+      cp_async(st.vel + lane, a.s.vel + P.m, 16);
+      cp_async(st.pos + lane, a.s.pos + P.m, 8);
+      cp_async(st.tgt + lane, a.s.tgt + P.m, 8);
+      cp_async(st.act + lane, a.io.action + P.m, 8);
+      cp_async(st.init + lane, a.s.init + P.m, 4);
+      cp_async(st.prev + lane, a.s.prev + P.m, 4);
+      nflags = ld_stream(a.s.flags + P.m);  // one register each: consumed only at the top of the next tile
+      nsteps = a.s.steps[P.env];
+    }
+  };
+  prefetch(wt);
+  cudaTriggerProgrammaticLaunchCompletion();
+  while (true) {
+    const Lane L = make_lane<NT, true>(a.B, a.N, wt);
+    cp_async_wait_all();
+    __syncwarp();
+    PfIO io{{a, L, ws.stage}, Uav{}, make_float2(0.f, 0.f), 0};
+    if (L.valid) {
+      const double2 v = st.vel[lane];
+      const float2 p = st.pos[lane], t = st.tgt[lane];
+      io.pre.px = p.x; io.pre.py = p.y; io.pre.tx = t.x; io.pre.ty = t.y; io.pre.vx = v.x; io.pre.vy = v.y;
+      io.pre.init = st.init[lane]; io.pre.prev = st.prev[lane]; io.pre.flags = nflags;
+      io.act = st.act[lane];
+      io.steps = nsteps;
+    } else {  // idle lanes (32 is not a multiple of N): a harmless UAV in ordinary flight, as in load_uav()
+      io.pre.px = io.pre.py = io.pre.ty = 0.f; io.pre.tx = 8.f; io.pre.init = io.pre.prev = 8.f;
+      io.pre.vx = 1.0; io.pre.vy = 0.0; io.pre.flags = 0u;
+    }
+    __syncwarp();  // the stage has been read out: refill it for the next tile while this one is computed
+    const int next = wt + stride;
+    if (next < num_tiles) prefetch(next);
+    step_core<NT>(a, ws, L, io);
+    if (next >= num_tiles) break;
+    wt = next;
+  }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(kThreads) reset_multi_kernel(const __grid_constant__ KernelArgs a, const uint8_t* mask) {
   __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
@@ -193,6 +301,7 @@ __global__ void __launch_bounds__(kThreads) reset_multi_kernel(const __grid_cons
       atomicAdd(a.s.stats + 1, (unsigned long long)a.s.reach[L.env]);
       atomicAdd(a.s.stats + 2, (unsigned long long)a.s.coll[L.env]);
       atomicAdd(a.s.stats + 3, (unsigned long long)a.s.steps[L.env]);
+      if (a.c.track_scores) fold_scores(a.s, L.env);
     }
     a.s.steps[L.env] = 0; a.s.reach[L.env] = 0; a.s.coll[L.env] = 0;
     a.s.episode[L.env] = episode + 1u;
@@ -285,6 +394,7 @@ __device__ __forceinline__ void fold_single(const KernelArgs& a, long long b, un
     atomicAdd(a.s.stats + 0, 1ull);
     atomicAdd(a.s.stats + 1, (unsigned long long)a.s.reach[b]);
     atomicAdd(a.s.stats + 3, (unsigned long long)steps);
+    if (a.c.track_scores) fold_scores(a.s, (int)b);
   }
   a.s.reach[b] = 0; a.s.coll[b] = 0;
   a.s.episode[b] = episode + 1u;
@@ -323,6 +433,13 @@ __device__ __forceinline__ bool step_single_core(const KernelArgs& a, long long 
   e.steps += 1;                                                                   // :170
   e.prev = dist;                                                                  // :172
   if (reached) a.s.reach[b] += 1;
+  if (c.track_scores) {  // test_sac.py-style score: sum of rewards; and rewards * (1 - done)
+    double2 sc = a.s.score[b];
+    sc.x += (double)r;
+    sc.y += done ? 0.0 : (double)r;
+    a.s.score[b] = sc;
+  }
+  if (!(fabsf(r) <= 3.4e38f) | !(fabsf(e.px) + fabsf(e.py) <= 3.4e38f)) atomicAdd(a.s.stats + 6, 1ull);
 
   float ob[4];
   obs_single(c, e, false, ob);
@@ -504,6 +621,36 @@ static inline int multi_grid(int B, int N) {
     default: { constexpr int NT = 0; CALL; } break;  \
   }
 
+// Wave shaping.  A launch of a few waves of CTAs pays a whole CTA lifetime for its last, partly filled wave (B = 65,536 x
+// N = 8 is 4,096 CTAs = 3.46 waves at 8 CTAs per SM: the fourth wave runs 46 % full).  Fewer resident CTAs per SM can
+// fill the last wave better (7 per SM: 3.95 waves); the count is enforced with dynamic shared-memory padding.  Returns
+// the padding in bytes (0: leave the launch alone).  UAVCA_WAVE_SHAPE=0 in the environment disables it (A/B runs).
+static size_t wave_pad_bytes(int grid, int cmax, size_t static_smem) {
+  static int enabled = -1, sms = 0;
+  if (enabled < 0) {
+    const char* v = std::getenv("UAVCA_WAVE_SHAPE");
+    enabled = (v && v[0] == '0') ? 0 : 1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  if (!enabled || grid <= sms * cmax || grid >= 12 * sms * cmax) return 0;
+  const double kSmemPerSM = 233472.0;  // 228 KB
+  int best_c = cmax;
+  double best = 0.0;
+  for (int c = cmax; c >= cmax - 3 && c >= 2; --c) {
+    const double waves = (double)grid / (sms * c);
+    double eff = waves / std::ceil(waves - 1e-9);
+    eff *= 1.0 - 0.02 * (cmax - c);  // fewer resident warps hide a little less latency
+    if (eff > best + 1e-9) { best = eff; best_c = c; }
+  }
+  if (best_c == cmax) return 0;
+  // smallest per-CTA footprint that no longer fits best_c + 1 CTAs (1 KB is reserved per CTA by the runtime)
+  const double per_cta = kSmemPerSM / (best_c + 1) + 256.0;
+  const double pad = per_cta - (double)static_smem - 1024.0;
+  if (pad <= 0 || per_cta > kSmemPerSM / best_c) return 0;
+  return ((size_t)pad + 127) / 128 * 128;
+}
+
 // The step kernel is launched with programmatic stream serialization (PDL): its blocks may become resident while
 // the previous kernel in the stream drains, and wait in cudaGridDependencySynchronize() before touching memory.
 template <int NT>
@@ -511,7 +658,7 @@ static cudaError_t launch_step_multi_n(const KernelArgs& a, int grid, cudaStream
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = wave_pad_bytes(grid, kMinBlocksPerSM, kWarpsPerBlock * kScratchFloats * sizeof(float));
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -592,12 +739,66 @@ static int tma_tile_envs(int N) {
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// persistent prefetching kernel: grid = resident CTA slots of the device
+template <int NT>
+static cudaError_t launch_step_pf_n(const KernelArgs& a, int num_tiles, cudaStream_t st) {
+  constexpr int kMaxDev = 64;
+  static int slots[kMaxDev] = {0};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDev) return cudaErrorInvalidDevice;
+  auto kernel = step_multi_pf_kernel<NT>;
+  if (slots[dev] == 0) {
+    int per_sm = 0, sms = 0;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    slots[dev] = per_sm * sms;
+  }
+  const int ctas = (num_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  return launch_pdl(kernel, ctas < slots[dev] ? ctas : slots[dev], kThreads, 0, st, a, num_tiles);
+}
+
+
 cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path) {
   if (launched) *launched = 0;
   if (a.B <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
+  if (path == UAVCA_PATH_PREFETCH) {
+    // opt-in (UAVCA_STEP_PATH=prefetch; measured slower than the per-lane kernel at every size): whole
+    // warp-tiles go through the persistent cp.async-prefetch kernel, the ragged rest through the per-lane kernel
+    const int epw = 32 / a.N;
+    const int full_tiles = a.B / epw;
+    if (full_tiles > 0 && aligned16(a.s.vel) && aligned16(a.s.pos) && aligned16(a.s.tgt) && aligned16(a.io.action)) {
+      UAVCA_DISPATCH_N(a.N, (e = launch_step_pf_n<NT>(a, full_tiles, st)));
+      if (e != cudaSuccess) return e;
+      if (launched) *launched += 1;
+      const int done_envs = full_tiles * epw;
+      if (done_envs < a.B) {
+        KernelArgs r = a;
+        const long long m0 = (long long)done_envs * a.N;
+        r.s = offset_view(a.s, done_envs, a.N);
+        r.c.env_base += done_envs;
+        r.B = a.B - done_envs;
+        r.io.action += m0;
+        r.io.obs += m0 * UAVCA_OBS_DIM_MULTI;
+        r.io.reward += m0;
+        r.io.done += m0;
+        if (r.io.final_obs) r.io.final_obs += m0 * UAVCA_OBS_DIM_MULTI;
+        if (r.io.reset_mask) r.io.reset_mask += done_envs;
+        UAVCA_DISPATCH_N(r.N, (e = launch_step_multi_n<NT>(r, multi_grid(r.B, r.N), st)));
+        if (e != cudaSuccess) return e;
+        if (launched) *launched += 1;
+      }
+      return cudaGetLastError();
+    }
+  }
   // whole tiles go through the bulk (TMA) kernel, the ragged rest through the per-lane kernel
-  int tile_envs = path == UAVCA_PATH_LANES ? 0 : tma_tile_envs(a.N);
+  int tile_envs = path == UAVCA_PATH_AUTO ? tma_tile_envs(a.N) : 0;
   if (tile_envs && !(aligned16(a.io.action) && aligned16(a.io.obs) && aligned16(a.io.reward) && aligned16(a.io.done) &&
                      aligned16(a.io.final_obs) && aligned16(a.s.pos) && aligned16(a.s.vel) && aligned16(a.s.tgt) &&
                      aligned16(a.s.init) && aligned16(a.s.prev) && aligned16(a.s.flags) && aligned16(a.s.steps)))
@@ -634,11 +835,12 @@ cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launche
 }
 
 template <typename Kernel>
-static cudaError_t launch_pdl2(Kernel kernel, int grid, cudaStream_t st, const KernelArgs& a, const RolloutArgs& r) {
+static cudaError_t launch_pdl2(Kernel kernel, int grid, cudaStream_t st, const KernelArgs& a, const RolloutArgs& r,
+                               size_t static_smem) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = static_smem ? wave_pad_bytes(grid, UAVCA_ROLLOUT_MINB, static_smem) : 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -652,13 +854,13 @@ cudaError_t launch_rollout_multi(const KernelArgs& a, const RolloutArgs& r, cuda
   if (a.B <= 0 || r.K <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
   const int grid = multi_grid(a.B, a.N);
-  UAVCA_DISPATCH_N(a.N, (e = launch_pdl2(rollout_multi_kernel<NT>, grid, st, a, r)));
+  UAVCA_DISPATCH_N(a.N, (e = launch_pdl2(rollout_multi_kernel<NT>, grid, st, a, r, kWarpsPerBlock * kScratchFloats * sizeof(float))));
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_rollout_single(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st) {
   if (a.B <= 0 || r.K <= 0) return cudaSuccess;
-  const cudaError_t e = launch_pdl2(rollout_single_kernel, flat_grid(a.B), st, a, r);
+  const cudaError_t e = launch_pdl2(rollout_single_kernel, flat_grid(a.B), st, a, r, 0);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -497,6 +497,24 @@ __device__ __forceinline__ void reset_multi(const KernelArgs& a, const Lane& L, 
 //   bool  wants_final();
 // ================================================================================================================
 
+// Sum of v over the N adjacent lanes of this lane's env (valid in the env's first lane).
+__device__ __forceinline__ float env_sum(float v, const Lane& L) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float o = __shfl_down_sync(kFull, v, off);
+    v += (L.i + off < L.N) ? o : 0.0f;
+  }
+  return v;
+}
+
+// An env starts a new episode: its running scores join the totals over finished episodes (stats[4], stats[5]: doubles).
+__device__ __forceinline__ void fold_scores(const StateView& s, int env) {
+  const double2 sc = s.score[env];
+  atomicAdd(reinterpret_cast<double*>(s.stats + 4), sc.x);
+  atomicAdd(reinterpret_cast<double*>(s.stats + 5), sc.y);
+  s.score[env] = make_double2(0.0, 0.0);
+}
+
 // UAVAgent.finish (uav_agent.py:38-42): park at 1 mm/s along the current heading (NaN -> 0 for a zero velocity)
 static __device__ __forceinline__ double2 finish_velocity(double vx, double vy, double vsq) {
   const double nv = sqrt(vsq);
@@ -588,8 +606,22 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
                    (steps_new >= c.steps_limit)) & L.valid;
   const bool leader = L.valid & (L.i == 0);
   if (leader) io.store_reset(rs);
+  // per-episode scores the training loops keep on the host (test_sac_multi.py:105: score += rewards[0];
+  // :152-156: total_score += rewards[i] * (1 - dones[i])), accumulated per env when asked for
+  if (c.track_scores) {
+    const float live = env_sum((done | !L.valid) ? 0.0f : r, L);
+    if (leader) {
+      double2 sc = a.s.score[L.env];
+      sc.x += (double)r;
+      sc.y += (double)live;
+      a.s.score[L.env] = sc;
+    }
+  }
+  // a NaN / infinite reward or position (the reference zeroes some silently, uav_agent.py:40-42, and propagates the
+  // rest): counted in stats[6] so that a run can assert it never happened
+  const bool bad = (!(fabsf(r) <= 3.4e38f) | !(fabsf(u.px) + fabsf(u.py) <= 3.4e38f)) & L.valid;
 
-  if (!__any_sync(kFull, rs | newly_reached | hard)) {  // nothing to count, nobody resets: the common case
+  if (!__any_sync(kFull, rs | newly_reached | hard | bad)) {  // nothing to count, nobody resets: the common case
     io.store_steps(steps_new, leader);
     io.commit_obs();
     if (io.wants_final()) io.commit_final();
@@ -600,6 +632,10 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
   // ---- rare: some env of this warp counts a reach / a hard collision or starts a new episode in place
   const unsigned ev_reach = __ballot_sync(kFull, newly_reached), ev_coll = __ballot_sync(kFull, hard);
   const int reach_inc = __popc((ev_reach >> L.base) & L.envmask), coll_inc = __popc((ev_coll >> L.base) & L.envmask);
+  {
+    const unsigned ev_bad = __ballot_sync(kFull, bad);
+    if (ev_bad != 0u && L.lane == 0) atomicAdd(a.s.stats + 6, (unsigned long long)__popc(ev_bad));
+  }
   if (io.wants_final()) io.commit_final();
   if (!__any_sync(kFull, rs)) {
     io.store_steps(steps_new, leader);
@@ -621,6 +657,7 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
         atomicAdd(a.s.stats + 1, (unsigned long long)(a.s.reach[L.env] + reach_inc));
         atomicAdd(a.s.stats + 2, (unsigned long long)(a.s.coll[L.env] + coll_inc));
         atomicAdd(a.s.stats + 3, (unsigned long long)steps_new);
+        if (c.track_scores) fold_scores(a.s, L.env);
       }
       a.s.reach[L.env] = 0; a.s.coll[L.env] = 0;  // :166-168
       a.s.episode[L.env] = episode + 1u;

@@ -200,3 +200,15 @@ class BatchedRollout:
         s = self.env.stats()
         denom = max(1, s["episodes"]) * self.env.num_agents
         return s["reach"] / denom, s["collisions"] / denom, s["episodes"]
+
+    def evaluation_summary(self) -> dict:
+        """The numbers the reference's evaluation block prints (test_sac_multi.py:164-176) over the finished episodes:
+        SR = reach / (N * episodes), CR = collisions / (N * episodes), Avg_Score = sum_i rewards[i] * (1 - dones[i])
+        / (N * episodes), plus the mean per-episode `score` (sum of rewards[0], :105).  The scores need an env built
+        with track_scores=True."""
+        s = self.env.stats()
+        eps = max(1, s["episodes"])
+        denom = eps * self.env.num_agents
+        return dict(episodes=s["episodes"], SR=s["reach"] / denom, CR=s["collisions"] / denom,
+                    Avg_Score=s["score_live_sum"] / denom, mean_episode_score=s["score0_sum"] / eps,
+                    nonfinite=s["nonfinite"])

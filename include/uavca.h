@@ -82,13 +82,18 @@ typedef struct uavca_config {
   double reach_distance;        /* 0.5  (multi_uav_world_2d.py:218, uav_world_2d.py:159) */
   double reach_speed;           /* 0.2  (multi_uav_world_2d.py:218) */
   double polar_scale;           /* action scale of UAVCA_ACTION_POLAR: ||action_space.high|| (multi) or high[0] (single) */
+  int32_t track_scores;         /* accumulate the per-episode scores the training loops keep on the host
+                                   (test_sac_multi.py:105,152-156): score[b][0] += rewards[0],
+                                   score[b][1] += sum_i rewards[i] * (1 - dones[i]); folded into stats at reset */
+  int32_t reserved0;
 } uavca_config;
 
 /* Byte offsets of the structure-of-arrays fields inside one state blob (all 256-byte aligned).
  * M = num_envs * num_agents.  The blob is allocated by the caller (uavca_state_layout gives its size). */
 typedef struct uavca_layout {
   size_t total_bytes;
-  size_t stats;   /* uint64[8]: episodes, reach, collisions, steps summed over FINISHED episodes, 4 spare */
+  size_t stats;   /* 8 x 8 bytes over FINISHED episodes: uint64 episodes, reach, collisions, steps; double sum of
+                     score[.][0], double sum of score[.][1] (track_scores); uint64 non-finite UAV-steps seen; 1 spare */
   size_t pos;     /* float  [M][2]  UAV location          (float32 in the reference after reset) */
   size_t vel;     /* double [M][2]  UAV velocity          (float64 in the reference) */
   size_t tgt;     /* float  [M][2]  target location */
@@ -99,6 +104,7 @@ typedef struct uavca_layout {
   size_t reach;   /* int32  [B]     env.target_reach_count */
   size_t coll;    /* int32  [B]     env.collision_count */
   size_t episode; /* uint32 [B]     episodes started by this env (Philox counter word) */
+  size_t score;   /* double [B][2]  running scores of the episode in flight (track_scores) */
 } uavca_layout;
 
 typedef struct uavca_handle uavca_handle;
@@ -146,7 +152,8 @@ int uavca_step_single(uavca_handle* h, void* state, const float* action, int act
 int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* out, void* stream);
 
 /* out8 (device int64[8]): episodes finished, reach, collisions, steps over finished episodes; then the
- * same three counters summed over the episodes in flight (reach, collisions, steps) and B. */
+ * same three counters summed over the episodes in flight (reach, collisions, steps) and B.  The score sums and the
+ * non-finite counter are read from the `stats` field of the state blob directly (see uavca_layout). */
 int uavca_stats(uavca_handle* h, const void* state, int64_t* out8, void* stream);
 
 /* End-to-end form with HOST buffers; ordered after the work already queued on `stream`, returns when the

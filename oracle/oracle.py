@@ -46,6 +46,8 @@ class Config(C.Structure):
         ("reach_distance", C.c_double),
         ("reach_speed", C.c_double),
         ("polar_scale", C.c_double),
+        ("track_scores", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -76,7 +78,7 @@ def single_config(num_envs, **kw) -> Config:
 
 class _CState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "stats")]
+                ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score", "stats")]
 
 
 def build(force: bool = False) -> str:
@@ -111,7 +113,7 @@ def max_threads() -> int:
 class State:
     """Host structure-of-arrays state for B envs x N UAVs."""
 
-    FIELDS = ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "stats")
+    FIELDS = ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score", "stats")
 
     def __init__(self, num_envs: int, num_agents: int):
         B, N = num_envs, num_agents
@@ -126,7 +128,8 @@ class State:
         self.reach = np.zeros(B, np.int32)
         self.coll = np.zeros(B, np.int32)
         self.episode = np.zeros(B, np.uint32)
-        self.stats = np.zeros(8, np.uint64)
+        self.stats = np.zeros(8, np.uint64)  # [4], [5] hold float64 score sums (view with .view(np.float64))
+        self.score = np.zeros((B, 2), np.float64)
 
     def copy(self) -> "State":
         s = State(self.B, self.N)

@@ -39,8 +39,26 @@ typedef struct uavo_state {
   int32_t* reach;    /* [B] */
   int32_t* coll;     /* [B] */
   uint32_t* episode; /* [B] */
-  uint64_t* stats;   /* [8] */
+  double* score;     /* [B][2] running scores of the episode in flight (config.track_scores) */
+  uint64_t* stats;   /* [8]: episodes, reach, collisions, steps; double score sums in [4], [5]; non-finite count in [6] */
 } uavo_state;
+
+/* stats[4], stats[5] hold doubles; the auto-reset pass runs on the thread pool, so they are added with a CAS loop */
+static void atomic_add_double(uint64_t* slot, double v) {
+  uint64_t old = __atomic_load_n(slot, __ATOMIC_RELAXED), neu;
+  do {
+    double d;
+    memcpy(&d, &old, 8);
+    d += v;
+    memcpy(&neu, &d, 8);
+  } while (!__atomic_compare_exchange_n(slot, &old, neu, 0, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+}
+static void fold_scores(const uavca_config* c, uavo_state* s, int b) {
+  if (!c->track_scores || !s->score || !s->stats) return;
+  atomic_add_double(&s->stats[4], s->score[2 * b]);
+  atomic_add_double(&s->stats[5], s->score[2 * b + 1]);
+  s->score[2 * b] = 0.0; s->score[2 * b + 1] = 0.0;
+}
 
 /* ---- numpy primitives as they execute in the reference ---------------------------------------------- */
 
@@ -211,6 +229,7 @@ static void reset_env_multi(const uavca_config* c, uavo_state* s, const uavo_sta
     __atomic_fetch_add(&s->stats[1], (uint64_t)s->reach[b], __ATOMIC_RELAXED);
     __atomic_fetch_add(&s->stats[2], (uint64_t)s->coll[b], __ATOMIC_RELAXED);
     __atomic_fetch_add(&s->stats[3], (uint64_t)s->steps[b], __ATOMIC_RELAXED);
+    fold_scores(c, s, b);
   }
 
   if (c->reset_source == UAVCA_SOURCE_POOL && pool && pool_envs > 0) {
@@ -279,6 +298,7 @@ static void reset_env_single(const uavca_config* c, uavo_state* s, const uavo_st
     __atomic_fetch_add(&s->stats[1], (uint64_t)s->reach[b], __ATOMIC_RELAXED);
     __atomic_fetch_add(&s->stats[2], (uint64_t)s->coll[b], __ATOMIC_RELAXED);
     __atomic_fetch_add(&s->stats[3], (uint64_t)s->steps[b], __ATOMIC_RELAXED);
+    fold_scores(c, s, b);
   }
   if (c->reset_source == UAVCA_SOURCE_POOL && pool && pool_envs > 0) {
     const size_t p = (size_t)((env_global + (int64_t)ep) % pool_envs);
@@ -401,6 +421,15 @@ static void step_env_multi(const uavca_config* c, uavo_state* s, int b, const fl
   }
   for (int i = 0; i < N; ++i) obs_multi(c, pos, vel, tgt, N, i, obs + 10 * i); /* :233-235 */
   s->steps[b] += 1;                                            /* :238 */
+  if (c->track_scores && s->score) { /* what the callers accumulate: test_sac_multi.py:105 and :152-156 */
+    double live = 0.0;
+    for (int i = 0; i < N; ++i) live += reward[i] * (1 - done[i]);
+    s->score[2 * b] += reward[0];
+    s->score[2 * b + 1] += live;
+  }
+  if (s->stats)
+    for (int i = 0; i < N; ++i)
+      if (!isfinite(reward[i]) || !isfinite(pos[2 * i]) || !isfinite(pos[2 * i + 1])) __atomic_fetch_add(&s->stats[6], 1, __ATOMIC_RELAXED);
 }
 
 /* ---- step: UAVWorld2D.step, uav_world_2d.py:137-173 ------------------------------------------------- */
@@ -446,6 +475,11 @@ static void step_env_single(const uavca_config* c, uavo_state* s, int b, const f
   s->prev[b] = dist;                                                   /* :172 */
   *reward = (double)r;
   *done = (uint8_t)d;
+  if (c->track_scores && s->score) {
+    s->score[2 * b] += (double)r;
+    s->score[2 * b + 1] += d ? 0.0 : (double)r;
+  }
+  if (s->stats && (!isfinite(r) || !isfinite(pos[0]) || !isfinite(pos[1]))) __atomic_fetch_add(&s->stats[6], 1, __ATOMIC_RELAXED);
 }
 
 /* ---- persistent pthread pool: parallel-for over environments ----------------------------------------

@@ -36,4 +36,27 @@ def test_algorithmic_bytes_follow_the_survey():
     assert bench.algorithmic_bytes_per_unit("multi", 8) == 110.0       # 41 read + 66 written + 24/N counters
     assert bench.algorithmic_bytes_per_unit("multi", 32) == 107.75
     assert bench.algorithmic_bytes_per_unit("single", 1) == 89.0
-    assert set(bench.WORKLOADS) == {"c2", "c3", "c4", "c4s", "c5"} and bench.WORKLOADS["c3"]["B"] == 65536 and bench.WORKLOADS["c3"]["N"] == 8
+    assert set(bench.WORKLOADS) == {"c1", "c2", "c3", "c4", "c4s", "c5", "c5r"}
+    assert bench.WORKLOADS["c3"]["B"] == 65536 and bench.WORKLOADS["c3"]["N"] == 8
+    assert bench.WORKLOADS["c4s"]["B"] == 1048576 and bench.WORKLOADS["c4s"]["N"] == 32 and bench.WORKLOADS["c4s"]["shard_total"]
+
+
+def test_reference_arm_runs_the_full_batch_and_the_literal_reference():
+    """Same config as the GPU arm (BASELINE configs[2]: all 65,536 envs per step) and, where the literal reference is
+    reachable (/root/reference here, oracle/_ref on the GPU box), its single-core number beside the port's."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["config"]["envs_per_step"] == 65536 and d["config"]["envs_per_gpu"] == 65536 and d["config"]["uavs_per_env"] == 8
+    lit = d["cpu_baseline_literal"]
+    assert "unavailable" in lit or (lit["kind"] == "reference" and lit["cores"] == 1 and 1e3 < lit["value"] < d["value"])
+
+
+def test_multi_gpu_default_workload_is_configs3():
+    """`--gpus N>1` with no --workload measures BASELINE configs[3]: N=32, 1,048,576 envs in total, sharded."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "8", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["config"]["uavs_per_env"] == 32 and d["config"]["envs_total"] == 1048576 and d["config"]["envs_per_gpu"] == 131072
+    assert d["scaling"] == "strong"

@@ -96,3 +96,42 @@ def test_misaligned_buffers_are_rejected_before_any_launch(capi):
     lib = capi.load()
     assert lib.uavca_step_multi(None, 16, 16, 0, 0, 16, 16, 16, None, None, None) == -1
     assert "null handle" in capi.last_error()
+
+
+def test_register_gym_ids_against_a_stub_gym(monkeypatch):
+    """`register_gym_ids()` registers the reference's two ids (gym_uav_collision_avoidance/__init__.py:3-10) with whichever
+    of gym / gymnasium is importable; neither is installed here, so a stub `gym` records the calls."""
+    import sys
+    import types
+
+    from gym_uav_collision_avoidance_b200 import compat
+
+    monkeypatch.delitem(sys.modules, "gym", raising=False)
+    monkeypatch.delitem(sys.modules, "gymnasium", raising=False)
+    try:
+        import gym  # noqa: F401
+        pytest.skip("a real gym is installed")
+    except ImportError:
+        pass
+    assert compat.register_gym_ids() is False  # nothing to register with
+    calls = {}
+    gym = types.ModuleType("gym")
+    envs = types.ModuleType("gym.envs")
+    reg = types.ModuleType("gym.envs.registration")
+    reg.register = lambda id, entry_point=None, **kw: calls.__setitem__(id, entry_point)  # noqa: A002
+    envs.registration, gym.envs = reg, envs
+    for name, mod in (("gym", gym), ("gym.envs", envs), ("gym.envs.registration", reg)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    assert compat.register_gym_ids() is True
+    assert calls == {
+        "gym_uav_collision_avoidance/UAVWorld2D-v0": "gym_uav_collision_avoidance_b200.compat:UAVWorld2D",
+        "gym_uav_collision_avoidance/MultiUAVWorld2D-v0": "gym_uav_collision_avoidance_b200.compat:MultiUAVWorld2D",
+    }
+    # the entry points resolve to the drop-in classes with the reference's constructor signatures
+    import importlib
+    import inspect
+
+    for entry in calls.values():
+        mod, cls = entry.split(":")
+        klass = getattr(importlib.import_module(mod), cls)
+        assert "max_speed" in inspect.signature(klass.__init__).parameters

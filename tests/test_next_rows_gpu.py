@@ -343,3 +343,122 @@ def test_config5_rollout_env_parity_under_policy_actions():
             assert_state_equal(env, orc.state, f"(config 5, step {t})")
             assert torch.equal(fused.state.blob, env.state.blob) and torch.equal(fused.obs, env.obs)
     assert env.stats()["episodes"] == int(orc.state.stats[0]) > B
+
+
+# ---- episode scores, non-finite counter, trajectory export --------------------------------
+
+
+@pytest.mark.parametrize("kind,n", [("multi", 5), ("multi", 8), ("multi", 32), ("single", 1)])
+def test_score_accumulators_match_the_oracle(kind, n):
+    """`score += rewards[0]` (test_sac_multi.py:105) and `total_score += rewards[i] * (1 - dones[i])` (:152-156) kept per
+    env on the device and folded into the totals at every auto-reset — against the oracle's float64 accumulation."""
+    import gym_uav_collision_avoidance_b200 as G
+    from oracle import oracle as O
+
+    B, steps = 600, 150
+    if kind == "single":
+        kw = dict(reset_mode=O.RESET_ON_ANY_DONE, max_episode_steps=45, seed=7)
+        env = G.BatchedUAVWorld2D(B, track_scores=True, **kw)
+        cfg = O.single_config(B, track_scores=1, **kw)
+        amax = 12.0
+    else:
+        kw = dict(reset_mode=O.RESET_ON_DONE0, max_episode_steps=45, seed=7, x_size=18.0, y_size=18.0)
+        env = G.BatchedMultiUAVWorld2D(B, num_agents=n, track_scores=True, **kw)
+        cfg = O.multi_config(B, n, track_scores=1, **kw)
+        amax = 10.0
+    orc = O.Oracle(cfg, nthreads=4)
+    env.reset()
+    orc.reset()
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    for t in range(steps):
+        a = torch.rand((B, n, 2), generator=gen, device="cuda") * 2 * amax - amax
+        if kind == "multi" and t % 2:  # head for the targets: reaches (+10) and collisions (-2) enter the scores
+            a = ((env.state.tgt - env.state.pos) * 2).clamp(-amax, amax).contiguous()
+        env.step(a)
+        orc.step(a.cpu().numpy())
+        if t % 10 == 0 or t == steps - 1:
+            sc, so = env.score.cpu().numpy(), orc.state.score
+            assert np.allclose(sc, so, rtol=2e-5, atol=2e-4), f"running scores differ at step {t}: {np.abs(sc - so).max()}"
+    s = env.stats()
+    of = orc.state.stats.view(np.float64)
+    assert s["episodes"] == int(orc.state.stats[0]) > B
+    assert np.isclose(s["score0_sum"], of[4], rtol=1e-5, atol=1e-2) and np.isclose(s["score_live_sum"], of[5], rtol=1e-5, atol=1e-2)
+    assert s["nonfinite"] == int(orc.state.stats[6]) == 0
+    if kind == "multi":
+        ro = G.BatchedRollout(env, None)
+        ev = ro.evaluation_summary()
+        assert np.isclose(ev["Avg_Score"], of[5] / (n * s["episodes"]), rtol=1e-5)
+        assert np.isclose(ev["mean_episode_score"], of[4] / s["episodes"], rtol=1e-5)
+        assert ev["SR"] == s["reach"] / (n * s["episodes"]) and ev["CR"] == s["collisions"] / (n * s["episodes"])
+
+
+def test_scores_are_off_by_default_and_nonfinite_steps_are_counted():
+    import gym_uav_collision_avoidance_b200 as G
+    from oracle import oracle as O
+
+    B, N = 64, 4
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=N, seed=1)
+    orc = O.Oracle(O.multi_config(B, N, seed=1))
+    env.reset()
+    orc.reset()
+    # the reference divides by init_distance (multi_uav_world_2d.py:189-194): a UAV injected ON its target with
+    # init_distance 0 gets a NaN reward (0 * inf), which the reference silently propagates
+    env.state.tgt[:8, 0] = env.state.pos[:8, 0]
+    env.state.init[:8, 0] = 0.0
+    env.state.prev[:8, 0] = 0.0
+    orc.state.tgt[:8, 0] = orc.state.pos[:8, 0]
+    orc.state.init[:8, 0] = 0.0
+    orc.state.prev[:8, 0] = 0.0
+    zero = torch.zeros((B, N, 2), device="cuda")
+    env.step(zero)
+    out = orc.step(zero.cpu().numpy())
+    bad_ref = int((~np.isfinite(out["reward"])).sum())
+    assert bad_ref == 8 and int(orc.state.stats[6]) == 8
+    assert env.stats()["nonfinite"] == 8 and int((~torch.isfinite(env.reward)).sum()) == 8
+    assert float(env.score.abs().sum()) == 0.0  # track_scores is off: nothing accumulated
+
+
+def test_export_trajectory_is_the_plotting_scripts_record():
+    """pos / target / done per step for an env slice (test_sac_multi_plot_trajectory.py:46-68), equal to stepping by hand."""
+    import gym_uav_collision_avoidance_b200 as G
+
+    B, N, T = 128, 6, 40
+    kw = dict(num_agents=N, seed=5, reset_mode=G.RESET_ON_DONE0, max_episode_steps=25)
+    e1, e2 = G.BatchedMultiUAVWorld2D(B, **kw), G.BatchedMultiUAVWorld2D(B, **kw)
+    e1.reset()
+    e2.reset()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    acts = torch.rand((T, B, N, 2), generator=gen, device="cuda") * 20 - 10
+    tr = e1.export_trajectory(slice(10, 14), T, actions=acts)
+    assert tr["pos"].shape == (T + 1, 4, N, 2) and tr["target"].shape == (T + 1, 4, N, 2) and tr["done"].shape == (T, 4, N)
+    assert tr["reset"].shape == (T, 4) and tr["done_step"].shape == (4, N) and list(tr["env_index"]) == [10, 11, 12, 13]
+    assert np.array_equal(tr["pos"][0], e2.state.pos[10:14].cpu().numpy())
+    for t in range(T):
+        _, r, d, info = e2.step(acts[t])
+        assert np.array_equal(tr["pos"][t + 1], e2.state.pos[10:14].cpu().numpy())
+        assert np.array_equal(tr["target"][t + 1], e2.state.tgt[10:14].cpu().numpy())
+        assert np.array_equal(tr["done"][t], d[10:14].cpu().numpy().astype(bool)) and np.array_equal(tr["reward"][t], r[10:14].cpu().numpy())
+        assert np.array_equal(tr["reset"][t], info["reset_mask"][10:14].cpu().numpy().astype(bool))
+    assert tr["reset"].any(), "the slice should have gone through an auto-reset (25-step limit)"
+    ds = tr["done_step"]
+    assert ((ds == -1) | (tr["done"][np.clip(ds, 0, T - 1), np.arange(4)[:, None], np.arange(N)[None, :]])).all()
+    # random-stream and policy-driven variants run too
+    tr2 = e1.export_trajectory(3, 5)
+    assert tr2["pos"].shape == (6, 1, N, 2)
+    tr3 = e1.export_trajectory(slice(0, 2), 5, policy=lambda obs: torch.zeros((B, N, 2), device="cuda"))
+    assert tr3["velocity"].shape == (6, 2, N, 2)
+
+
+def test_compat_render_records_a_trajectory():
+    from gym_uav_collision_avoidance_b200 import compat
+
+    env = compat.MultiUAVWorld2D(num_agents=3, seed=2)
+    env.reset()
+    for _ in range(5):
+        env.step([np.array([1.0, 0.0])] * 3)
+        assert env.render() is None
+    tr = env.export_trajectory()
+    assert tr["pos"].shape == (5, 3, 2) and tr["target"].shape == (5, 3, 2) and tr["done"].shape == (5, 3)
+    assert list(tr["step"]) == [1, 2, 3, 4, 5]
+    assert np.array_equal(tr["pos"][-1], np.stack([a.location for a in env.agent_list]))
+    env.close()
