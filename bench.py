@@ -13,12 +13,14 @@ region, each bracketed by events; the line reports the MEDIAN repetition (`value
 Multi-GPU runs are one process per GPU (torchrun), envs sharded with no per-step collective, time = max over ranks.
 
 The JSON line carries
-  value        device-resident throughput, one launch per step (inputs resident in HBM);
+  value        device-resident throughput of the workload (inputs resident in HBM) through the fastest product path for
+               open-loop actions: `uavca_rollout`, K env steps per launch from an action block, ONE stream (bit-identical
+               to K single steps); `per_step_launch` holds the one-launch-per-step numbers (`--headline per_step` swaps them);
   e2e          the same metric through `uavca_step_host` with pinned HOST buffers: H2D actions + step + D2H
                obs/reward/done inside the timed region, next to the PCIe copy ceiling measured on the same rank;
   roofline     algorithmic bytes per launch / measured launch time against MEASURED_PEAKS.json (+ the same for one
                dependent launch at a time, `frac_single_stream`);
-  rollout      K steps per launch (`uavca_rollout`: Philox actions / an action block), one stream;
+  rollout      both rollout variants (action block / on-device Philox actions: the run_multi.py loop), one stream;
   cpu_baseline the oracle port of the reference step on one host thread, `cpu_baseline_literal` the LITERAL Python
                reference (oracle/_ref, when it travelled) on one core.
 `--impl reference` times the reference's CPU algorithm (oracle port, all host threads) on the same workload.
@@ -464,13 +466,16 @@ def run_ours(args, wl, rank, world, local_rank):
     ms_med, ms_best, n_reps = reduce_reps(tS)
     ms1_med, ms1_best, n_reps1 = reduce_reps(t1)
     gpu_launches = per_region_launches * (n_reps + (n_reps1 if S > 1 else 0))
-    value = world * units_per_step * K / (ms_med * 1e-3)
+    per_step_value = world * units_per_step * K / (ms_med * 1e-3)
 
-    # ---- K steps per launch (uavca_rollout), ONE stream: Philox actions (the run_multi.py loop) and an action block
+    # ---- K steps per launch (uavca_rollout), ONE stream: an action block resident in HBM, and on-device Philox actions
     rollout = None
     if not args.no_rollout:
-        rollout = measure_rollout(torch, G, envs, ring, kind, N, B, amax, dev, stream, barrier, reduce_reps, world, args.rollout_k)
-        gpu_launches += rollout.pop("_launches")
+        rollout = measure_rollout(torch, G, envs, ring, kind, N, B, amax, dev, stream, barrier, reduce_reps, world, args.rollout_k, K,
+                                  local_rank)
+        if rollout is not None:
+            gpu_launches += rollout.pop("_launches")
+    headline_rollout = rollout is not None and args.headline == "rollout"
 
     # ---- end to end through the host-buffer C-ABI call (uavca_step_host): pinned host buffers, H2D + step + D2H
     D = 4 if kind == "single" else 10
@@ -512,9 +517,35 @@ def run_ours(args, wl, rank, world, local_rank):
     if rank == 0:
         peak, peak_src = measured_peaks()
         alg = algorithmic_bytes_per_unit(kind, N)
-        launch_s = ms_med * 1e-3 / K
-        achieved = units_per_step * alg / launch_s / 1e9
         serial_us = ms1_med / K * 1e3
+        step_us = ms_med / K * 1e3
+        per_step = {
+            "what": "one uavca_step_* launch per env step (closed-loop capable: the caller sees every observation before it acts)",
+            "value": per_step_value, "us_per_step": step_us, "streams": S,
+            "pipelining": (f"independent batches of the ring pipelined over {S} streams (a batch's own steps stay ordered)"
+                           if S > 1 else "none: every launch waits for the previous one"),
+            "frac": units_per_step * alg / (step_us * 1e-6) / 1e9 / peak,
+            "frac_best_rep": units_per_step * alg / (ms_best * 1e-3 / K) / 1e9 / peak, "repetitions": n_reps,
+            "single_stream_us_per_step": serial_us, "single_stream_value": world * units_per_step * K / (ms1_med * 1e-3),
+            "frac_single_stream": units_per_step * alg / (serial_us * 1e-6) / 1e9 / peak,
+            "clocks": clocks.summary(),
+        }
+        if headline_rollout:
+            hb = rollout["block"]
+            value, ms_step, head_clocks = hb["value"], hb["us_per_step"] / 1e3, hb["clocks"]
+            units_per_launch = units_per_step * rollout["steps_per_launch"]
+            path = (f"uavca_rollout: {rollout['steps_per_launch']} env steps per launch, actions from a [K,B,N,2] block resident in HBM, "
+                    "per-step obs/reward/done written to [K,...] blocks; ONE stream (every launch waits for the previous one); "
+                    "bit-identical to one uavca_step_* launch per step (tests/test_rollout_gpu.py), whose numbers are in `per_step_launch`")
+            n_head_reps, frac_best = hb["repetitions"], hb["frac_best_rep"]
+            l2 = (f"ring of {ring} independent batches; per launch the state is read once and {rollout['steps_per_launch']} steps of actions / "
+                  f"outputs ({units_per_launch * 53 / 1e6:.0f} MB > L2) stream through HBM")
+        else:
+            value, ms_step, head_clocks = per_step_value, ms_med / K, clocks.summary()
+            units_per_launch, path, n_head_reps, frac_best = units_per_step, per_step["what"] + "; " + per_step["pipelining"], n_reps, per_step["frac_best_rep"]
+            l2 = f"ring of {ring} independent batches ({ring * per_batch / 1e6:.0f} MB > L2) so every launch streams from HBM"
+        launch_s = ms_step * 1e-3 * (units_per_launch / units_per_step)
+        achieved = units_per_launch * alg / launch_s / 1e9
         cpu = lit = None
         if not args.no_cpu_baseline and world == 1:  # reported baselines, timed on rank 0 at N=1 only
             c_envs = min(B, 4096 if N <= 8 else 512)
@@ -528,40 +559,39 @@ def run_ours(args, wl, rank, world, local_rank):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(args.workload)
+                traffic = json.load(f).get(args.workload + ("_rollout" if headline_rollout else ""))
         e2e_bytes_s = e2e_value / world * (D * 4 + 4 + 1 + 8)
         line = {
             "metric": "UAV env-steps/sec", "value": value, "unit": "UAV env-steps/s", "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms_med / K, "higher_is_better": True, "scaling": "strong" if wl.get("shard_total") else "weak",
+            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if wl.get("shard_total") else "weak",
             "vs_baseline": None, "dtype": "f64 velocity / f32 position+obs (as the reference)", "data": "synthetic",
-            "config": dict(workload_config(args, wl, world, B), env_steps_per_s=value / N,
-                           actions_resident="in HBM", auto_reset_source="on-device Philox",
-                           l2=f"ring of {ring} independent batches ({ring * per_batch / 1e6:.0f} MB > L2) so every launch streams from HBM",
-                           timing=f"CUDA events around each of {n_reps} repetitions of the {K}-step region (CUDA-graph replays, "
-                                  f"{GRAPH_STEPS} steps per graph); value = median repetition",
-                           parallelism=f"env-sharded x{world}, no per-step collective", streams=S,
-                           pipelining=(f"independent batches of the ring pipelined over {S} streams (a batch's own steps stay ordered)"
-                                       if S > 1 else "none: every launch waits for the previous one"),
-                           best_rep_value=world * units_per_step * K / (ms_best * 1e-3), repetitions=n_reps,
-                           single_stream_us_per_step=serial_us, single_stream_value=world * units_per_step * K / (ms1_med * 1e-3)),
+            "config": dict(workload_config(args, wl, world, B), env_steps_per_s=value / N, path=path,
+                           actions_resident="in HBM", auto_reset_source="on-device Philox", l2=l2,
+                           timing=f"CUDA events around each of {n_head_reps} repetitions of the {K}-step region; value = median repetition",
+                           parallelism=f"env-sharded x{world}, no per-step collective", repetitions=n_head_reps),
             "e2e": {"value": e2e_value, "unit": "UAV env-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "host_gbs_per_gpu": e2e_bytes_s / 1e9, "pcie_ceiling": pcie,
                     "frac_of_pcie_ceiling": (e2e_bytes_s / 1e9) / pcie["duplex_gbs"] if pcie and pcie.get("duplex_gbs") else None,
                     "host_topology": topos,
-                    "path": "uavca_step_host on the caller's stream, pinned host buffers: outputs >= 256 MB leave by DMA (chunked "
-                            "H2D/step/D2H pipeline over two streams), smaller batches are zero-copy (the kernel reads/writes mapped host "
-                            "memory through PCIe)" + (f" [forced: {os.environ['UAVCA_HOST_PATH']}]" if os.environ.get("UAVCA_HOST_PATH") else "")},
+                    "path": "one uavca_step_host call per env step on the caller's stream, pinned host buffers: outputs >= 256 MB leave by DMA "
+                            "(chunked H2D/step/D2H pipeline over two streams), smaller batches are zero-copy (the kernel reads/writes mapped "
+                            "host memory through PCIe)" + (f" [forced: {os.environ['UAVCA_HOST_PATH']}]" if os.environ.get("UAVCA_HOST_PATH") else "")},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_unit": alg,
-                         "units_per_launch": units_per_step, "launch_us": launch_s * 1e6,
-                         "launch_us_is": "median repetition / launches" + (f" ({S} independent launches in flight)" if S > 1 else ""),
-                         "frac_best_rep": units_per_step * alg / (ms_best * 1e-3 / K) / 1e9 / peak,
-                         "frac_single_stream": units_per_step * alg / (serial_us * 1e-6) / 1e9 / peak},
+                         "units_per_launch": units_per_launch, "launch_us": launch_s * 1e6,
+                         "kernel": ("rollout_multi_kernel" if kind == "multi" else "rollout_single_kernel") if headline_rollout
+                                   else ("step_multi_kernel" if kind == "multi" else "step_single_kernel"),
+                         "frac_best_rep": frac_best,
+                         "frac_of_bytes_moved": rollout["block"]["frac_of_bytes_moved"] if headline_rollout else None,
+                         "bytes_moved_per_unit": rollout["block"]["bytes_moved_per_unit"] if headline_rollout else None,
+                         "note": (rollout["frac_is"] if headline_rollout else None),
+                         "frac_per_step_launch": per_step["frac"], "frac_single_stream": per_step["frac_single_stream"]},
+            "per_step_launch": per_step,
             "rollout": rollout,
             "cpu_baseline": cpu,
             "cpu_baseline_literal": lit,
-            "clocks": clocks.summary(),
+            "clocks": head_clocks,
             "episode_stats": stats,
         }
         emit(line)
@@ -609,50 +639,55 @@ def measure_pcie(torch, dev, env, h_obs, h_act, d_act, barrier, sharding):
         return {"unavailable": repr(exc)[:160]}
 
 
-def measure_rollout(torch, G, envs, ring, kind, N, B, amax, dev, stream, barrier, reduce_reps, world, Kr):
-    """`uavca_rollout`: Kr steps per launch on ONE stream, the ring of batches cycled as in the main measurement (each
-    launch finds its state in HBM, not in L2); outputs go to one shared [Kr, ...] block per ring slot parity."""
+def measure_rollout(torch, G, envs, ring, kind, N, B, amax, dev, stream, barrier, reduce_reps, world, Kr, K, local_rank):
+    """`uavca_rollout` on ONE stream: a repetition is exactly K env steps, done as launches of Kr steps (+ one launch of
+    the remainder), each launch on the next batch of the ring (every launch finds its state in HBM, not in L2); the
+    [Kr, ...] output blocks (>> L2) are shared by the batches.  Two variants: actions from an action block resident in
+    HBM, and on-device Philox actions (the run_multi.py loop)."""
     M = B * N
     if kind != "single" and (M * 10 * 4) % 16:
-        return {"unavailable": "B*N*40 bytes is not a multiple of 16", "_launches": 0}
-    # bound the output blocks to ~6 GB
+        return None
     out_bytes = M * ((4 if kind == "single" else 10) * 4 + 4 + 1)
-    Kr = int(max(2, min(Kr, 6e9 // (2 * out_bytes))))
-    res = {"steps_per_launch": Kr, "_launches": 0, "streams": 1}
+    Kr = int(max(1, min(Kr, K, 12e9 // (2 * out_bytes))))
+    q, rem = divmod(K, Kr)
+    res = {"steps_per_launch": Kr, "launches_per_rep": q + (1 if rem else 0), "_launches": 0, "streams": 1}
     outs = [envs[0].rollout(Kr, None, action_seed=1, step0=0, sync_last=False) for _ in range(2)]
+    outs_rem = [{k: v[:rem] for k, v in o.items()} for o in outs] if rem else None
     n_blocks = int(max(1, min(4, 3e9 // (Kr * M * 8))))
     gen = torch.Generator(device=dev).manual_seed(99)
     blocks = [(torch.rand((Kr, B, N, 2), generator=gen, device=dev) * 2 - 1) * amax for _ in range(n_blocks)]
     peak, _ = measured_peaks()
     alg = algorithmic_bytes_per_unit(kind, N)
     for name in ("philox", "block"):
-        launches_per_rep = max(ring, 4)
-        state = {"t": 0}
+        state = {"t": 0, "j": 0}
 
         def rep(name=name):
-            for j in range(launches_per_rep):
-                e = envs[j % ring]
-                acts = None if name == "philox" else blocks[j % n_blocks]
-                e.rollout(Kr, acts, action_seed=1, step0=state["t"], out=outs[j % 2], sync_last=False)
-            state["t"] += Kr
+            for i in range(q + (1 if rem else 0)):
+                k = Kr if i < q else rem
+                j = state["j"]
+                acts = None if name == "philox" else blocks[j % n_blocks][:k]
+                envs[j % ring].rollout(k, acts, action_seed=1, step0=state["t"], out=(outs if i < q else outs_rem)[j % 2], sync_last=False)
+                state["t"] += k
+                state["j"] = j + 1
 
         with torch.cuda.stream(stream):
             rep()
         torch.cuda.synchronize(dev)
-        est_ms = launches_per_rep * Kr * M * 45 / 3.0e12 * 1e3
-        ts = timed_reps(torch, stream, rep, est_ms, dev, barrier)
+        est_ms = K * M * 45 / 3.0e12 * 1e3
+        with ClockSampler(local_rank) as clocks:
+            ts = timed_reps(torch, stream, rep, est_ms, dev, barrier)
         med, best, n = reduce_reps(ts)
-        us_per_step = med * 1e3 / (launches_per_rep * Kr)
+        us_per_step = med * 1e3 / K
         moved = rollout_bytes_per_unit(kind, N, name == "block")
-        res[name] = {"us_per_step": us_per_step, "value": world * M / us_per_step * 1e6, "best_us_per_step": best * 1e3 / (launches_per_rep * Kr),
-                     "frac": M * alg / (us_per_step * 1e-6) / 1e9 / peak,
-                     "frac_is": f"SURVEY 8d algorithmic bytes of a step ({alg:g} B/UAV-step) / time / peak, as for `roofline.frac`",
+        res[name] = {"us_per_step": us_per_step, "ms_per_rep": med, "value": world * M / us_per_step * 1e6,
+                     "best_us_per_step": best * 1e3 / K, "frac": M * alg / (us_per_step * 1e-6) / 1e9 / peak,
+                     "frac_best_rep": M * alg / (best * 1e3 / K * 1e-6) / 1e9 / peak,
                      "bytes_moved_per_unit": moved, "frac_of_bytes_moved": M * moved / (us_per_step * 1e-6) / 1e9 / peak,
-                     "repetitions": n}
-        res["_launches"] += launches_per_rep * (n + 1)
-    res["note"] = ("the env state stays in registers for the K steps of a launch, so only obs/reward/done (+ an action block) cross "
-                   "HBM: `frac` uses the per-step algorithmic bytes for comparability with `roofline.frac`, `frac_of_bytes_moved` "
-                   "what this mode really has to move; the kernel is instruction-issue bound here")
+                     "repetitions": n, "clocks": clocks.summary()}
+        res["_launches"] += (q + (1 if rem else 0)) * (n + 1)
+    res["frac_is"] = (f"SURVEY 8d algorithmic bytes of a step ({alg:g} B per UAV-step) x UAV-steps of the launch / launch time / peak — the "
+                      "contract's definition; the env state stays in registers for the K steps of a launch, so only obs/reward/done (+ the "
+                      "action block) really cross HBM (`bytes_moved_per_unit`, `frac_of_bytes_moved`): the kernel is instruction-issue bound")
     del outs, blocks
     return res
 
@@ -781,6 +816,9 @@ def main():
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--rollout-k", type=int, default=32, help="steps per launch of the rollout measurement")
+    ap.add_argument("--headline", default="rollout", choices=["rollout", "per_step"],
+                    help="which product path `value` / `roofline` describe: K steps per launch from an action block (default: the "
+                         "bench's actions are open-loop random) or one launch per step; the other one is reported beside it")
     ap.add_argument("--acting-precision", default="fp32", choices=["fp32", "tf32", "fused"])
     ap.add_argument("--streams", type=int, default=None,
                     help="streams the independent batches of the ring are pipelined over (default: 2; 4 for the small c2/c5 batches)")

@@ -13,7 +13,7 @@ RESET_ON_DONE0, RESET_ON_ALL_DONE, RESET_ON_ANY_DONE = 1, 2, 4
 SOURCE_PHILOX, SOURCE_POOL = 0, 1
 FLAG_PARKED, FLAG_COLLIDED = 1, 2
 OBS_DIM = {KIND_MULTI: 10, KIND_SINGLE: 4}
-MAX_AGENTS = 32
+MAX_AGENTS = 1024
 
 
 class Config(C.Structure):
@@ -51,7 +51,7 @@ class Layout(C.Structure):
     """`uavca_layout`: byte offsets of the SoA fields inside a state blob."""
 
     _fields_ = [(n, C.c_size_t) for n in
-                ("total_bytes", "stats", "pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score")]
+                ("total_bytes", "stats", "pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score", "pos64", "tgt64", "init64", "prev64")]
 
 
 # every symbol include/uavca.h declares: name -> (restype, argtypes)

@@ -60,6 +60,14 @@ class StateBlob:
         self.stats = self.blob[layout.stats:layout.stats + 64].view(torch.int64)
         self.stats_f64 = self.blob[layout.stats:layout.stats + 64].view(torch.float64)  # slots 4, 5: score sums
         self.score = self.blob[layout.score:layout.score + num_envs * 16].view(torch.float64).view(num_envs, 2)
+        self.float64_world = layout.tgt64 != layout.pos64  # config.circular: float64 locations, as the reference keeps them
+        if self.float64_world:
+            f64 = lambda off, inner: self.blob[off:off + M * max(inner, 1) * 8].view(torch.float64).view(  # noqa: E731
+                (num_envs, num_agents, inner) if inner else (num_envs, num_agents))
+            self.pos64, self.tgt64 = f64(layout.pos64, 2), f64(layout.tgt64, 2)
+            self.init64, self.prev64 = f64(layout.init64, 0), f64(layout.prev64, 0)
+            self.init64.fill_(1.0)
+            self.prev64.fill_(1.0)
         self.init.fill_(1.0)
         self.prev.fill_(1.0)
 
@@ -76,6 +84,8 @@ class StateBlob:
 
     def to_host(self) -> dict:
         out = {k: getattr(self, k).cpu().numpy() for k in self.FIELDS}
+        if self.float64_world:
+            out.update({k: getattr(self, k).cpu().numpy() for k in ("pos64", "tgt64", "init64", "prev64")})
         out["stats"] = self.stats.cpu().numpy()
         return out
 
@@ -326,9 +336,19 @@ class _BatchedBase:
                 out["distance"] = torch.empty((K, B), dtype=torch.float32, **kw)
         if out["obs"].shape[0] != K:
             raise ValueError("the `out` buffers were made for a different number of steps")
-        ops.rollout(self._h, self.state.blob, K, actions, _ACTION_MODES[action_mode], bool(evaluate), int(action_seed),
-                    int(step0), out["obs"], out["reward"], out["done"], out.get("actions") if actions is None else None,
-                    out.get("final_obs"), out.get("reset_mask"), out.get("distance"))
+        act_out = out.get("actions") if actions is None else None
+        if self._direct():  # plain eager code: the C-ABI entry point itself (the custom op below costs ~20 us more per call)
+            p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+            rc = self._lib.uavca_rollout(self._h, self.state.blob.data_ptr(), K, p(actions), _ACTION_MODES[action_mode],
+                                         int(bool(evaluate)), int(action_seed), int(step0), out["obs"].data_ptr(),
+                                         out["reward"].data_ptr(), out["done"].data_ptr(), p(act_out), p(out.get("final_obs")),
+                                         p(out.get("reset_mask")), p(out.get("distance")), self._stream())
+            if rc:
+                _capi.check(rc, "uavca_rollout")
+        else:
+            ops.rollout(self._h, self.state.blob, K, actions, _ACTION_MODES[action_mode], bool(evaluate), int(action_seed),
+                        int(step0), out["obs"], out["reward"], out["done"], act_out, out.get("final_obs"),
+                        out.get("reset_mask"), out.get("distance"))
         if sync_last:  # keep the env object coherent: env.obs is what a policy acts on next
             self.obs.copy_(out["obs"][-1])
             self.reward.copy_(out["reward"][-1])

@@ -9,7 +9,10 @@ reference's loops run unchanged against the CUDA path (parity, migration); throu
 classes in `batched.py`.  Differences, all forced by the design: episodes are drawn from the counter-based Philox
 stream (`seed=` kwarg) instead of the global `np.random`; observations/rewards are float32 values widened to
 float64; in-place edits of a returned array (`agent.location[0] = x`) do not reach the device — assign the
-attribute instead; `render()` is a no-op.
+attribute instead; `render()` opens no window but records the frame into `env.trajectory` (`export_trajectory()`);
+float64 cartesian actions are rounded to float32 before the step (the reference's `(action - v) / tau` then starts
+from the float64 action: bit-identical whenever the action is float32-representable or the acceleration clip is
+active, within 1e-7 relative otherwise).
 """
 from __future__ import annotations
 
@@ -49,12 +52,24 @@ class _AgentView:
         self.max_acceleration = env.max_acceleratoin.copy()
         self.tau = env.tau
 
+    _F64 = {"pos": "pos64", "tgt": "tgt64", "init": "init64", "prev": "prev64"}
+
+    def _field(self, field):
+        st = self._env._live.state
+        if st.float64_world:  # an episode started by reset(circular=True): the reference holds float64 arrays there
+            field = self._F64.get(field, field)
+        return getattr(st, field)
+
     def _get(self, field):
-        return getattr(self._env._b.state, field)[0, self._i].cpu().numpy()
+        return self._field(field)[0, self._i].cpu().numpy()
 
     def _set(self, field, value):
-        t = getattr(self._env._b.state, field)
+        t = self._field(field)
         t[0, self._i] = torch.as_tensor(np.asarray(value, dtype=np.float64)).to(t.dtype)
+        st = self._env._live.state
+        if st.float64_world and field in self._F64:  # keep the float32 mirror in step
+            m = getattr(st, field)
+            m[0, self._i] = t[0, self._i].to(m.dtype)
 
     location = property(lambda s: s._get("pos"), lambda s, v: s._set("pos", v))
     target_location = property(lambda s: s._get("tgt"), lambda s, v: s._set("tgt", v))
@@ -64,10 +79,10 @@ class _AgentView:
     prev_distance = property(lambda s: np.float32(s._get("prev")), lambda s, v: s._set("prev", v))
 
     def _flag(self, bit):
-        return bool(int(self._env._b.state.flags[0, self._i].item()) & bit)
+        return bool(int(self._env._live.state.flags[0, self._i].item()) & bit)
 
     def _set_flag(self, bit, on):
-        f = self._env._b.state.flags
+        f = self._env._live.state.flags
         cur = int(f[0, self._i].item())
         f[0, self._i] = (cur | bit) if on else (cur & ~bit)
 
@@ -86,7 +101,8 @@ class MultiUAVWorld2D:
                   num_agents=num_agents, collider_radius=collider_radius, d_sense=d_sense, device=device, seed=seed)
         self._b = BatchedMultiUAVWorld2D(1, **kw)
         self._kw = kw
-        self._circ = None  # second handle sharing the state blob, created on the first reset(circular=True)
+        self._circ = None  # float64-world twin (its own state), created on the first reset(circular=True)
+        self._live = self._b  # the env the current episode runs in
         for name in ("x_size", "y_size", "map_diagonal_size", "min_location", "max_location", "max_speed", "min_speed",
                      "max_acceleratoin", "min_acceleratoin", "tau", "collider_radius", "d_sense", "observation_space",
                      "action_space"):
@@ -103,10 +119,10 @@ class MultiUAVWorld2D:
     # counters live in the device state (multi_uav_world_2d.py:166-168)
     def _counter(name):
         def get(self):
-            return int(getattr(self._b.state, name)[0].item())
+            return int(getattr(self._live.state, name)[0].item())
 
         def set_(self, v):
-            getattr(self._b.state, name)[0] = int(v)
+            getattr(self._live.state, name)[0] = int(v)
 
         return property(get, set_)
 
@@ -120,24 +136,25 @@ class MultiUAVWorld2D:
         return [o[i] for i in range(self.num_agents)]
 
     def _get_obs(self, agent):
-        return self._obs_list(self._b.observe())[agent._i]
+        return self._obs_list(self._live.observe())[agent._i]
 
     def reset(self, return_info=False, circular=False):
+        """reset(circular=True) starts an episode in the FLOAT64 world (multi_uav_world_2d.py:157-163 assigns float64
+        arrays to the locations, and they stay float64 until the next plain reset()): it runs on a twin env whose state
+        keeps float64 positions (`circular=True` of the batched class)."""
         if circular:
             if self._circ is None:
                 self._circ = BatchedMultiUAVWorld2D(1, circular=True, **self._kw)
-            self._circ.state.blob.copy_(self._b.state.blob)  # carries the episode counter
-            self._circ.reset()
-            self._b.state.blob.copy_(self._circ.state.blob)
-            obs = self._obs_list(self._b.observe())
+            self._live = self._circ
         else:
-            obs = self._obs_list(self._b.reset())
+            self._live = self._b
+        obs = self._obs_list(self._live.reset())
         info = {"distance": 0}
         return (obs, info) if return_info else obs
 
     def step(self, n_action, evaluate=False):
         a = torch.as_tensor(np.asarray(n_action, dtype=np.float64).reshape(1, self.num_agents, 2), dtype=torch.float32)
-        obs, reward, done, _ = self._b.step(a.to(self._b.device), evaluate=evaluate)
+        obs, reward, done, _ = self._live.step(a.to(self._b.device), evaluate=evaluate)
         r = reward[0].cpu().numpy()
         d = done[0].cpu().numpy()
         return (self._obs_list(obs), [float(x) for x in r], [bool(x) for x in d], {"distance": 0})
@@ -147,7 +164,7 @@ class MultiUAVWorld2D:
         Every call appends the current locations / targets / done latches to `self.trajectory` (a list of dicts of
         NumPy arrays), which is what the reference's plotting script collects by hand
         (test_sac_multi_plot_trajectory.py:46-68); `export_trajectory()` stacks it."""
-        st = self._b.state
+        st = self._live.state
         self.trajectory.append(dict(pos=st.pos[0].cpu().numpy(), target=st.tgt[0].cpu().numpy(),
                                     done=(st.flags[0].cpu().numpy() & 1).astype(bool), step=self.steps))
         return None

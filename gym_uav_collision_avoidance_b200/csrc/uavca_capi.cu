@@ -28,7 +28,7 @@ constexpr size_t kAlign = 256;
 constexpr size_t kDmaThresholdBytes = 256u << 20;  // uavca_step_host: outputs at least this large leave by DMA (measured: 23 MB zero-copy 1.05e9 vs DMA 0.93e9 UAV-steps/s; 1.5 GB 1.12e9 vs 1.16e9)
 size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
-void compute_layout(int B, int N, uavca_layout* L) {
+void compute_layout(int B, int N, int float64_world, uavca_layout* L) {
   const size_t M = (size_t)B * (size_t)N;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes); return o; };
@@ -44,6 +44,11 @@ void compute_layout(int B, int N, uavca_layout* L) {
   L->coll = take((size_t)B * sizeof(int32_t));
   L->episode = take((size_t)B * sizeof(uint32_t));
   L->score = take((size_t)B * 2 * sizeof(double));
+  const size_t M64 = float64_world ? M : 0;  // the float64 fields exist only in that mode
+  L->pos64 = take(M64 * 2 * sizeof(double));
+  L->tgt64 = take(M64 * 2 * sizeof(double));
+  L->init64 = take(M64 * sizeof(double));
+  L->prev64 = take(M64 * sizeof(double));
   L->total_bytes = off;
 }
 
@@ -63,6 +68,12 @@ StateView view_of(void* blob, const uavca_layout& L) {
   v.coll = reinterpret_cast<int*>(p + L.coll);
   v.episode = reinterpret_cast<unsigned*>(p + L.episode);
   v.score = reinterpret_cast<double2*>(p + L.score);
+  if (L.tgt64 != L.pos64) {  // float64 world
+    v.pos64 = reinterpret_cast<double2*>(p + L.pos64);
+    v.tgt64 = reinterpret_cast<double2*>(p + L.tgt64);
+    v.init64 = reinterpret_cast<double*>(p + L.init64);
+    v.prev64 = reinterpret_cast<double*>(p + L.prev64);
+  }
   return v;
 }
 
@@ -122,6 +133,10 @@ Consts derive_consts(const uavca_config& g) {
     c.s_hard_le = std::fmin(c.s_two_h_le, below_sense);
   }
   c.s_reach_lt = lt_sq(c.reach_dist);
+  c.two_r_d = 2.0 * g.collider_radius;
+  c.two_h_d = 2.0 * g.hard_collision_radius;
+  c.dsense_d = g.d_sense;
+  c.reach_dist_d = g.reach_distance;
   c.lox_f = ceil_f(c.lox); c.hix_f = floor_f(c.hix);
   c.loy_f = ceil_f(c.loy); c.hiy_f = floor_f(c.hiy);
   c.vm2_floor_f = floor_f(c.vm2);
@@ -129,6 +144,7 @@ Consts derive_consts(const uavca_config& g) {
   c.inv_dsense = (float)(1.0 / g.d_sense);
   const double diag = n64(g.x_size, g.y_size);
   c.inv_diag = (float)(1.0 / diag);
+  c.inv_diag_d = 1.0 / diag;
   c.inv_vm2_f = (float)(1.0 / c.vm2);
   c.inv_vmax_f = (float)(1.0 / g.max_speed);
   c.inv_pi = (float)(1.0 / 3.141592653589793);
@@ -172,7 +188,6 @@ struct uavca_handle {
   const void* pool_blob = nullptr;
   int pool_envs = 0;
   uavca_layout pool_layout{};
-  float4* ring = nullptr;  // circular-reset table (owned)
   long long launches = 0;
   int path = UAVCA_PATH_LANES;  // UAVCA_STEP_PATH=tma in the environment selects the bulk (TMA) kernel for whole tiles (A/B measurements)
   // end-to-end (host buffer) path, created lazily
@@ -205,7 +220,6 @@ KernelArgs make_args(const uavca_handle* h, void* state) {
   a.s = view_of(state, h->layout);
   a.pool = view_of(const_cast<void*>(h->pool_blob), h->pool_layout);
   a.pool_envs = h->pool_envs;
-  a.ring = h->ring;
   a.B = h->cfg.num_envs;
   a.N = h->cfg.num_agents;
   return a;
@@ -224,7 +238,7 @@ int check_step_alignment(const void* state, const void* action, const void* obs,
 int validate_config(const uavca_config& g) {
   if (g.kind != UAVCA_KIND_MULTI && g.kind != UAVCA_KIND_SINGLE) return fail(-1, "config.kind must be UAVCA_KIND_MULTI or UAVCA_KIND_SINGLE");
   if (g.num_envs <= 0) return fail(-1, "config.num_envs must be positive");
-  if (g.num_agents < 1 || g.num_agents > UAVCA_MAX_AGENTS) return fail(-1, "config.num_agents must be in 1..32");
+  if (g.num_agents < 1 || g.num_agents > UAVCA_MAX_AGENTS) return fail(-1, "config.num_agents must be in 1..UAVCA_MAX_AGENTS (1024)");
   if ((long long)g.num_envs * g.num_agents > 0x7fffffffLL) return fail(-1, "num_envs * num_agents must be below 2^31 per handle (shard across handles)");
   if (g.kind == UAVCA_KIND_SINGLE && g.num_agents != 1) return fail(-1, "the single-UAV world has num_agents == 1");
   if (!(g.tau > 0) || !(g.max_speed > 0) || !(g.max_acceleration > 0)) return fail(-1, "tau, max_speed and max_acceleration must be positive");
@@ -282,26 +296,11 @@ int uavca_create(const uavca_config* cfg, int device, uavca_handle** out) {
   h->cfg = *cfg;
   h->consts = derive_consts(*cfg);
   h->device = device;
-  compute_layout(cfg->num_envs, cfg->num_agents, &h->layout);
+  compute_layout(cfg->num_envs, cfg->num_agents, cfg->kind == UAVCA_KIND_MULTI && cfg->circular, &h->layout);
   if (const char* p = std::getenv("UAVCA_STEP_PATH")) {  // A/B measurements: tma | prefetch (always) | plain (never prefetch)
     h->path = std::strcmp(p, "tma") == 0 ? UAVCA_PATH_AUTO
               : std::strcmp(p, "prefetch") == 0 ? UAVCA_PATH_PREFETCH
               : std::strcmp(p, "plain") == 0 ? UAVCA_PATH_PLAIN : UAVCA_PATH_LANES;
-  }
-  if (cfg->kind == UAVCA_KIND_MULTI && cfg->circular) {
-    // multi_uav_world_2d.py:157-163, computed with the host libm and rounded to the float32 state
-    DeviceGuard g(device);
-    const int N = cfg->num_agents;
-    std::vector<float4> ring(N);
-    const double pi = 3.141592653589793;
-    for (int i = 0; i < N; ++i) {
-      double th = 2 * i * pi / N;
-      ring[i] = make_float4((float)(20.0 * std::cos(th)), (float)(20.0 * std::sin(th)), (float)(23.0 * std::cos(th + pi)),
-                            (float)(23.0 * std::sin(th + pi)));
-    }
-    e = cudaMalloc(&h->ring, sizeof(float4) * N);
-    if (e == cudaSuccess) e = cudaMemcpy(h->ring, ring.data(), sizeof(float4) * N, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { delete h; return fail_cuda("circular reset table", e); }
   }
   *out = h;
   return 0;
@@ -310,7 +309,6 @@ int uavca_create(const uavca_config* cfg, int device, uavca_handle** out) {
 int uavca_destroy(uavca_handle* h) {
   if (!h) return 0;
   DeviceGuard g(h->device);
-  if (h->ring) cudaFree(h->ring);
   for (auto& s : h->hs) if (s) cudaStreamDestroy(s);
   for (auto& ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
   if (h->fork) cudaEventDestroy(h->fork);
@@ -339,7 +337,7 @@ int uavca_state_layout(const uavca_handle* h, uavca_layout* out) {
 int uavca_pool_layout(const uavca_handle* h, int32_t pool_envs, uavca_layout* out) {
   if (int rc = check_handle(h)) return rc;
   if (!out || pool_envs <= 0) return fail(-1, "bad pool_envs / null argument");
-  compute_layout(pool_envs, h->cfg.num_agents, out);
+  compute_layout(pool_envs, h->cfg.num_agents, 0, out);
   return 0;
 }
 
@@ -351,7 +349,7 @@ int uavca_set_reset_pool(uavca_handle* h, const void* pool_state, int32_t pool_e
   }
   h->pool_blob = pool_state;
   h->pool_envs = pool_envs;
-  compute_layout(pool_envs, h->cfg.num_agents, &h->pool_layout);
+  compute_layout(pool_envs, h->cfg.num_agents, 0, &h->pool_layout);
   return 0;
 }
 
@@ -592,6 +590,8 @@ int uavca_rollout(uavca_handle* h, void* state, int32_t K, const float* action_b
   if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
   if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
   const bool single = h->cfg.kind == UAVCA_KIND_SINGLE;
+  if (!single && (h->cfg.circular || h->cfg.num_agents > 32))
+    return fail(-1, "uavca_rollout serves the warp kernels (num_agents <= 32, float32 world); step circular / larger envs one at a time");
   const long long M = (long long)h->cfg.num_envs * h->cfg.num_agents;
   // the [K][...] blocks must keep every step's rows aligned for the 16-byte observation stores
   if (!single && (M * UAVCA_OBS_DIM_MULTI * sizeof(float)) % 16 != 0 && K > 1)

@@ -36,6 +36,7 @@ struct Consts {
   double vm2, inv_vm2;  // ||(vmax, vmax)|| as np.linalg.norm computes it, and its reciprocal
   double lox, hix, loy, hiy;  // box (float64 compare, multi_uav_world_2d.py:213,224)
   double reach_speed_sq;      // least s with sqrt(s) >= reach_speed: ||v|| < reach_speed  <=>  s < this
+  double two_r_d, two_h_d, dsense_d, reach_dist_d, inv_diag_d;  // float64 world (uavca_seq.cuh): thresholds as python floats
   // float32 thresholds (python scalars are weak against float32 norms under NumPy 2)
   float two_r, two_h, dsense, reach_dist;
   // the same thresholds in squared-distance space (sqrt is monotone, so the flags stay bit-exact without a sqrt):
@@ -73,6 +74,8 @@ struct StateView {
   int* coll;
   unsigned* episode;
   double2* score;  // per env: (sum of rewards[0], sum_i rewards[i] * (1 - dones[i])) of the episode in flight
+  double2 *pos64, *tgt64;  // float64 world (config.circular): the reference keeps float64 locations after reset(circular=True)
+  double *init64, *prev64;
   unsigned long long* stats;
 };
 
@@ -93,7 +96,6 @@ struct KernelArgs {
   StateView s;
   StateView pool;  // reset pool (pos == nullptr when absent)
   int pool_envs;
-  const float4* ring;  // circular reset table [N]: (pos.x, pos.y, tgt.x, tgt.y), nullable
   StepIO io;
   int B, N;
 };

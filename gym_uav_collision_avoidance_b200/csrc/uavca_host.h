@@ -37,6 +37,7 @@ inline StateView offset_view(const StateView& v, long long env0, int N) {
   const long long m0 = env0 * N;
   o.pos += m0; o.vel += m0; o.tgt += m0; o.init += m0; o.prev += m0; o.flags += m0;
   o.steps += env0; o.reach += env0; o.coll += env0; o.episode += env0; o.score += env0;
+  if (o.pos64) { o.pos64 += m0; o.tgt64 += m0; o.init64 += m0; o.prev64 += m0; }
   return o;
 }
 

@@ -14,6 +14,7 @@
 
 #include "uavca_host.h"
 #include "uavca_multi.cuh"
+#include "uavca_seq.cuh"
 #include "uavca_tma.cuh"
 
 namespace uavca {
@@ -621,36 +622,6 @@ static inline int multi_grid(int B, int N) {
     default: { constexpr int NT = 0; CALL; } break;  \
   }
 
-// Wave shaping.  A launch of a few waves of CTAs pays a whole CTA lifetime for its last, partly filled wave (B = 65,536 x
-// N = 8 is 4,096 CTAs = 3.46 waves at 8 CTAs per SM: the fourth wave runs 46 % full).  Fewer resident CTAs per SM can
-// fill the last wave better (7 per SM: 3.95 waves); the count is enforced with dynamic shared-memory padding.  Returns
-// the padding in bytes (0: leave the launch alone).  UAVCA_WAVE_SHAPE=0 in the environment disables it (A/B runs).
-static size_t wave_pad_bytes(int grid, int cmax, size_t static_smem) {
-  static int enabled = -1, sms = 0;
-  if (enabled < 0) {
-    const char* v = std::getenv("UAVCA_WAVE_SHAPE");
-    enabled = (v && v[0] == '0') ? 0 : 1;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
-  if (!enabled || grid <= sms * cmax || grid >= 12 * sms * cmax) return 0;
-  const double kSmemPerSM = 233472.0;  // 228 KB
-  int best_c = cmax;
-  double best = 0.0;
-  for (int c = cmax; c >= cmax - 3 && c >= 2; --c) {
-    const double waves = (double)grid / (sms * c);
-    double eff = waves / std::ceil(waves - 1e-9);
-    eff *= 1.0 - 0.02 * (cmax - c);  // fewer resident warps hide a little less latency
-    if (eff > best + 1e-9) { best = eff; best_c = c; }
-  }
-  if (best_c == cmax) return 0;
-  // smallest per-CTA footprint that no longer fits best_c + 1 CTAs (1 KB is reserved per CTA by the runtime)
-  const double per_cta = kSmemPerSM / (best_c + 1) + 256.0;
-  const double pad = per_cta - (double)static_smem - 1024.0;
-  if (pad <= 0 || per_cta > kSmemPerSM / best_c) return 0;
-  return ((size_t)pad + 127) / 128 * 128;
-}
-
 // The step kernel is launched with programmatic stream serialization (PDL): its blocks may become resident while
 // the previous kernel in the stream drains, and wait in cudaGridDependencySynchronize() before touching memory.
 template <int NT>
@@ -658,7 +629,7 @@ static cudaError_t launch_step_multi_n(const KernelArgs& a, int grid, cudaStream
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = wave_pad_bytes(grid, kMinBlocksPerSM, kWarpsPerBlock * kScratchFloats * sizeof(float));
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -764,10 +735,19 @@ static cudaError_t launch_step_pf_n(const KernelArgs& a, int num_tiles, cudaStre
 }
 
 
+// the general one-thread-per-env kernels (uavca_seq.cuh) serve the float64 world and envs wider than a warp
+static inline bool wants_seq(const KernelArgs& a) { return a.c.circular != 0 || a.N > 32; }
+
 cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path) {
   if (launched) *launched = 0;
   if (a.B <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
+  if (wants_seq(a)) {
+    if (a.c.circular) step_multi_seq_kernel<double><<<flat_grid(a.B), kThreads, 0, st>>>(a);
+    else step_multi_seq_kernel<float><<<flat_grid(a.B), kThreads, 0, st>>>(a);
+    if (launched) *launched = 1;
+    return cudaGetLastError();
+  }
   if (path == UAVCA_PATH_PREFETCH) {
     // opt-in (UAVCA_STEP_PATH=prefetch; measured slower than the per-lane kernel at every size): whole
     // warp-tiles go through the persistent cp.async-prefetch kernel, the ragged rest through the per-lane kernel
@@ -835,12 +815,11 @@ cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launche
 }
 
 template <typename Kernel>
-static cudaError_t launch_pdl2(Kernel kernel, int grid, cudaStream_t st, const KernelArgs& a, const RolloutArgs& r,
-                               size_t static_smem) {
+static cudaError_t launch_pdl2(Kernel kernel, int grid, cudaStream_t st, const KernelArgs& a, const RolloutArgs& r) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = static_smem ? wave_pad_bytes(grid, UAVCA_ROLLOUT_MINB, static_smem) : 0;
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -854,13 +833,13 @@ cudaError_t launch_rollout_multi(const KernelArgs& a, const RolloutArgs& r, cuda
   if (a.B <= 0 || r.K <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
   const int grid = multi_grid(a.B, a.N);
-  UAVCA_DISPATCH_N(a.N, (e = launch_pdl2(rollout_multi_kernel<NT>, grid, st, a, r, kWarpsPerBlock * kScratchFloats * sizeof(float))));
+  UAVCA_DISPATCH_N(a.N, (e = launch_pdl2(rollout_multi_kernel<NT>, grid, st, a, r)));
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_rollout_single(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st) {
   if (a.B <= 0 || r.K <= 0) return cudaSuccess;
-  const cudaError_t e = launch_pdl2(rollout_single_kernel, flat_grid(a.B), st, a, r, 0);
+  const cudaError_t e = launch_pdl2(rollout_single_kernel, flat_grid(a.B), st, a, r);
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
@@ -875,6 +854,11 @@ cudaError_t launch_sample_actions(const Consts& c, float* out, int B, int N, uns
 
 cudaError_t launch_reset_multi(const KernelArgs& a, const uint8_t* mask, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  if (wants_seq(a)) {
+    if (a.c.circular) reset_multi_seq_kernel<double><<<flat_grid(a.B), kThreads, 0, st>>>(a, mask);
+    else reset_multi_seq_kernel<float><<<flat_grid(a.B), kThreads, 0, st>>>(a, mask);
+    return cudaGetLastError();
+  }
   const int grid = multi_grid(a.B, a.N);
   UAVCA_DISPATCH_N(a.N, (reset_multi_kernel<NT><<<grid, kThreads, 0, st>>>(a, mask)));
   return cudaGetLastError();
@@ -882,6 +866,11 @@ cudaError_t launch_reset_multi(const KernelArgs& a, const uint8_t* mask, cudaStr
 
 cudaError_t launch_observe_multi(const KernelArgs& a, cudaStream_t st) {
   if (a.B <= 0) return cudaSuccess;
+  if (wants_seq(a)) {
+    if (a.c.circular) observe_multi_seq_kernel<double><<<flat_grid(a.B), kThreads, 0, st>>>(a);
+    else observe_multi_seq_kernel<float><<<flat_grid(a.B), kThreads, 0, st>>>(a);
+    return cudaGetLastError();
+  }
   const int grid = multi_grid(a.B, a.N);
   UAVCA_DISPATCH_N(a.N, (observe_multi_kernel<NT><<<grid, kThreads, 0, st>>>(a)));
   return cudaGetLastError();

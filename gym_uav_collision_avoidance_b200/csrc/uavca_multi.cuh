@@ -467,11 +467,6 @@ __device__ __forceinline__ void reset_multi(const KernelArgs& a, const Lane& L, 
     }
   }
   if (do_reset) {
-    if (c.circular && a.ring != nullptr) {  // :157-163 (host-computed ring, rounded to float32)
-      float4 r = a.ring[L.i];
-      cand = make_float2(r.x, r.y);
-      tg = make_float2(r.z, r.w);
-    }
     u.px = cand.x; u.py = cand.y; u.tx = tg.x; u.ty = tg.y;
     u.vx = 0.0; u.vy = 0.0; u.flags = 0u;                              // :118-123
     u.init = n32(__fsub_rn(u.tx, u.px), __fsub_rn(u.ty, u.py));        // :154

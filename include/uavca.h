@@ -58,16 +58,20 @@ extern "C" {
 
 #define UAVCA_OBS_DIM_MULTI 10
 #define UAVCA_OBS_DIM_SINGLE 4
-#define UAVCA_MAX_AGENTS 32 /* one env never spans more than a warp */
+#define UAVCA_MAX_AGENTS 1024 /* up to 32 UAVs an env lives in one warp (the fast kernels); larger envs and the float64
+                                 world of circular episodes run on the general one-thread-per-env kernel */
 
 typedef struct uavca_config {
   int32_t kind;                 /* UAVCA_KIND_* */
   int32_t num_envs;             /* B, environments held by THIS handle (this GPU's shard) */
-  int32_t num_agents;           /* N, UAVs per env (1..32); must be 1 for UAVCA_KIND_SINGLE */
+  int32_t num_agents;           /* N, UAVs per env (1..UAVCA_MAX_AGENTS); must be 1 for UAVCA_KIND_SINGLE */
   int32_t reset_mode;           /* UAVCA_RESET_* bits */
   int32_t max_episode_steps;    /* also reset when env steps >= this; 0 = no limit */
   int32_t reset_source;         /* UAVCA_SOURCE_* */
-  int32_t circular;             /* multi reset: deterministic ring layout (multi_uav_world_2d.py:157-163) */
+  int32_t circular;             /* multi reset: deterministic ring layout, reset(circular=True) (multi_uav_world_2d.py:157-163).
+                                   The reference holds float64 locations from there on, so this mode is the FLOAT64 WORLD:
+                                   positions, targets, distances in float64 (state fields pos64 / tgt64 / init64 / prev64;
+                                   pos / tgt / init / prev keep float32 mirrors) */
   int32_t single_f32_first_step;/* single world: replicate the float32 first-step quotient the reference
                                    produces when handed float32 actions (uav_world_2d.py:122,142) */
   int64_t env_index_base;       /* global index of env 0 of this shard (Philox streams are shard-invariant) */
@@ -105,6 +109,10 @@ typedef struct uavca_layout {
   size_t coll;    /* int32  [B]     env.collision_count */
   size_t episode; /* uint32 [B]     episodes started by this env (Philox counter word) */
   size_t score;   /* double [B][2]  running scores of the episode in flight (track_scores) */
+  size_t pos64;   /* double [M][2]  float64 world only (config.circular; zero-sized otherwise): location */
+  size_t tgt64;   /* double [M][2]  target_location */
+  size_t init64;  /* double [M]     init_distance */
+  size_t prev64;  /* double [M]     prev_distance */
 } uavca_layout;
 
 typedef struct uavca_handle uavca_handle;

@@ -39,6 +39,12 @@ SINGLE_CASES = [
     dict(name="single_f64_actions", E=12, T=400, seed=201, f32=0),
     dict(name="single_f32_actions", E=12, T=400, seed=202, f32=1),
 ]
+CIRCULAR_CASES = [
+    # reset(circular=True): float64 locations on a ring, targets across it — everybody meets in the middle
+    dict(name="circular_n6", N=6, E=3, T=600, seed=306, evaluate=0, max_steps=0),
+    dict(name="circular_n12_eval", N=12, E=2, T=700, seed=312, evaluate=1, max_steps=0),
+    dict(name="circular_n5_limit", N=5, E=3, T=500, seed=305, evaluate=0, max_steps=170),
+]
 POOL = 16
 
 
@@ -58,12 +64,12 @@ def run_reference_multi(case) -> dict:
     init = O.State(E, N)
     for b in range(E):
         s = O.sample_multi_states(1, N, rng, region=regions[b])
-        for f in O.State.FIELDS[:-1]:
+        for f in ("pos", "vel", "tgt", "init", "prev", "flags"):
             getattr(init, f)[b] = getattr(s, f)[0]
     pool = O.State(POOL, N)
     for p in range(POOL):
         s = O.sample_multi_states(1, N, rng, region=regions[p % E])
-        for f in O.State.FIELDS[:-1]:
+        for f in ("pos", "vel", "tgt", "init", "prev", "flags"):
             getattr(pool, f)[p] = getattr(s, f)[0]
 
     envs = [MultiUAVWorld2D(num_agents=N) for _ in range(E)]
@@ -113,6 +119,53 @@ def run_reference_multi(case) -> dict:
     for f in ("pos", "vel", "tgt", "init", "prev", "flags"):
         res["init_" + f] = getattr(init, f)
         res["pool_" + f] = getattr(pool, f)
+    res.update(out)
+    return res
+
+
+def run_reference_circular(case) -> dict:
+    """Episodes started by reset(circular=True) (multi_uav_world_2d.py:157-163): the locations are float64 arrays from
+    then on.  Env e flies a go-to-goal controller of gain 0.5 + 0.4 e with noise; the episode restarts (circular again)
+    when dones[0] (training protocol), when all(dones) under evaluate, or at the step limit."""
+    _, MultiUAVWorld2D = R.load_reference()
+    N, E, T = case["N"], case["E"], case["T"]
+    rng = np.random.default_rng(case["seed"])
+    envs = [MultiUAVWorld2D(num_agents=N) for _ in range(E)]
+    obs0 = np.stack([np.stack(env.reset(circular=True)) for env in envs])
+    out = dict(
+        action=np.zeros((T, E, N, 2), np.float32), obs=np.zeros((T, E, N, 10)), final_obs=np.zeros((T, E, N, 10)),
+        reward=np.zeros((T, E, N)), done=np.zeros((T, E, N), np.uint8), reset_mask=np.zeros((T, E), np.uint8),
+        pos64=np.zeros((T, E, N, 2)), vel=np.zeros((T, E, N, 2)), flags=np.zeros((T, E, N), np.uint8),
+        prev64=np.zeros((T, E, N)), steps=np.zeros((T, E), np.int32), reach=np.zeros((T, E), np.int32),
+        coll=np.zeros((T, E), np.int32),
+    )
+    for t in range(T):
+        for b, env in enumerate(envs):
+            loc = np.stack([a.location for a in env.agent_list])
+            tgt = np.stack([a.target_location for a in env.agent_list])
+            a = np.clip((tgt - loc) * (0.5 + 0.4 * b) + rng.normal(0, 0.6, size=(N, 2)), -10, 10).astype(np.float32)
+            out["action"][t, b] = a
+            o, r, d, _ = env.step([a[i].astype(np.float64) for i in range(N)], evaluate=bool(case["evaluate"]))
+            o = np.stack(o)
+            out["final_obs"][t, b] = o
+            out["reward"][t, b] = np.array(r, dtype=np.float64)
+            out["done"][t, b] = np.array(d, dtype=np.uint8)
+            rs = all(d) if case["evaluate"] else bool(d[0])
+            if case["max_steps"] > 0:
+                rs |= env.steps >= case["max_steps"]
+            # the counters are read before the restart zeroes them, like the scripts do (test_sac_multi.py:164-166)
+            out["steps"][t, b], out["reach"][t, b], out["coll"][t, b] = env.steps, env.target_reach_count, env.collision_count
+            if rs:
+                o = np.stack(env.reset(circular=True))
+            out["reset_mask"][t, b] = rs
+            out["obs"][t, b] = o
+            assert all(ag.location.dtype == np.float64 for ag in env.agent_list)
+            out["pos64"][t, b] = np.stack([ag.location for ag in env.agent_list])
+            out["vel"][t, b] = np.stack([ag.velocity for ag in env.agent_list])
+            out["prev64"][t, b] = np.array([ag.prev_distance for ag in env.agent_list], dtype=np.float64)
+            out["flags"][t, b] = np.array([(1 if ag.done else 0) | (2 if ag.collided else 0) for ag in env.agent_list], np.uint8)
+    meta = dict(kind="circular", **case, reset_mode=(O.RESET_ON_ALL_DONE if case["evaluate"] else O.RESET_ON_DONE0))
+    res = dict(meta=np.array(json.dumps(meta)), obs0=obs0)
     res.update(out)
     return res
 
@@ -171,7 +224,19 @@ def run_reference_single(case) -> dict:
 
 
 def main():
+    import sys
+
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = sys.argv[1] if len(sys.argv) > 1 else None  # e.g. "circular": regenerate just those cases
+    if only == "circular":
+        for case in CIRCULAR_CASES:
+            res = run_reference_circular(case)
+            path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+            np.savez_compressed(path, **res)
+            print(f"{case['name']}: done-events={int(res['done'].sum())} resets={int(res['reset_mask'].sum())} "
+                  f"reach={int(res['reach'].max())} coll={int(res['coll'].max())} parked-steps={int((res['flags'] & 1).sum())} "
+                  f"-> {os.path.getsize(path) / 1e6:.2f} MB")
+        return
     for case in MULTI_CASES:
         res = run_reference_multi(case)
         path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
@@ -180,6 +245,13 @@ def main():
         np.savez_compressed(path, **res)
         print(f"{case['name']}: done-events={int(res['done'].sum())} resets={int(res['reset_mask'].sum())} "
               f"reach={int(res['reach'].max())} coll={int(res['coll'].max())} -> {os.path.getsize(path) / 1e6:.2f} MB")
+    for case in CIRCULAR_CASES:
+        res = run_reference_circular(case)
+        path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+        np.savez_compressed(path, **res)
+        print(f"{case['name']}: done-events={int(res['done'].sum())} resets={int(res['reset_mask'].sum())} "
+              f"reach={int(res['reach'].max())} coll={int(res['coll'].max())} parked-steps={int((res['flags'] & 1).sum())} "
+              f"-> {os.path.getsize(path) / 1e6:.2f} MB")
     for case in SINGLE_CASES:
         res = run_reference_single(case)
         path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")

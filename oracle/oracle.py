@@ -78,7 +78,7 @@ def single_config(num_envs, **kw) -> Config:
 
 class _CState(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
-                ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score", "stats")]
+                ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score", "pos64", "tgt64", "init64", "prev64", "stats")]
 
 
 def build(force: bool = False) -> str:
@@ -113,7 +113,8 @@ def max_threads() -> int:
 class State:
     """Host structure-of-arrays state for B envs x N UAVs."""
 
-    FIELDS = ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score", "stats")
+    FIELDS = ("pos", "vel", "tgt", "init", "prev", "flags", "steps", "reach", "coll", "episode", "score", "pos64", "tgt64",
+              "init64", "prev64", "stats")
 
     def __init__(self, num_envs: int, num_agents: int):
         B, N = num_envs, num_agents
@@ -130,6 +131,11 @@ class State:
         self.episode = np.zeros(B, np.uint32)
         self.stats = np.zeros(8, np.uint64)  # [4], [5] hold float64 score sums (view with .view(np.float64))
         self.score = np.zeros((B, 2), np.float64)
+        # float64 world (config.circular: the reference keeps float64 locations after reset(circular=True))
+        self.pos64 = np.zeros((B, N, 2), np.float64)
+        self.tgt64 = np.zeros((B, N, 2), np.float64)
+        self.init64 = np.ones((B, N), np.float64)
+        self.prev64 = np.ones((B, N), np.float64)
 
     def copy(self) -> "State":
         s = State(self.B, self.N)

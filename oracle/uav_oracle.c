@@ -40,6 +40,13 @@ typedef struct uavo_state {
   int32_t* coll;     /* [B] */
   uint32_t* episode; /* [B] */
   double* score;     /* [B][2] running scores of the episode in flight (config.track_scores) */
+  /* float64 world (config.circular): after reset(circular=True) the reference holds locations and targets as float64
+   * arrays (multi_uav_world_2d.py:157-163), so every distance, threshold test and reward term of such an episode is
+   * float64.  These fields are the state of that mode; pos/tgt/init/prev above then hold rounded mirrors. */
+  double* pos64;     /* [B][N][2] */
+  double* tgt64;     /* [B][N][2] */
+  double* init64;    /* [B][N] */
+  double* prev64;    /* [B][N] */
   uint64_t* stats;   /* [8]: episodes, reach, collisions, steps; double score sums in [4], [5]; non-finite count in [6] */
 } uavo_state;
 
@@ -265,17 +272,6 @@ static void reset_env_multi(const uavca_config* c, uavo_state* s, const uavo_sta
         if (!rej || a + 1 >= MAX_RESET_ATTEMPTS) { tgt[2 * i] = x; tgt[2 * i + 1] = y; break; }
       }
     }
-    if (c->circular) {
-      /* :157-163 ring layout.  The reference keeps these as float64 arrays; this framework stores
-       * positions as float32, so the ring is rounded once here (documented deviation). */
-      for (int i = 0; i < N; ++i) {
-        double theta = 2 * i * PI_D / N;
-        pos[2 * i] = (float)(20.0 * cos(theta));
-        pos[2 * i + 1] = (float)(20.0 * sin(theta));
-        tgt[2 * i] = (float)(23.0 * cos(theta + PI_D));
-        tgt[2 * i + 1] = (float)(23.0 * sin(theta + PI_D));
-      }
-    }
     for (int i = 0; i < N; ++i) {
       init[i] = n32(tgt[2 * i] - pos[2 * i], tgt[2 * i + 1] - pos[2 * i + 1]); /* :154 */
       prev[i] = init[i];                                                        /* :155 */
@@ -482,6 +478,162 @@ static void step_env_single(const uavca_config* c, uavo_state* s, int b, const f
   if (s->stats && (!isfinite(r) || !isfinite(pos[0]) || !isfinite(pos[1]))) __atomic_fetch_add(&s->stats[6], 1, __ATOMIC_RELAXED);
 }
 
+/* ==== float64 world: episodes started by reset(circular=True) ==========================================
+ * multi_uav_world_2d.py:157-163 assigns `20 * np.ones(2) * np.array([cos, sin])` — float64 arrays — to location and
+ * target_location, so UAVAgent.step's `self.location += dx` (uav_agent.py:28-29), every np.linalg.norm and every
+ * comparison of the episode run in float64.  Same control flow as the float32 functions above, restated with the
+ * float64 dtype sequence.  Exact-distance ties (the ring is symmetric) keep the candidate-list order of
+ * uavs_in_range, i.e. ascending agent index (ndarray.argsort is an insertion sort, hence stable, below 17 elements). */
+
+static void nearest2_f64(const double* pos, int N, int i, int* j1, int* j2, double* d1, double* d2) {
+  *j1 = *j2 = -1; *d1 = *d2 = INFINITY;
+  for (int j = 0; j < N; ++j) {                               /* uav_agent.py:47-55, candidate order = agent index */
+    if (j == i) continue;
+    double d = n64(pos[2 * j] - pos[2 * i], pos[2 * j + 1] - pos[2 * i + 1]);
+    if (d < *d1) { *d2 = *d1; *j2 = *j1; *d1 = d; *j1 = j; }
+    else if (d < *d2) { *d2 = d; *j2 = j; }
+  }
+}
+
+static void obs_multi_f64(const uavca_config* c, const double* pos, const double* vel, const double* tgt, int N, int i,
+                          double* o) {
+  const double vm2 = n64(c->max_speed, c->max_speed), diag = n64(c->x_size, c->y_size);
+  const double vx = vel[2 * i], vy = vel[2 * i + 1];
+  const double th = atan2(vy, vx);
+  o[0] = n64(vx, vy) / vm2;
+  o[1] = th / PI_D;
+  const double tdx = tgt[2 * i] - pos[2 * i], tdy = tgt[2 * i + 1] - pos[2 * i + 1];
+  o[2] = n64(tdx, tdy) / diag;
+  o[3] = wrap(atan2(tdy, tdx) - th) / PI_D;
+  int nb[2]; double dd[2];
+  nearest2_f64(pos, N, i, &nb[0], &nb[1], &dd[0], &dd[1]);
+  int have = 1;
+  for (int k = 0; k < 2; ++k) {
+    double* ok = o + 4 + 3 * k;
+    have = have && nb[k] >= 0 && dd[k] < c->d_sense;           /* uav_agent.py:52 */
+    if (have) {
+      int j = nb[k];
+      ok[0] = dd[k] / c->d_sense;
+      ok[1] = wrap(atan2(pos[2 * j + 1] - pos[2 * i + 1], pos[2 * j] - pos[2 * i]) - th) / PI_D;
+      ok[2] = wrap(atan2(vel[2 * j + 1], vel[2 * j]) - th) / PI_D;
+    } else {
+      ok[0] = 1.0;
+      ok[1] = wrap((PI_D + th) - th) / PI_D;
+      ok[2] = wrap(th - th) / PI_D;
+    }
+  }
+}
+
+static void mirror_f32(uavo_state* s, int b, int N) {
+  for (int i = 0; i < N; ++i) {
+    size_t m = (size_t)b * N + i;
+    s->pos[2 * m] = (float)s->pos64[2 * m]; s->pos[2 * m + 1] = (float)s->pos64[2 * m + 1];
+    s->tgt[2 * m] = (float)s->tgt64[2 * m]; s->tgt[2 * m + 1] = (float)s->tgt64[2 * m + 1];
+    s->init[m] = (float)s->init64[m]; s->prev[m] = (float)s->prev64[m];
+  }
+}
+
+static void reset_env_circular(const uavca_config* c, uavo_state* s, int b) {
+  const int N = c->num_agents;
+  const uint32_t ep = s->episode[b];
+  if (s->stats && ep > 0) {
+    __atomic_fetch_add(&s->stats[0], 1, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[1], (uint64_t)s->reach[b], __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[2], (uint64_t)s->coll[b], __ATOMIC_RELAXED);
+    __atomic_fetch_add(&s->stats[3], (uint64_t)s->steps[b], __ATOMIC_RELAXED);
+    fold_scores(c, s, b);
+  }
+  for (int i = 0; i < N; ++i) {                                /* :118-123, :157-163 */
+    size_t m = (size_t)b * N + i;
+    double theta = 2 * i * PI_D / N;
+    s->vel[2 * m] = 0.0; s->vel[2 * m + 1] = 0.0; s->flags[m] = 0;
+    s->pos64[2 * m] = 20.0 * cos(theta); s->pos64[2 * m + 1] = 20.0 * sin(theta);
+    s->tgt64[2 * m] = 23.0 * cos(theta + PI_D); s->tgt64[2 * m + 1] = 23.0 * sin(theta + PI_D);
+    s->init64[m] = n64(s->tgt64[2 * m] - s->pos64[2 * m], s->tgt64[2 * m + 1] - s->pos64[2 * m + 1]);
+    s->prev64[m] = s->init64[m];
+  }
+  mirror_f32(s, b, N);
+  s->steps[b] = 0; s->reach[b] = 0; s->coll[b] = 0;
+  s->episode[b] = ep + 1;
+}
+
+static void step_env_multi_f64(const uavca_config* c, uavo_state* s, int b, const float* action, int action_mode,
+                               int evaluate, double* obs, double* reward, uint8_t* done) {
+  const int N = c->num_agents;
+  double* pos = s->pos64 + (size_t)b * N * 2;
+  double* vel = s->vel + (size_t)b * N * 2;
+  const double* tgt = s->tgt64 + (size_t)b * N * 2;
+  const double* init = s->init64 + (size_t)b * N;
+  double* prev = s->prev64 + (size_t)b * N;
+  uint8_t* flags = s->flags + (size_t)b * N;
+  const double tau = c->tau, amax = c->max_acceleration, vmax = c->max_speed;
+  const double vm2 = n64(vmax, vmax);
+  const double two_r = 2.0 * c->collider_radius, two_h = 2.0 * c->hard_collision_radius;
+  const double lox = -c->x_size / 2.0, hix = c->x_size / 2.0, loy = -c->y_size / 2.0, hiy = c->y_size / 2.0;
+  for (int i = 0; i < N; ++i) {
+    const int parked = flags[i] & UAVCA_FLAG_PARKED;
+    double prev_d, dist;
+    if (parked) {
+      prev_d = 0.0; dist = 0.0;
+    } else {
+      float ax, ay;
+      map_action(c, action_mode, action[2 * i], action[2 * i + 1], &ax, &ay);
+      double dvx = clipd(((double)ax - vel[2 * i]) / tau, -amax, amax);
+      double dvy = clipd(((double)ay - vel[2 * i + 1]) / tau, -amax, amax);
+      double vx = clipd(vel[2 * i] + dvx * tau, -vmax, vmax);
+      double vy = clipd(vel[2 * i + 1] + dvy * tau, -vmax, vmax);
+      pos[2 * i] = pos[2 * i] + vx * tau;                      /* uav_agent.py:28-29 in float64 */
+      pos[2 * i + 1] = pos[2 * i + 1] + vy * tau;
+      vel[2 * i] = vx; vel[2 * i + 1] = vy;
+      prev_d = prev[i];
+      dist = n64(tgt[2 * i] - pos[2 * i], tgt[2 * i + 1] - pos[2 * i + 1]);
+    }
+    const double px = pos[2 * i], py = pos[2 * i + 1];
+    double dth = wrap(atan2(tgt[2 * i + 1] - py, tgt[2 * i] - px) - atan2(vel[2 * i + 1], vel[2 * i]));
+    double m = vm2 / init[i];
+    if (1.0 < m) m = 1.0;
+    double r = 0.0 - 0.01 * m;
+    r += 50.0 * ((prev_d - dist) / vm2);
+    r *= (r > 0) ? (1.0 - dist / (1.5 * init[i])) : (1.0 + dist / (1.5 * init[i]));
+    r -= 0.01 * fabs(dth);
+    int j1, j2; double d1, d2;
+    nearest2_f64(pos, N, i, &j1, &j2, &d1, &d2);
+    int collision = 0;
+    if (j1 >= 0 && d1 < c->d_sense) {                          /* the nearest in-range neighbour decides (:199-210) */
+      if (d1 <= two_r) { r = -2.0; collision = 1; }
+      if (d1 <= two_h && !parked && !(flags[i] & UAVCA_FLAG_COLLIDED)) { s->coll[b] += 1; flags[i] |= UAVCA_FLAG_COLLIDED; }
+    }
+    const double speed = n64(vel[2 * i], vel[2 * i + 1]);
+    const int oob = !(px >= lox && px <= hix && py >= loy && py <= hiy);
+    int d;
+    if (dist < c->reach_distance && !collision && speed < c->reach_speed) {
+      d = 1;
+      if (!parked) s->reach[b] += 1;
+      flags[i] |= UAVCA_FLAG_PARKED;
+      double fx = vel[2 * i] / speed * 0.001, fy = vel[2 * i + 1] / speed * 0.001;
+      if (fx != fx || fy != fy) { fx = 0.0; fy = 0.0; }
+      vel[2 * i] = fx; vel[2 * i + 1] = fy;
+      r += 10.0;
+    } else if (oob) {
+      d = evaluate ? 0 : 1;
+    } else {
+      d = 0;
+    }
+    prev[i] = dist;
+    reward[i] = r;
+    done[i] = (uint8_t)d;
+  }
+  for (int i = 0; i < N; ++i) obs_multi_f64(c, pos, vel, tgt, N, i, obs + 10 * i);
+  s->steps[b] += 1;
+  if (c->track_scores && s->score) {
+    double live = 0.0;
+    for (int i = 0; i < N; ++i) live += reward[i] * (1 - done[i]);
+    s->score[2 * b] += reward[0];
+    s->score[2 * b + 1] += live;
+  }
+  mirror_f32(s, b, N);
+}
+
 /* ---- persistent pthread pool: parallel-for over environments ----------------------------------------
  * Workers are created once and parked on a condition variable; a job hands out chunks of envs through an
  * atomic counter (dynamic schedule: episodes that reset cost more than ones that do not), the calling
@@ -568,14 +720,26 @@ static int want_reset(const uavca_config* c, const uint8_t* done, int N, int ste
 static void step_multi_body(void* p, int b) {
   step_ctx* x = (step_ctx*)p;
   const int N = x->c->num_agents;
-  step_env_multi(x->c, x->s, b, x->action + (size_t)b * N * 2, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
-                 x->reward + (size_t)b * N, x->done + (size_t)b * N);
+  const int f64 = x->c->circular && x->s->pos64;
+  if (f64)
+    step_env_multi_f64(x->c, x->s, b, x->action + (size_t)b * N * 2, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
+                       x->reward + (size_t)b * N, x->done + (size_t)b * N);
+  else
+    step_env_multi(x->c, x->s, b, x->action + (size_t)b * N * 2, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
+                   x->reward + (size_t)b * N, x->done + (size_t)b * N);
   if (x->final_obs) memcpy(x->final_obs + (size_t)b * N * 10, x->obs + (size_t)b * N * 10, sizeof(double) * N * 10);
   /* auto-reset in place (envs are independent; the shared totals are folded atomically) */
   const int rs = want_reset(x->c, x->done + (size_t)b * N, N, x->s->steps[b]);
   if (x->reset_mask) x->reset_mask[b] = (uint8_t)rs;
   if (rs) {
     uavo_state* s = x->s;
+    if (f64) {
+      reset_env_circular(x->c, s, b);
+      for (int i = 0; i < N; ++i)
+        obs_multi_f64(x->c, s->pos64 + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt64 + (size_t)b * N * 2, N, i,
+                      x->obs + ((size_t)b * N + i) * 10);
+      return;
+    }
     reset_env_multi(x->c, s, x->pool, x->pool_envs, b);
     for (int i = 0; i < N; ++i)
       obs_multi(x->c, s->pos + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt + (size_t)b * N * 2, N, i,
@@ -614,6 +778,12 @@ int uavo_reset(const uavca_config* c, uavo_state* s, const uavo_state* pool, int
     if (c->kind == UAVCA_KIND_SINGLE) {
       reset_env_single(c, s, pool, pool_envs, b);
       if (obs) obs_single(c, s->pos + (size_t)b * 2, s->vel + (size_t)b * 2, s->tgt + (size_t)b * 2, 1, obs + (size_t)b * 4);
+    } else if (c->circular && s->pos64) {
+      reset_env_circular(c, s, b);
+      if (obs)
+        for (int i = 0; i < N; ++i)
+          obs_multi_f64(c, s->pos64 + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt64 + (size_t)b * N * 2, N, i,
+                        obs + ((size_t)b * N + i) * 10);
     } else {
       reset_env_multi(c, s, pool, pool_envs, b);
       if (obs)
@@ -630,6 +800,10 @@ int uavo_observe(const uavca_config* c, const uavo_state* s, double* obs) {
   for (int b = 0; b < c->num_envs; ++b) {
     if (c->kind == UAVCA_KIND_SINGLE)
       obs_single(c, s->pos + (size_t)b * 2, s->vel + (size_t)b * 2, s->tgt + (size_t)b * 2, s->steps[b] == 0, obs + (size_t)b * 4);
+    else if (c->circular && s->pos64)
+      for (int i = 0; i < N; ++i)
+        obs_multi_f64(c, s->pos64 + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt64 + (size_t)b * N * 2, N, i,
+                      obs + ((size_t)b * N + i) * 10);
     else
       for (int i = 0; i < N; ++i)
         obs_multi(c, s->pos + (size_t)b * N * 2, s->vel + (size_t)b * N * 2, s->tgt + (size_t)b * N * 2, N, i,

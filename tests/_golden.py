@@ -12,10 +12,12 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names(kind=None):
+    """Golden cases by name prefix; without a prefix: the float32-world cases (multi_*, single_*), which share one replay
+    loop — the float64-world cases (circular_*) have their own tests."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
     if kind:
-        names = [n for n in names if n.startswith(kind)]
-    return names
+        return [n for n in names if n.startswith(kind)]
+    return [n for n in names if not n.startswith("circular")]
 
 
 class Case:
@@ -33,6 +35,8 @@ class Case:
         if self.kind == "single":
             return O.single_config(self.E, reset_mode=m["reset_mode"], reset_source=O.SOURCE_POOL,
                                    single_f32_first_step=m["f32"])
+        if self.kind == "circular":  # reset(circular=True): the float64 world, every episode restarts on the ring
+            return O.multi_config(self.E, self.N, reset_mode=m["reset_mode"], max_episode_steps=m["max_steps"], circular=1)
         return O.multi_config(self.E, self.N, reset_mode=m["reset_mode"], max_episode_steps=m["max_steps"],
                               reset_source=O.SOURCE_POOL)
 

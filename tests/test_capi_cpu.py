@@ -69,7 +69,7 @@ def test_create_fails_loudly_without_a_gpu(capi):
 
 def test_bad_configs_are_rejected_before_touching_the_device(capi):
     lib = capi.load()
-    for field, value in (("num_agents", 33), ("num_agents", 0), ("num_envs", 0), ("tau", 0.0), ("kind", 7)):
+    for field, value in (("num_agents", 1025), ("num_agents", 0), ("num_envs", 0), ("tau", 0.0), ("kind", 7)):
         cfg = capi.default_config(capi.KIND_MULTI)
         setattr(cfg, field, value)
         h = C.c_void_p()

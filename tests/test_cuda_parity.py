@@ -593,15 +593,87 @@ def test_reset_is_uniform_over_the_box():
     assert (np.abs(hist / len(pos) - 0.1) < 0.005).all()
 
 
-def test_circular_reset():
-    cfg = O.multi_config(64, 6, circular=1, seed=1)
+def assert_state_equal_f64(env, st: O.State, where=""):
+    h = env.state.to_host()
+    for f in ("pos64", "tgt64", "init64", "prev64", "vel", "flags", "steps", "reach", "coll", "pos", "tgt", "init", "prev"):
+        assert np.array_equal(h[f], getattr(st, f)), f"state field {f} differs {where}"
+
+
+@pytest.mark.parametrize("n", [2, 6, 12, 24, 40])
+def test_circular_reset_is_the_float64_ring(n):
+    cfg = O.multi_config(64, n, circular=1, seed=1)
     env = make_env(cfg)
     orc = O.Oracle(cfg)
     obs = env.reset().cpu().numpy()
     obs_o = orc.reset()
-    assert_state_equal(env, orc.state, "after circular reset")
+    assert env.state.float64_world and env.state.pos64.dtype == torch.float64
+    assert_state_equal_f64(env, orc.state, "after circular reset")
     assert obs_close(obs, obs_o, RTOL, ATOL).all()
-    assert np.allclose(np.linalg.norm(env.state.pos.cpu().numpy(), axis=-1), 20.0, atol=1e-5)
+    assert np.allclose(np.linalg.norm(env.state.pos64.cpu().numpy(), axis=-1), 20.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", golden_names("circular"))
+def test_cuda_matches_reference_golden_circular(name):
+    """Episodes started by reset(circular=True) against the LITERAL reference: it keeps float64 locations there
+    (multi_uav_world_2d.py:157-163), so does the float64 world of the CUDA path — positions, velocities, prev
+    distances, latches, counters and every flag bit-exact; rewards / observations within tolerance."""
+    case = Case(name)
+    env = make_env(case.config())
+    env.enable_final_obs()
+    z = case.z
+    assert obs_close(env.reset().cpu().numpy(), z["obs0"], RTOL, ATOL).all()
+    for t in range(case.T):
+        env.step(torch.from_numpy(z["action"][t]).cuda(), evaluate=case.evaluate)
+        w = f"({name}, step {t})"
+        assert np.array_equal(env.done.cpu().numpy(), z["done"][t]), f"done flags differ {w}"
+        assert np.array_equal(env.reset_mask.cpu().numpy(), z["reset_mask"][t]), f"reset mask differs {w}"
+        h = env.state.to_host()
+        assert np.array_equal(h["pos64"], z["pos64"][t]), f"float64 positions differ {w}"
+        assert np.array_equal(h["vel"], z["vel"][t]), f"velocities differ {w}"
+        assert np.array_equal(h["prev64"], z["prev64"][t]), f"prev_distance differs {w}"
+        assert np.array_equal(h["flags"], z["flags"][t]), f"latches differ {w}"
+        keep = z["reset_mask"][t] == 0
+        assert np.array_equal(h["reach"][keep], z["reach"][t][keep]) and np.array_equal(h["coll"][keep], z["coll"][t][keep])
+        assert close(env.reward.cpu().numpy(), z["reward"][t]).all(), f"reward {w}"
+        assert obs_close(env.obs.cpu().numpy(), z["obs"][t], RTOL, ATOL).all(), f"obs {w}"
+        assert obs_close(env.final_obs.cpu().numpy(), z["final_obs"][t], RTOL, ATOL).all(), f"final obs {w}"
+
+
+def test_circular_rollout_vs_oracle_with_scores():
+    """A batch of float64-world envs (different actions per env) against the oracle's float64 world, auto-resets on."""
+    B, n = 300, 10
+    cfg = O.multi_config(B, n, circular=1, reset_mode=O.RESET_ON_ALL_DONE, max_episode_steps=260, seed=2, track_scores=1)
+    G = _b200()
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=n, circular=True, reset_mode=O.RESET_ON_ALL_DONE, max_episode_steps=260, seed=2,
+                                   track_scores=True)
+    orc = O.Oracle(cfg, nthreads=4)
+    env.reset()
+    orc.reset()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    gain = torch.linspace(0.3, 2.0, B, device="cuda").view(B, 1, 1)
+    for t in range(400):
+        a = ((env.state.tgt - env.state.pos) * gain + torch.randn((B, n, 2), generator=gen, device="cuda") * 0.5).clamp(-10, 10).contiguous()
+        env.step(a, evaluate=True)
+        out = orc.step(a.cpu().numpy(), evaluate=True)
+        assert np.array_equal(env.done.cpu().numpy(), out["done"]) and np.array_equal(env.reset_mask.cpu().numpy(), out["reset_mask"])
+        if t % 20 == 0 or t == 399:
+            assert_state_equal_f64(env, orc.state, f"(step {t})")
+            assert close(env.reward.cpu().numpy(), out["reward"]).all() and obs_close(env.obs.cpu().numpy(), out["obs"], RTOL, ATOL).all()
+            assert np.allclose(env.score.cpu().numpy(), orc.state.score, rtol=2e-5, atol=2e-4)
+    st = env.stats()
+    assert st["episodes"] == int(orc.state.stats[0]) >= B and st["reach"] == int(orc.state.stats[1]) > 0
+    assert st["collisions"] == int(orc.state.stats[2]) > 0
+    with pytest.raises(G.UavcaError):
+        env.rollout(4, None)  # K steps per launch serves the warp kernels only
+
+
+@pytest.mark.parametrize("n", [33, 40, 64, 100])
+def test_more_agents_than_a_warp_holds(n):
+    """`num_agents` is unbounded in the reference (multi_uav_world_2d.py:13,36-41): envs wider than a warp run on the
+    general one-thread-per-env kernel, same float32 semantics, same oracle."""
+    cfg = O.multi_config(130, n, reset_mode=O.RESET_ON_DONE0, max_episode_steps=30, seed=500 + n, x_size=60.0, y_size=60.0)
+    ev, _ = rollout_vs_oracle(cfg, steps=70, seed=n, crowd=0.4, check_every=3)
+    assert ev["resets"] > 0
 
 
 # ---- sharding, action modes, host path, graphs -----------------------------------------------------------------
@@ -780,7 +852,7 @@ def test_misaligned_tensors_are_rejected():
 def test_errors_are_loud():
     G = _b200()
     with pytest.raises(G.UavcaError):
-        G.BatchedMultiUAVWorld2D(16, num_agents=33)
+        G.BatchedMultiUAVWorld2D(16, num_agents=1025)
     env = G.BatchedMultiUAVWorld2D(16, num_agents=4)
     with pytest.raises(ValueError):
         env.step(torch.zeros((16, 3, 2), device="cuda"))

@@ -63,17 +63,41 @@ def test_compat_multi_surface():
     assert loc.dtype == np.float32 and (np.abs(loc) <= 25).all()
     obs2 = env.reset()
     assert not np.allclose(np.stack(obs), np.stack(obs2))  # a new episode is a new draw
-    ring = env.reset(circular=True)  # multi_uav_world_2d.py:157-163
-    loc = np.stack([a.location for a in env.agent_list]).astype(np.float64)
-    assert np.allclose(np.linalg.norm(loc, axis=1), 20.0, atol=1e-5) and len(ring) == 5
-    tgt = np.stack([a.target_location for a in env.agent_list]).astype(np.float64)
-    assert np.allclose(np.linalg.norm(tgt, axis=1), 23.0, atol=1e-5)
-    env.agent_list[2].location = np.array([1.5, -2.5])
-    assert np.array_equal(env.agent_list[2].location, np.array([1.5, -2.5], np.float32))
+    ring = env.reset(circular=True)  # multi_uav_world_2d.py:157-163: float64 locations from here to the next reset()
+    loc = np.stack([a.location for a in env.agent_list])
+    assert loc.dtype == np.float64 and np.allclose(np.linalg.norm(loc, axis=1), 20.0, atol=1e-12) and len(ring) == 5
+    tgt = np.stack([a.target_location for a in env.agent_list])
+    assert tgt.dtype == np.float64 and np.allclose(np.linalg.norm(tgt, axis=1), 23.0, atol=1e-12)
+    env.agent_list[2].location = np.array([1.5, -2.5000000001])
+    assert np.array_equal(env.agent_list[2].location, np.array([1.5, -2.5000000001]))
     for _ in range(3):
         env.step([env.action_space.sample() for _ in range(5)])
-    assert env.steps == 3
+    assert env.steps == 3 and env.agent_list[0].location.dtype == np.float64
     env.render()
+    env.reset()  # a plain reset leaves the float64 world
+    assert env.agent_list[0].location.dtype == np.float32 and env.steps == 0
+    env.close()
+
+
+def test_compat_circular_episode_is_the_references_float64_world():
+    """The plotting script's loop (test_sac_multi_plot_trajectory.py:40-68: reset(circular=True), step, read
+    agent.location / .done) through the drop-in class, against the literal reference's golden vectors."""
+    from gym_uav_collision_avoidance_b200 import compat
+
+    case = Case("circular_n6")
+    z, N = case.z, case.N
+    env = compat.MultiUAVWorld2D(num_agents=N)
+    obs = env.reset(circular=True)
+    assert obs_close(np.stack(obs), z["obs0"][0], RTOL, ATOL).all()
+    for t in range(150):
+        if z["reset_mask"][t, 0]:
+            break
+        obs, rewards, dones, _ = env.step([z["action"][t, 0, i].astype(np.float64) for i in range(N)])
+        assert dones == [bool(d) for d in z["done"][t, 0]]
+        assert np.array_equal(np.stack([a.location for a in env.agent_list]), z["pos64"][t, 0]), f"float64 locations, step {t}"
+        assert _close(rewards, z["reward"][t, 0]).all() and obs_close(np.stack(obs), z["obs"][t, 0], RTOL, ATOL).all()
+        assert [a.done for a in env.agent_list] == [bool(f & 1) for f in z["flags"][t, 0]]
+    assert t > 100
     env.close()
 
 

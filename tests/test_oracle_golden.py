@@ -37,6 +37,33 @@ def test_oracle_matches_reference_golden(name):
             assert np.array_equal(out["distance"], z["distance"][t]), f"info distance, step {t}"
 
 
+@pytest.mark.parametrize("name", golden_names("circular"))
+def test_oracle_matches_reference_golden_circular(name):
+    """Episodes started by reset(circular=True): the reference keeps float64 locations (multi_uav_world_2d.py:157-163), the
+    oracle's float64 world must reproduce them bit for bit — positions, velocities, rewards, observations, flags."""
+    case = Case(name)
+    orc = O.Oracle(case.config())
+    z = case.z
+    assert np.array_equal(orc.reset(), z["obs0"]), "reset(circular=True) observation"
+    assert np.allclose(np.linalg.norm(orc.state.pos64, axis=-1), 20.0, atol=1e-12)
+    for t in range(case.T):
+        steps_before = orc.state.steps.copy()
+        out = orc.step(z["action"][t], evaluate=case.evaluate, want_final_obs=True)
+        assert np.array_equal(out["done"], z["done"][t]), f"done flags, step {t}"
+        assert np.array_equal(out["reset_mask"], z["reset_mask"][t]), f"reset mask, step {t}"
+        assert np.array_equal(out["reward"], z["reward"][t]), f"reward, step {t}"
+        assert np.array_equal(out["final_obs"], z["final_obs"][t]), f"terminal observation, step {t}"
+        assert np.array_equal(out["obs"], z["obs"][t]), f"observation, step {t}"
+        assert np.array_equal(orc.state.pos64, z["pos64"][t]), f"position, step {t}"
+        assert np.array_equal(orc.state.vel, z["vel"][t]), f"velocity, step {t}"
+        assert np.array_equal(orc.state.prev64, z["prev64"][t]), f"prev_distance, step {t}"
+        assert np.array_equal(orc.state.flags, z["flags"][t]), f"parked/collided latches, step {t}"
+        keep = z["reset_mask"][t] == 0  # the golden counters were read before a restart zeroed them
+        assert np.array_equal(orc.state.steps[keep], z["steps"][t][keep]) and np.array_equal(steps_before + 1, z["steps"][t])
+        assert np.array_equal(orc.state.reach[keep], z["reach"][t][keep]) and np.array_equal(orc.state.coll[keep], z["coll"][t][keep])
+        assert np.array_equal(orc.state.pos, z["pos64"][t].astype(np.float32))  # the float32 mirrors follow
+
+
 def test_golden_cases_exercise_the_interesting_events():
     ev = dict(done=0, resets=0, reach=0, coll=0, parked=0)
     for name in golden_names("multi"):
