@@ -477,6 +477,16 @@ def run_ours(args, wl, rank, world, local_rank):
             gpu_launches += rollout.pop("_launches")
     headline_rollout = rollout is not None and args.headline == "rollout"
 
+    # ---- BASELINE configs[4] beside it (one GPU, default workload only): policy + env step + replay append per acting step
+    acting = None
+    if world == 1 and args.workload == "c3" and not args.no_acting:
+        a_wl = WORKLOADS["c5r"]
+        rows, a_launches = measure_acting(args, G, torch, dev, rank, world, dist, barrier, a_wl["B"], a_wl["N"], min(K, 400))
+        acting = {"workload": a_wl["desc"], "rows": rows,
+                  "what": "us per acting step and UAV env-steps/s; fp32 = eager PyTorch policy in the reference's arithmetic, "
+                          "fused = uavca_policy_act (one tcgen05 kernel, fp16 operands / fp32 accumulate)"}
+        gpu_launches += a_launches
+
     # ---- end to end through the host-buffer C-ABI call (uavca_step_host): pinned host buffers, H2D + step + D2H
     D = 4 if kind == "single" else 10
     h_act = [torch.empty((B, N, 2), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -513,6 +523,21 @@ def run_ours(args, wl, rank, world, local_rank):
             local[k] += s[k]
     stats = sharding.reduce_stats(local, device=dev)
     topos = gather_objects(dist, topo, world)
+
+    # strong-scaling workloads (configs[3]): the SAME total workload on ONE GPU, measured by rank 0 alone while the other
+    # ranks wait — the N=1 bench line is a different workload (configs[2]), so this is the number to scale against
+    one_gpu = None
+    if wl.get("shard_total") and world > 1 and not args.no_rollout:
+        for e in envs:
+            e.close()
+        envs.clear()
+        torch.cuda.empty_cache()
+        if rank == 0:
+            try:
+                one_gpu = measure_one_gpu_total(torch, G, wl, dev, amax, args.headline)
+            except Exception as exc:  # noqa: BLE001
+                one_gpu = {"unavailable": repr(exc)[:200]}
+        barrier()
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -568,7 +593,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "config": dict(workload_config(args, wl, world, B), env_steps_per_s=value / N, path=path,
                            actions_resident="in HBM", auto_reset_source="on-device Philox", l2=l2,
                            timing=f"CUDA events around each of {n_head_reps} repetitions of the {K}-step region; value = median repetition",
-                           parallelism=f"env-sharded x{world}, no per-step collective", repetitions=n_head_reps),
+                           parallelism=f"env-sharded x{world}, no per-step collective", repetitions=n_head_reps,
+                           one_gpu_same_workload=one_gpu),
             "e2e": {"value": e2e_value, "unit": "UAV env-steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "host_gbs_per_gpu": e2e_bytes_s / 1e9, "pcie_ceiling": pcie,
                     "frac_of_pcie_ceiling": (e2e_bytes_s / 1e9) / pcie["duplex_gbs"] if pcie and pcie.get("duplex_gbs") else None,
@@ -589,6 +615,7 @@ def run_ours(args, wl, rank, world, local_rank):
                          "frac_per_step_launch": per_step["frac"], "frac_single_stream": per_step["frac_single_stream"]},
             "per_step_launch": per_step,
             "rollout": rollout,
+            "acting_c5r": acting,
             "cpu_baseline": cpu,
             "cpu_baseline_literal": lit,
             "clocks": head_clocks,
@@ -597,6 +624,43 @@ def run_ours(args, wl, rank, world, local_rank):
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def measure_one_gpu_total(torch, G, wl, dev, amax, headline):
+    """The whole strong-scaling workload (all wl["B"] envs) on one GPU through the headline path: UAV env-steps/s."""
+    B, N = wl["B"], wl["N"]
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=1500, seed=0x5EED, device=dev)
+    env.reset()
+    M = B * N
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if headline == "rollout":
+        Kr = int(max(1, min(4, 12e9 // (2 * M * 45))))
+        acts = (torch.rand((Kr, B, N, 2), device=dev) * 2 - 1) * amax
+        out = env.rollout(Kr, acts, sync_last=False)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(reps):
+            env.rollout(Kr, acts, out=out, sync_last=False)
+        e1.record()
+        steps = reps * Kr
+        path = f"uavca_rollout, {Kr} steps per launch, action block"
+    else:
+        acts = (torch.rand((B, N, 2), device=dev) * 2 - 1) * amax
+        for _ in range(3):
+            env.step(acts)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(4 * reps):
+            env.step(acts)
+        e1.record()
+        steps = 4 * reps
+        path = "one launch per step"
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    env.close()
+    return {"n_gpus": 1, "envs": B, "value": M * steps / (ms * 1e-3), "us_per_step": ms * 1e3 / steps, "path": path,
+            "what": "the same total workload on ONE GPU (rank 0 alone, the other ranks idle), for the strong-scaling ratio"}
 
 
 def gather_objects(dist, obj, world):
@@ -726,15 +790,14 @@ def run_c1(args, wl, G, torch, dev):
           "gpu_launches": int(launches), "roofline": None, "cpu_baseline": lit, "cpu_baseline_literal": lit})
 
 
-def run_acting(args, wl, G, torch, dev, rank, world, dist, barrier):
+def measure_acting(args, G, torch, dev, rank, world, dist, barrier, B, N, K):
     """BASELINE configs[4]: one acting step = policy forward over all B*N observations + env step (polar action map
     fused) + append of the B*N transitions to the device replay ring.  Rows: eager fp32 (the reference's arithmetic),
-    TF32, and the fused tcgen05 acting kernel; value = the fp32 row unless --acting-precision says otherwise."""
+    TF32, and the fused tcgen05 acting kernel.  Returns (rows, launches of ours)."""
     from gym_uav_collision_avoidance_b200 import sharding
 
-    B, N = wl["B"], wl["N"]
-    K = args.steps
     torch.manual_seed(0)
+    tf32_before = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     rows = {}
     stream = torch.cuda.Stream(device=dev)
@@ -750,7 +813,7 @@ def run_acting(args, wl, G, torch, dev, rank, world, dist, barrier):
             for _ in range(3):
                 ro.step()
         torch.cuda.synchronize(dev)
-        n_graph = min(K, 50)
+        n_graph = max(2, min(K, 50) // 2 * 2)  # even: the rollout ping-pongs two observation buffers
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=stream):
             for _ in range(n_graph):
@@ -763,14 +826,22 @@ def run_acting(args, wl, G, torch, dev, rank, world, dist, barrier):
             for _ in range(q):
                 g.replay()
 
-        ts = timed_reps(torch, stream, rep, 0.07 * q * n_graph if precision == "fused" else 1.0 * q * n_graph, dev, barrier)
+        ts = timed_reps(torch, stream, rep, (0.07 if precision == "fused" else 1.0) * q * n_graph, dev, barrier)
         ts = [sharding.max_over_ranks(t, device=dev) for t in ts] if dist is not None else ts
         med = statistics.median(ts)
         us = med * 1e3 / (q * n_graph)
         rows[precision] = {"us_per_acting_step": us, "value": world * B * N / us * 1e6, "best_us": min(ts) * 1e3 / (q * n_graph),
-                           "repetitions": len(ts), "replay_size": len(replay)}
+                           "repetitions": len(ts), "steps_per_repetition": q * n_graph, "replay_size": len(replay)}
         total_launches += env.launch_count
         del g, ro, replay, env
+    torch.backends.cuda.matmul.allow_tf32 = tf32_before
+    return rows, total_launches
+
+
+def run_acting(args, wl, G, torch, dev, rank, world, dist, barrier):
+    """`--workload c5r`: the acting step as the headline; value = the fp32 row unless --acting-precision says otherwise."""
+    B, N, K = wl["B"], wl["N"], args.steps
+    rows, total_launches = measure_acting(args, G, torch, dev, rank, world, dist, barrier, B, N, K)
     head = args.acting_precision
     if rank == 0:
         us = rows[head]["us_per_acting_step"]
@@ -814,6 +885,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-acting", action="store_true", help="skip the configs[4] acting-step rows of the default line")
     ap.add_argument("--no-numa-bind", action="store_true")
     ap.add_argument("--rollout-k", type=int, default=32, help="steps per launch of the rollout measurement")
     ap.add_argument("--headline", default="rollout", choices=["rollout", "per_step"],

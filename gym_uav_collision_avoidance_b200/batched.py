@@ -170,6 +170,15 @@ class _BatchedBase:
         return pool
 
     # -- gym-shaped API --------------------------------------------------------------------------------------------
+    def set_obs_buffer(self, obs: torch.Tensor) -> None:
+        """Make `obs` ([B, N, D] float32 CUDA, contiguous) the tensor the next step / reset writes its observation into
+        (`env.obs` afterwards).  Lets a caller ping-pong two buffers instead of copying the observation it acted on."""
+        if obs.shape != self.obs.shape or obs.dtype != torch.float32 or obs.device != self.device or not obs.is_contiguous():
+            raise ValueError("set_obs_buffer needs a contiguous float32 CUDA tensor shaped like env.obs")
+        self.obs = obs
+        self._ptrs = (self.state.blob.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                      self.reset_mask.data_ptr())
+
     def enable_final_obs(self, on: bool = True):
         """Also emit the step's own next-observation before any auto-reset (what a replay buffer stores)."""
         self.final_obs = torch.zeros_like(self.obs) if on else None

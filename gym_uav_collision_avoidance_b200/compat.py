@@ -43,6 +43,34 @@ def register_gym_ids() -> bool:
     return False
 
 
+class _HostIO:
+    """Pinned host tensors the B=1 step reads its action from and writes obs / reward / done into directly (mapped host
+    memory: the kernel's loads and stores go through PCIe, one launch + one stream synchronisation per step, no copies)."""
+
+    def __init__(self, b):
+        N, D = b.num_agents, b.obs_dim
+        pin = lambda *shape, dtype=torch.float32: torch.zeros(shape, dtype=dtype).pin_memory()  # noqa: E731
+        self.action, self.obs, self.reward = pin(1, N, 2), pin(1, N, D), pin(1, N)
+        self.done, self.mask, self.distance = pin(1, N, dtype=torch.uint8), pin(1, dtype=torch.uint8), pin(1)
+        self.np = {k: getattr(self, k).numpy() for k in ("action", "obs", "reward", "done", "distance")}
+        self.ptr = {k: getattr(self, k).data_ptr() for k in ("action", "obs", "reward", "done", "mask", "distance")}
+
+    def step(self, b, n_action, evaluate=False):
+        from . import _capi
+
+        self.np["action"][...] = np.asarray(n_action, dtype=np.float64).reshape(1, b.num_agents, 2)
+        p, st = self.ptr, torch.cuda.current_stream(b.device)
+        if b.kind == _capi.KIND_SINGLE:
+            rc = b._lib.uavca_step_single(b._h, b.state.blob.data_ptr(), p["action"], 0, p["obs"], p["reward"], p["done"],
+                                          p["distance"], None, p["mask"], st.cuda_stream)
+        else:
+            rc = b._lib.uavca_step_multi(b._h, b.state.blob.data_ptr(), p["action"], 0, int(bool(evaluate)), p["obs"], p["reward"],
+                                         p["done"], None, p["mask"], st.cuda_stream)
+        _capi.check(rc, "uavca_step")
+        st.synchronize()
+        return self.np
+
+
 class _AgentView:
     """`UAVAgent` (uav_agent.py:7-20) as a window onto UAV `i` of the device state."""
 
@@ -101,6 +129,7 @@ class MultiUAVWorld2D:
                   num_agents=num_agents, collider_radius=collider_radius, d_sense=d_sense, device=device, seed=seed)
         self._b = BatchedMultiUAVWorld2D(1, **kw)
         self._kw = kw
+        self._io = _HostIO(self._b)
         self._circ = None  # float64-world twin (its own state), created on the first reset(circular=True)
         self._live = self._b  # the env the current episode runs in
         for name in ("x_size", "y_size", "map_diagonal_size", "min_location", "max_location", "max_speed", "min_speed",
@@ -153,11 +182,10 @@ class MultiUAVWorld2D:
         return (obs, info) if return_info else obs
 
     def step(self, n_action, evaluate=False):
-        a = torch.as_tensor(np.asarray(n_action, dtype=np.float64).reshape(1, self.num_agents, 2), dtype=torch.float32)
-        obs, reward, done, _ = self._live.step(a.to(self._b.device), evaluate=evaluate)
-        r = reward[0].cpu().numpy()
-        d = done[0].cpu().numpy()
-        return (self._obs_list(obs), [float(x) for x in r], [bool(x) for x in d], {"distance": 0})
+        out = self._io.step(self._live, n_action, evaluate)
+        o = out["obs"][0].astype(np.float64)
+        return ([o[i] for i in range(self.num_agents)], [float(x) for x in out["reward"][0]],
+                [bool(x) for x in out["done"][0]], {"distance": 0})
 
     def render(self, mode="human"):
         """No window: the reference's pygame drawing (multi_uav_world_2d.py:243-331) is replaced by a trajectory tap.
@@ -196,6 +224,7 @@ class UAVWorld2D:
             setattr(self, name, getattr(self._b, name))
         self.map_dimension = np.array([x_size, y_size])
         self.window = self.clock = None
+        self._io = _HostIO(self._b)
 
     def _field(name, scalar=False):
         def get(self):
@@ -235,10 +264,9 @@ class UAVWorld2D:
         return (obs, self._get_info()) if return_info else obs
 
     def step(self, action):
-        a = torch.as_tensor(np.asarray(action, dtype=np.float64).reshape(1, 1, 2), dtype=torch.float32)
-        obs, reward, done, info = self._b.step(a.to(self._b.device))
-        return (obs[0, 0].cpu().numpy().astype(np.float64), np.float32(reward[0, 0].item()), bool(done[0, 0].item()),
-                {"distance": np.float32(info["distance"][0].item())})
+        out = self._io.step(self._b, action)
+        return (out["obs"][0, 0].astype(np.float64), np.float32(out["reward"][0, 0]), bool(out["done"][0, 0]),
+                {"distance": np.float32(out["distance"][0])})
 
     def render(self, mode="human"):
         return None

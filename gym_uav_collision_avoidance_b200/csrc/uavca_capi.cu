@@ -188,6 +188,7 @@ struct uavca_handle {
   const void* pool_blob = nullptr;
   int pool_envs = 0;
   uavca_layout pool_layout{};
+  double4* ring64 = nullptr;  // reset(circular=True) table (owned): per UAV (pos.x, pos.y, tgt.x, tgt.y) in float64
   long long launches = 0;
   int path = UAVCA_PATH_LANES;  // UAVCA_STEP_PATH=tma in the environment selects the bulk (TMA) kernel for whole tiles (A/B measurements)
   // end-to-end (host buffer) path, created lazily
@@ -220,6 +221,7 @@ KernelArgs make_args(const uavca_handle* h, void* state) {
   a.s = view_of(state, h->layout);
   a.pool = view_of(const_cast<void*>(h->pool_blob), h->pool_layout);
   a.pool_envs = h->pool_envs;
+  a.ring64 = h->ring64;
   a.B = h->cfg.num_envs;
   a.N = h->cfg.num_agents;
   return a;
@@ -302,6 +304,21 @@ int uavca_create(const uavca_config* cfg, int device, uavca_handle** out) {
               : std::strcmp(p, "prefetch") == 0 ? UAVCA_PATH_PREFETCH
               : std::strcmp(p, "plain") == 0 ? UAVCA_PATH_PLAIN : UAVCA_PATH_LANES;
   }
+  if (cfg->kind == UAVCA_KIND_MULTI && cfg->circular) {
+    // multi_uav_world_2d.py:157-163 with the HOST libm: the reference evaluates math.cos / math.sin (glibc) in float64,
+    // and the device's cos / sin are not bit-identical to it; the ring is a table of N entries computed once here
+    DeviceGuard g(device);
+    const int N = cfg->num_agents;
+    std::vector<double4> ring(N);
+    const double pi = 3.141592653589793;
+    for (int i = 0; i < N; ++i) {
+      const double th = 2 * i * pi / N;
+      ring[i] = make_double4(20.0 * std::cos(th), 20.0 * std::sin(th), 23.0 * std::cos(th + pi), 23.0 * std::sin(th + pi));
+    }
+    e = cudaMalloc(&h->ring64, sizeof(double4) * N);
+    if (e == cudaSuccess) e = cudaMemcpy(h->ring64, ring.data(), sizeof(double4) * N, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { delete h; return fail_cuda("circular reset table", e); }
+  }
   *out = h;
   return 0;
 }
@@ -309,6 +326,7 @@ int uavca_create(const uavca_config* cfg, int device, uavca_handle** out) {
 int uavca_destroy(uavca_handle* h) {
   if (!h) return 0;
   DeviceGuard g(h->device);
+  if (h->ring64) cudaFree(h->ring64);
   for (auto& s : h->hs) if (s) cudaStreamDestroy(s);
   for (auto& ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
   if (h->fork) cudaEventDestroy(h->fork);

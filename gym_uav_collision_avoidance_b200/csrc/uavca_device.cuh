@@ -96,6 +96,7 @@ struct KernelArgs {
   StateView s;
   StateView pool;  // reset pool (pos == nullptr when absent)
   int pool_envs;
+  const double4* ring64;  // reset(circular=True): per UAV (pos.x, pos.y, tgt.x, tgt.y), float64, computed with the host libm
   StepIO io;
   int B, N;
 };

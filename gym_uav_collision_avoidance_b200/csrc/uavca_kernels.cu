@@ -86,6 +86,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_kernel(c
 }
 
 
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc, int bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+  else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- K steps per launch -------------------------------------------------------------------------------------------
 // I/O policy of step_core for uavca_rollout: the state of the warp's UAVs stays in REGISTERS for all K steps (loaded
 // once, stored once), only the per-step outputs stream out, as [K][...] blocks.  Removes the launch, ramp-up and tail
@@ -100,7 +108,8 @@ struct RolloutIO {
   Uav cur;
   float2 act;
   int steps;
-  int k;
+  int k;  // step of the launch: outputs go to slot k of the [K][...] blocks (one 64-bit multiply-add per store; running
+          // pointers were tried and cost ten more live registers across step_core: 300 bytes of spills at 64 registers)
   __device__ __forceinline__ Uav load_uav() const { return cur; }
   __device__ __forceinline__ float2 load_action() const { return act; }
   __device__ __forceinline__ int load_steps() const { return steps; }
@@ -131,19 +140,23 @@ struct RolloutIO {
 
 template <int NT, bool FULL>
 __device__ __forceinline__ void rollout_multi_body(const KernelArgs& a, const RolloutArgs& r, const WarpScratch& ws,
-                                                   int warp_global) {
+                                                   float* act_smem, int warp_global) {
   const Lane L = make_lane<NT, FULL>(a.B, a.N, warp_global);
   RolloutIO io{a, r, L, ws.stage, load_uav(a.s, L), make_float2(0.f, 0.f), L.valid ? a.s.steps[L.env] : 0, 0};
   cudaTriggerProgrammaticLaunchCompletion();
   const long long env_global = a.c.env_base + L.env;
   uint4 words = make_uint4(0u, 0u, 0u, 0u);
-  float2 next_act = make_float2(0.f, 0.f);  // action block: the load of step k+1 is in flight while step k is computed
-  if (r.action_block != nullptr && L.valid) next_act = ld_stream(r.action_block + L.m);
+  // Action block: the action of step k+1 travels while step k is computed — by cp.async into a per-lane shared-memory slot
+  // (two slots, alternating), not into registers: at 64 registers ptxas sinks a register prefetch down to its use, and
+  // ncu showed 15 % of the warp-time waiting on that load (profiles/r2_full_rollout_n32.md).
+  float2* act_slot = reinterpret_cast<float2*>(act_smem) + L.lane;
+  if (r.action_block != nullptr && L.valid) cp_async(act_slot, r.action_block + L.m, 8);
   for (int k = 0; k < r.K; ++k) {
     io.k = k;
     if (r.action_block != nullptr) {
-      io.act = next_act;
-      if (k + 1 < r.K && L.valid) next_act = ld_stream(r.action_block + (size_t)(k + 1) * r.M + L.m);
+      cp_async_wait_all();
+      io.act = L.valid ? act_slot[(k & 1) * 32] : make_float2(0.f, 0.f);
+      if (k + 1 < r.K && L.valid) cp_async(act_slot + ((k + 1) & 1) * 32, r.action_block + (size_t)(k + 1) * r.M + L.m, 8);
     } else {
       const unsigned long long t = r.step0 + (unsigned long long)k;
       if (k == 0 || (t & 1ull) == 0ull) words = action_words(r.seed_lo, r.seed_hi, env_global, L.i, t);
@@ -165,13 +178,15 @@ template <int NT>
 __global__ void __launch_bounds__(kThreads, UAVCA_ROLLOUT_MINB) rollout_multi_kernel(const __grid_constant__ KernelArgs a,
                                                                                   const __grid_constant__ RolloutArgs r) {
   __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
+  __shared__ __align__(16) float act_smem[kWarpsPerBlock * 128];  // per warp: two slots of 32 float2 actions
   const WarpScratch ws = warp_scratch(smem);
   const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int N = NT > 0 ? NT : a.N;
   const bool full = uavs_left(a.B, N, warp_global) >= (32 / N) * N;  // warp-uniform
   cudaGridDependencySynchronize();
-  if (full) rollout_multi_body<NT, true>(a, r, ws, warp_global);
-  else rollout_multi_body<NT, false>(a, r, ws, warp_global);
+  float* const my_act = act_smem + (threadIdx.x >> 5) * 128;
+  if (full) rollout_multi_body<NT, true>(a, r, ws, my_act, warp_global);
+  else rollout_multi_body<NT, false>(a, r, ws, my_act, warp_global);
 }
 
 // The action stream of uavca_rollout on its own, one step: out[m] = the policy-space action of global step t.
@@ -196,13 +211,6 @@ __global__ void __launch_bounds__(kThreads) sample_actions_kernel(const __grid_c
 // (UAVCA_STEP_PATH=prefetch), parity-tested.
 constexpr int kPfStageBytes = 32 * (16 + 8 + 8 + 8 + 4 + 4);  // vel, pos, tgt, action, init, prev of one warp-tile
 
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc, int bytes) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-  else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct PfStage {
   double2* vel;
@@ -474,16 +482,21 @@ __global__ void __launch_bounds__(kThreads) step_single_kernel(const __grid_cons
 // K steps of UAVWorld2D per launch, the env in registers throughout (see RolloutIO above).
 __global__ void __launch_bounds__(kThreads) rollout_single_kernel(const __grid_constant__ KernelArgs a,
                                                                   const __grid_constant__ RolloutArgs r) {
+  __shared__ __align__(16) float2 act_smem[2 * kThreads];  // per thread two alternating slots: the next step's action by cp.async
   const long long b = (long long)blockIdx.x * kThreads + threadIdx.x;
   cudaGridDependencySynchronize();
   if (b >= a.B) return;
   SingleEnv e = load_single(a.s, b);
   cudaTriggerProgrammaticLaunchCompletion();
   uint4 words = make_uint4(0u, 0u, 0u, 0u);
+  float2* slot = act_smem + threadIdx.x;
+  if (r.action_block != nullptr) cp_async(slot, r.action_block + b, 8);
   for (int k = 0; k < r.K; ++k) {
     float2 act;
     if (r.action_block != nullptr) {
-      act = ld_stream(r.action_block + (size_t)k * r.M + b);
+      cp_async_wait_all();
+      act = slot[(k & 1) * kThreads];
+      if (k + 1 < r.K) cp_async(slot + ((k + 1) & 1) * kThreads, r.action_block + (size_t)(k + 1) * r.M + b, 8);
     } else {
       const unsigned long long t = r.step0 + (unsigned long long)k;
       if (k == 0 || (t & 1ull) == 0ull) words = action_words(r.seed_lo, r.seed_hi, a.c.env_base + b, 0, t);
@@ -560,28 +573,42 @@ __global__ void __launch_bounds__(kThreads) replay_push_kernel(const V* obs, con
                                                                const uint8_t* done, long long M, long long od, long long ad,
                                                                V* r_obs, V* r_act, float* r_rew, V* r_nxt, float* r_mask,
                                                                long long cap, long long head, long long* meta) {
-  // meta (nullable, device): [0] ring head, [1] block ticket, [2] transitions held.  With it the head lives on the
+  // meta (nullable, device): [0] ring head, [1] block ticket, [2] transitions held, [3] appends so far.  With it the head lives on the
   // device, so a CUDA-graph replay of the push appends where the previous replay stopped; the last block to finish
   // (every block has read the head by then) advances it.
   if (meta != nullptr) head = meta[0];
-  const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (j < M * od) {
+  // grid-stride: the grid is capped at a few CTAs per SM so that the block ticket below stays a few hundred atomics
+  const long long stride = (long long)gridDim.x * kThreads;
+  for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < M * od; j += stride) {
     long long d = head * od + j;
     if (d >= cap * od) d -= cap * od;
     r_obs[d] = ld_stream(obs + j);
     r_nxt[d] = ld_stream(nxt + j);
+    if (j < M * ad) {
+      long long da = head * ad + j;
+      if (da >= cap * ad) da -= cap * ad;
+      r_act[da] = ld_stream(act + j);
+    }
+    if (j < M) {
+      long long d1 = head + j;
+      if (d1 >= cap) d1 -= cap;
+      r_rew[d1] = ld_stream(rew + j);
+      r_mask[d1] = done[j] ? 0.0f : 1.0f;
+    }
   }
-  if (j < M * ad) {
-    long long d = head * ad + j;
-    if (d >= cap * ad) d -= cap * ad;
-    r_act[d] = ld_stream(act + j);
-  }
-  if (j < M) {
-    long long d = head + j;
-    if (d >= cap) d -= cap;
-    r_rew[d] = ld_stream(rew + j);
-    r_mask[d] = done[j] ? 0.0f : 1.0f;
-  }
+  if (ad > od)  // an action wider than an observation (never the case for the reference's worlds): its tail
+    for (long long j = M * od + (long long)blockIdx.x * kThreads + threadIdx.x; j < M * ad; j += stride) {
+      long long da = head * ad + j;
+      if (da >= cap * ad) da -= cap * ad;
+      r_act[da] = ld_stream(act + j);
+    }
+  if (od < 1)  // no observation columns: rewards and masks on their own
+    for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < M; j += stride) {
+      long long d1 = head + j;
+      if (d1 >= cap) d1 -= cap;
+      r_rew[d1] = ld_stream(rew + j);
+      r_mask[d1] = done[j] ? 0.0f : 1.0f;
+    }
   if (meta != nullptr) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -592,6 +619,7 @@ __global__ void __launch_bounds__(kThreads) replay_push_kernel(const V* obs, con
         meta[0] = nh >= cap ? nh - cap : nh;
         const long long held = meta[2] + M;
         meta[2] = held > cap ? cap : held;
+        meta[3] += 1;  // appends so far: a per-step device counter other kernels of an acting step can key their RNG on
         meta[1] = 0;
       }
     }
@@ -901,6 +929,11 @@ cudaError_t launch_map_action(const Consts& c, const float* in, float* out, long
   return cudaGetLastError();
 }
 
+static inline int push_grid(long long n) {
+  const int g = flat_grid(n);
+  return g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8;
+}
+
 cudaError_t launch_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs,
                                const uint8_t* done, long long M, int obs_dim, int act_dim, float* r_obs, float* r_act,
                                float* r_rew, float* r_next, float* r_mask, long long capacity, long long head,
@@ -912,13 +945,13 @@ cudaError_t launch_replay_push(const float* obs, const float* action, const floa
   const long long widest = (long long)(obs_dim > act_dim ? obs_dim : act_dim);
   if (wide) {
     const long long n = M * (widest / 2) > M ? M * (widest / 2) : M;
-    replay_push_kernel<float2><<<flat_grid(n), kThreads, 0, st>>>(
+    replay_push_kernel<float2><<<push_grid(n), kThreads, 0, st>>>(
         reinterpret_cast<const float2*>(obs), reinterpret_cast<const float2*>(action), reward,
         reinterpret_cast<const float2*>(next_obs), done, M, obs_dim / 2, act_dim / 2, reinterpret_cast<float2*>(r_obs),
         reinterpret_cast<float2*>(r_act), r_rew, reinterpret_cast<float2*>(r_next), r_mask, capacity, head, meta);
   } else {
     const long long n = M * (widest > 1 ? widest : 1);
-    replay_push_kernel<float><<<flat_grid(n), kThreads, 0, st>>>(obs, action, reward, next_obs, done, M, obs_dim, act_dim,
+    replay_push_kernel<float><<<push_grid(n), kThreads, 0, st>>>(obs, action, reward, next_obs, done, M, obs_dim, act_dim,
                                                                   r_obs, r_act, r_rew, r_next, r_mask, capacity, head, meta);
   }
   return cudaGetLastError();

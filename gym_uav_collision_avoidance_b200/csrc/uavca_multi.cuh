@@ -111,6 +111,18 @@ struct WarpScratch {
   float4* cand;   // [32]  by lane of the UAV
   float* th;      // [32]  by lane of the UAV
   float* stage;   // [320] observation rows of the warp
+  // Small envs (SweepKind::kMixed) use the same memory as ONE doubled ring of (old, new) positions instead (see below):
+  __device__ __forceinline__ float4* ring() const { return pairs; }                                    // [64]
+  __device__ __forceinline__ float* ring_th() const { return reinterpret_cast<float*>(pairs) + 256; }  // [64]
+};
+// Up to this many UAVs per env the neighbour sweep computes BOTH distances of a neighbour (sequential pass and
+// observation pass) in one packed instruction stream — 11.5 instructions per neighbour and nothing afterwards; above it
+// the two-neighbours-per-load sweep of the new positions (8 per neighbour + ~30 once) wins.  Crossover at N ~ 12
+// (ncu: N=8 executes 575 warp-instructions per step with the latter, ~550 with the former).
+constexpr int kMixedMaxN = 10;
+template <int NT>
+struct SweepKind {
+  static constexpr bool kMixed = NT > 0 && NT <= kMixedMaxN;
 };
 constexpr int kRingFloats = 48 * 4 + 32 * 4 + 32;
 constexpr int kScratchFloats = kRingFloats + 32 * 10;
@@ -253,6 +265,23 @@ __device__ __forceinline__ void pair_scan(const Consts& c, const WarpScratch& ws
 struct ObsTail {
   float2 a, b, c;  // (o4, o5) (o6, o7) (o8, o9)
 };
+// Observation features 4..9 from the two selected neighbours (multi_uav_world_2d.py:75-95).
+__device__ __forceinline__ ObsTail obs_tail(const Consts& c, float dx1, float dy1, float dx2, float dy2, float s1, float s2,
+                                            float h1, float h2, bool have1, bool have2, float th_u) {
+  const float2 b = fast_atan2_pair(dy1, dx1, dy2, dx2);
+  const float2 nth = make_float2(-th_u, -th_u);
+  const float2 v1 = wrap_units2(__ffma2_rn(b, make_float2(c.inv_pi, c.inv_pi), nth));  // bearings relative to the heading
+  const float2 v2 = wrap_units2(__fadd2_rn(make_float2(h1, h2), nth));                 // neighbour headings, relative
+  ObsTail o;
+  o.a.x = have1 ? sqrt_approx(s1) * c.inv_dsense : 1.0f;  // :77
+  o.a.y = have1 ? v1.x : 1.0f;                            // :78-81 (no neighbour: bearing pi)
+  o.b.x = have1 ? v2.x : 0.0f;                            // :82-85
+  o.b.y = have2 ? sqrt_approx(s2) * c.inv_dsense : 1.0f;  // :87
+  o.c.x = have2 ? v1.y : 1.0f;                            // :88-91
+  o.c.y = have2 ? v2.y : 0.0f;                            // :92-95
+  return o;
+}
+
 // smin (WANT_A): squared distance to the nearest other UAV as the reference's sequential sweep sees it — j < i at the
 // NEW position, j > i at the OLD one (multi_uav_world_2d.py:181-210).  Only a UAV within `near` of the new position
 // can be within collision reach of the old one (a UAV moves at most sqrt(2) v_max tau per step; Consts::near_key),
@@ -280,18 +309,115 @@ __device__ __forceinline__ ObsTail neighbours(const Consts& c, const WarpScratch
   }
   const bool have1 = (k1 != 0) & (s1 < c.s_dsense_lt);  // uav_agent.py:52 strict <
   const bool have2 = have1 & (k2 != 0) & (s2 < c.s_dsense_lt);
-  const float2 b = fast_atan2_pair(dy1, dx1, dy2, dx2);
-  const float2 nth = make_float2(-th_u, -th_u);
-  const float2 v1 = wrap_units2(__ffma2_rn(b, make_float2(c.inv_pi, c.inv_pi), nth));  // bearings relative to the heading
-  const float2 v2 = wrap_units2(__fadd2_rn(make_float2(h1, h2), nth));                 // neighbour headings, relative
-  ObsTail o;
-  o.a.x = have1 ? sqrt_approx(s1) * c.inv_dsense : 1.0f;  // :77
-  o.a.y = have1 ? v1.x : 1.0f;                            // :78-81 (no neighbour: bearing pi)
-  o.b.x = have1 ? v2.x : 0.0f;                            // :82-85
-  o.b.y = have2 ? sqrt_approx(s2) * c.inv_dsense : 1.0f;  // :87
-  o.c.x = have2 ? v1.y : 1.0f;                            // :88-91
-  o.c.y = have2 ? v2.y : 0.0f;                            // :92-95
-  return o;
+  return obs_tail(c, dx1, dy1, dx2, dy2, s1, s2, h1, h2, have1, have2, th_u);
+}
+
+// ---- small envs: one sweep for both pairwise passes ----------------------------------------------------------------------
+// Each env owns a DOUBLED ring of 2N slots: slot m < N holds UAV m's (old position, new position), slot N+m holds (new,
+// new).  Lane i reads slot i+k for k = 1..N-1, i.e. its ring neighbour j = (i+k) mod N, and receives as "a" exactly the
+// position the reference's sequential sweep would see — OLD for j > i (not moved yet), NEW for j < i — and as "n" the NEW
+// position, with no index arithmetic, no compare and no select.  A slot is laid out (a.x, n.x, a.y, n.y) so that both
+// squared distances come out of five packed FP32 instructions (2 FADD2, 2 FFMA2 with a +0 addend, FADD2).
+__device__ __forceinline__ void publish_mixed(const WarpScratch& ws, const Lane& L, float nx, float ny, float ox, float oy, float th_u) {
+  if (L.valid) {
+    const int slot = 2 * L.base + L.i;
+    ws.ring()[slot] = make_float4(ox, nx, oy, ny);
+    ws.ring()[slot + L.N] = make_float4(nx, nx, ny, ny);
+    ws.ring_th()[slot] = th_u;
+    ws.ring_th()[slot + L.N] = th_u;
+  }
+  __syncwarp();
+}
+
+static __device__ __noinline__ int nearest2_exact_ring(const float4* row, float px, float py, int N) {
+  const float inf = __int_as_float(kInfBits);
+  float s1 = inf, s2 = inf;
+  int j1 = 0, j2 = 0;
+  for (int k = 1; k < N; ++k) {
+    const float4 q = row[k];
+    const float s = sq32(__fsub_rn(q.y, px), __fsub_rn(q.w, py));
+    const bool p1 = s < s1, p2 = s < s2;
+    j2 = p1 ? j1 : (p2 ? k : j2);
+    s2 = p1 ? s1 : (p2 ? s : s2);
+    j1 = p1 ? k : j1;
+    s1 = p1 ? s : s1;
+  }
+  return j1 | (j2 << 8);
+}
+
+// pass A (multi_uav_world_2d.py:198-210) -> smin; pass B (:75 via _get_obs) -> the ring offsets k1, k2 of the two nearest
+template <int NT>
+__device__ __forceinline__ void pair_scan_mixed(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
+                                                float& smin, int& k1, int& k2) {
+  constexpr int N = NT;
+  const float4* row = ws.ring() + 2 * L.base + L.i;
+  const float2 npx = make_float2(-px, -px), npy = make_float2(-py, -py), zero = make_float2(0.f, 0.f);
+  auto dist2 = [&](int k) {  // (pass-A distance, pass-B distance) of ring neighbour k, each exactly sq32()
+    const float4 q = row[k];
+    const float2 dx = __fadd2_rn(make_float2(q.x, q.y), npx), dy = __fadd2_rn(make_float2(q.z, q.w), npy);
+    return __fadd2_rn(__ffma2_rn(dx, dx, zero), __ffma2_rn(dy, dy, zero));
+  };
+  const int mask = c.key_mask;
+  auto key = [mask](float sq, int k) { return (__float_as_int(sq) & mask) | k; };
+  smin = __int_as_float(kInfBits);
+  int t1 = kInfBits, t2 = kInfBits + 32, t3 = kInfBits + 64;
+  int k = 1;
+#pragma unroll
+  for (; k + 1 < N; k += 2) {
+    const float2 s0 = dist2(k), s1 = dist2(k + 1);
+    smin = fminf(smin, fminf(s0.x, s1.x));
+    const int ka = key(s0.y, k), kb = key(s1.y, k + 1);
+    const int a = min(ka, kb), b = max(ka, kb);
+    const int m1a = max(t1, a), m2a = max(t2, a), m1b = max(t1, b);
+    t3 = __vimin3_s32(t3, m2a, m1b);
+    t2 = __vimin3_s32(t2, m1a, b);
+    t1 = min(t1, a);
+  }
+  if (k < N) {
+    const float2 s0 = dist2(k);
+    smin = fminf(smin, s0.x);
+    const int a = key(s0.y, k);
+    t3 = min(t3, max(t2, a));
+    t2 = min(t2, max(t1, a));
+    t1 = min(t1, a);
+  }
+  k1 = t1 & 31;
+  k2 = t2 & 31;
+  if (((unsigned)(t1 ^ t2) < 32u) | ((unsigned)(t2 ^ t3) < 32u)) {
+    const int e = nearest2_exact_ring(row, px, py, N);
+    k1 = e & 0xff;
+    k2 = e >> 8;
+  }
+}
+
+__device__ __forceinline__ ObsTail neighbours_mixed(const Consts& c, const WarpScratch& ws, const Lane& L, float px, float py,
+                                                    float th_u, int k1, int k2) {
+  const int slot = 2 * L.base + L.i;
+  const float4 q1 = ws.ring()[slot + k1], q2 = ws.ring()[slot + k2];
+  const float h1 = ws.ring_th()[slot + k1], h2 = ws.ring_th()[slot + k2];
+  const float dx1 = __fsub_rn(q1.y, px), dy1 = __fsub_rn(q1.w, py), dx2 = __fsub_rn(q2.y, px), dy2 = __fsub_rn(q2.w, py);
+  const float s1 = sq32(dx1, dy1), s2 = sq32(dx2, dy2);
+  const bool have1 = (k1 != 0) & (s1 < c.s_dsense_lt);
+  const bool have2 = have1 & (k2 != 0) & (s2 < c.s_dsense_lt);
+  return obs_tail(c, dx1, dy1, dx2, dy2, s1, s2, h1, h2, have1, have2, th_u);
+}
+
+// Both pairwise passes of a step (or just the observation pass of a state at rest: old == new) for this lane's UAV:
+// publish, sweep, look the two nearest up.  All lanes must call.  smin: squared distance to the nearest other UAV as the
+// reference's sequential sweep sees it.
+template <int NT>
+__device__ __forceinline__ ObsTail scan_neighbours(const Consts& c, const WarpScratch& ws, const Lane& L, float nx, float ny,
+                                                   float ox, float oy, float th_u, float& smin) {
+  int k1, k2;
+  if (SweepKind<NT>::kMixed) {
+    publish_mixed(ws, L, nx, ny, ox, oy, th_u);
+    pair_scan_mixed<NT>(c, ws, L, nx, ny, smin, k1, k2);
+    return neighbours_mixed(c, ws, L, nx, ny, th_u, k1, k2);
+  }
+  int t3;
+  publish(ws, L, nx, ny, ox, oy, th_u);
+  pair_scan<NT>(c, ws, L, nx, ny, k1, k2, t3);
+  return neighbours<NT, true>(c, ws, L, nx, ny, th_u, k1, k2, t3, smin);
 }
 
 // Everything the step and the observation need from a UAV's own state.
@@ -344,13 +470,10 @@ template <int NT>
 __device__ __forceinline__ ObsRow observe_state(const Consts& c, const WarpScratch& ws, const Lane& L, const Uav& u) {
   const Own w = own_features(c, u.px, u.py, u.tx, u.ty, u.vx, u.vy);
   __syncwarp();
-  publish(ws, L, u.px, u.py, u.px, u.py, w.th_u);
-  int k1, k2, t3;
-  pair_scan<NT>(c, ws, L, u.px, u.py, k1, k2, t3);
   ObsRow r;
   obs_own(c, w, w.vsq, r.o01, r.o23);
   float unused;
-  r.n = neighbours<NT, false>(c, ws, L, u.px, u.py, w.th_u, k1, k2, t3, unused);
+  r.n = scan_neighbours<NT>(c, ws, L, u.px, u.py, u.px, u.py, w.th_u, unused);
   return r;
 }
 
@@ -365,8 +488,12 @@ __device__ __forceinline__ void stage_neighbours(float* stage, int lane, const O
   row[2] = n.a; row[3] = n.b; row[4] = n.c;
 }
 // all lanes; the caller has __syncwarp()ed after the last stage_* call
+__device__ __forceinline__ void flush_warp_rows(const float* stage, float* g, const Lane& L);
 __device__ __forceinline__ void flush_rows(const float* stage, float* gobs, const Lane& L) {
-  float* g = gobs + (size_t)L.warp_m0 * 10;
+  flush_warp_rows(stage, gobs + (size_t)L.warp_m0 * 10, L);
+}
+// g: where the first row of this warp goes
+__device__ __forceinline__ void flush_warp_rows(const float* stage, float* g, const Lane& L) {
   const int n2 = L.valid_lanes * 5;  // float2 elements to write
   if ((L.lanes_used & 1) == 0) {     // every warp's run starts on a 16-byte boundary
     const int n4 = n2 >> 1;          // <= 80
@@ -542,7 +669,6 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
   const Own w = own_features(c, u.px, u.py, u.tx, u.ty, u.vx, u.vy);
   const float dist = parked ? 0.f : w.dist;
   const float prev_d = parked ? 0.f : u.prev;
-  publish(ws, L, u.px, u.py, ox, oy, w.th_u);
 
   // ---- reward shaping (:188-195).  Output only: float32 arithmetic, well inside the 1e-5 tolerance.
   float r;
@@ -558,9 +684,7 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
   // ---- both pairwise passes: one sweep at the NEW positions for the two nearest (observation), from which the
   // collision distance of the sequential pass follows (neighbours())
   float smin;
-  int k1, k2, t3;
-  pair_scan<NT>(c, ws, L, u.px, u.py, k1, k2, t3);
-  const ObsTail tail = neighbours<NT, true>(c, ws, L, u.px, u.py, w.th_u, k1, k2, t3, smin);
+  const ObsTail tail = scan_neighbours<NT>(c, ws, L, u.px, u.py, ox, oy, w.th_u, smin);
 
   // ---- collisions (:199-210), decided in squared-distance space (the thresholds already include "in sensing range")
   const bool collision = smin <= c.s_coll_le;

@@ -14,15 +14,18 @@
 //     tcgen05.mma  D1[128x256] (TMEM cols 0..255)   = A1 . [W1 | b1]^T                 1 MMA  (M=128, N=256, K=16)
 //     tcgen05.ld D1 -> relu -> fp16 -> A2 [128x256] in smem, written straight into the 128B-swizzled K-major
 //                                                                         layout the MMA descriptor expects
-//     tcgen05.mma  D2[128x256] (TMEM cols 256..511) = A2 . W2^T + ONES . [b2]^T         16 + 1 MMAs
-//     tcgen05.ld D2 -> relu -> fp16 -> A2 (reused)
-//     tcgen05.mma  D3[128x16]  (TMEM cols 256..271) = A2 . W3^T + ONES . [b3]^T         16 + 1 MMAs (N=16: 4 heads + padding)
-//                  ... followed at once by layer 1 of the CTA's NEXT tile, so that its result is waiting in D1
-//     tcgen05.ld D3 -> mean, log_std; eps ~ N(0,1) from Philox4x32-10 + Box-Muller (or caller-supplied)
+//     tcgen05.mma  D2[128x256] (TMEM cols 256..511) = A2 . W2^T                          16 MMAs
+//     tcgen05.ld D2 -> + b2 -> relu -> the four output heads on the CUDA cores: every thread folds its 64 hidden units
+//                   into 4 partial dot products with W3 (packed FP32 FMAs, W3 / b2 broadcast from shared memory), the
+//                   four column groups of a row meet in shared memory.  (Round 1 ran the heads as 17 more MMAs of N=16,
+//                   which cost as much tensor-pipe time as the 256-wide layer 2, plus a second fp16 round trip of the
+//                   activations through shared memory: 2,800 of 6,900 cycles per tile.)
+//                  ... layer 1 of the CTA's NEXT tile is issued meanwhile, so that its result is waiting in D1
+//     mean, log_std; eps ~ N(0,1) from Philox4x32-10 + Box-Muller (or caller-supplied)
 //                   -> action = tanh(mean + exp(clamp(log_std)) eps)
 //
-// W2 (fp16, 128 KB) stays resident in shared memory for the CTA's lifetime.  Operands (weights, biases, activations)
-// are fp16 with fp32 accumulation (11 significand bits, like TF32): the policy is the learner's side of the
+// W2 (fp16, 128 KB) stays resident in shared memory for the CTA's lifetime.  The tensor-core operands (W1 | b1, W2,
+// activations) are fp16 with fp32 accumulation (11 significand bits, like TF32); b2, W3 and b3 act in fp32: the policy is the learner's side of the
 // boundary, not part of the env-step parity contract; tests compare against the fp32 PyTorch policy at 2e-2
 // absolute on (mean, log_std) — measured 3e-4.
 #include <cuda_fp16.h>
@@ -42,24 +45,22 @@ constexpr int kObs = 10;
 constexpr uint32_t kTmemCols = 512;
 
 // shared-memory carve-up (bytes; the swizzled operands need 1024-byte alignment)
-constexpr int kOut = 16;                              // output heads padded to the smallest MMA N
 constexpr int kW2Bytes = kHidden * kHidden * 2;       // 131072: 4 K-blocks x [256 rows x 128 B], 128B swizzle
 constexpr int kA2Bytes = kRows * kHidden * 2;         //  65536: 4 K-blocks x [128 rows x 128 B], 128B swizzle
-constexpr int kW3Bytes = kOut * kHidden * 2;          //   8192: 4 K-blocks x [ 16 rows x 128 B], 128B swizzle
 constexpr int kW1Bytes = kHidden * kInPad * 2;        //   8192: K = 16, no swizzle, 8x16B core matrices ([W1 | b1])
-constexpr int kW2bBytes = kHidden * kInPad * 2;       //   8192: K = 16, column 0 = b2
 constexpr int kA1Bytes = kRows * kInPad * 2;          //   4096
-constexpr int kOnesBytes = kRows * kInPad * 2;        //   4096: column 0 = 1.0 (written once)
-constexpr int kW3bBytes = kOut * kInPad * 2;          //    512: column 0 = b3
+constexpr int kW3fBytes = kHidden * 16;               //   4096: float4 per hidden unit = its weight in the four heads
+constexpr int kB2fBytes = kHidden * 4;                //   1024: linear2.bias in fp32
+constexpr int kPartBytes = 3 * kRows * 16;            //   6144: head partials of column groups 1..3 (float4 per row)
 constexpr int kOffW2 = 0;
 constexpr int kOffA2 = kOffW2 + kW2Bytes;
-constexpr int kOffW3 = kOffA2 + kA2Bytes;
-constexpr int kOffW1 = kOffW3 + kW3Bytes;
-constexpr int kOffW2b = kOffW1 + kW1Bytes;
-constexpr int kOffA1 = kOffW2b + kW2bBytes;
-constexpr int kOffOnes = kOffA1 + kA1Bytes;
-constexpr int kOffW3b = kOffOnes + kOnesBytes;
-constexpr int kOffBar = kOffW3b + kW3bBytes;          // mbarrier + tmem base
+constexpr int kOffW1 = kOffA2 + kA2Bytes;
+constexpr int kOffA1 = kOffW1 + kW1Bytes;
+constexpr int kOffW3f = kOffA1 + kA1Bytes;
+constexpr int kOffB2f = kOffW3f + kW3fBytes;
+constexpr int kOffPart = kOffB2f + kB2fBytes;
+constexpr int kOffB3 = kOffPart + kPartBytes;         // float4: the four head biases
+constexpr int kOffBar = kOffB3 + 16;                  // mbarriers + tmem base
 constexpr int kSmemBytes = kOffBar + 64;
 constexpr int kSmemAlloc = kSmemBytes + 1024;         // slack to align the dynamic buffer to 1024 B
 static_assert(kSmemAlloc <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
@@ -162,7 +163,8 @@ struct Args {
 
 __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_constant__ Args a) {
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // aligned to 1024 B by pointer arithmetic on the __shared__ array (keeps the address space: LDS / STS, not generic LD / ST)
+  unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int q = warp & 3;          // TMEM lane quarter this warp may access
   const int g = warp >> 2;         // column group
@@ -189,21 +191,18 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_co
       const int n = idx >> 5, c = idx & 31;
       cp_async16(sbase + kOffW2 + sw128_chunk(n, c, kHidden * 128), w2g + idx);
     }
-    {  // 16 rows x 32 chunks: exactly one chunk per thread
-      const int n = t >> 5, c = t & 31;
-      cp_async16(sbase + kOffW3 + sw128_chunk(n, c, kOut * 128), reinterpret_cast<const uint4*>(a.w3) + t);
-    }
-    {  // [256][16] operands: 512 chunks each
-      cp_async16(sbase + kOffW1 + k16_chunk(t >> 1, t & 1), reinterpret_cast<const uint4*>(a.w1) + t);
-      cp_async16(sbase + kOffW2b + k16_chunk(t >> 1, t & 1), reinterpret_cast<const uint4*>(a.w2b) + t);
-    }
-    if (t < kOut * 2) cp_async16(sbase + kOffW3b + k16_chunk(t >> 1, t & 1), reinterpret_cast<const uint4*>(a.w3b) + t);
+    // [256][16] operand [W1 | b1]: 512 chunks, one per thread
+    cp_async16(sbase + kOffW1 + k16_chunk(t >> 1, t & 1), reinterpret_cast<const uint4*>(a.w1) + t);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    if (t < kRows) {  // the constant operand that carries the biases: 1.0 in column 0
-      __half2 one[4] = {__floats2half2_rn(1.f, 0.f), __floats2half2_rn(0.f, 0.f), __floats2half2_rn(0.f, 0.f), __floats2half2_rn(0.f, 0.f)};
-      *reinterpret_cast<uint4*>(sm + kOffOnes + k16_chunk(t, 0)) = *reinterpret_cast<const uint4*>(one);
-      *reinterpret_cast<uint4*>(sm + kOffOnes + k16_chunk(t, 1)) = make_uint4(0u, 0u, 0u, 0u);
+    if (t < kHidden) {  // fp32 tables of the CUDA-core head layer: W3 transposed to one float4 per hidden unit, b2
+      const __half* w3 = a.w3;
+      reinterpret_cast<float4*>(sm + kOffW3f)[t] = make_float4(__half2float(w3[t]), __half2float(w3[kHidden + t]),
+                                                               __half2float(w3[2 * kHidden + t]), __half2float(w3[3 * kHidden + t]));
+      reinterpret_cast<float*>(sm + kOffB2f)[t] = __half2float(a.w2b[t * kInPad]);
     }
+    if (t == 0)
+      *reinterpret_cast<float4*>(sm + kOffB3) = make_float4(__half2float(a.w3b[0]), __half2float(a.w3b[kInPad]),
+                                                            __half2float(a.w3b[2 * kInPad]), __half2float(a.w3b[3 * kInPad]));
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   fence_async_smem();
@@ -215,7 +214,6 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_co
   const uint32_t lane_addr = lane_base + (uint32_t)(g * 64);        // first of its 64 hidden columns
   uint32_t phase = 0;
   const unsigned long long ctr = a.ctr + (a.ctr_dev ? *a.ctr_dev : 0ull);
-  const uint64_t d_ones = smem_desc(sbase + kOffOnes, 128, 256, 0);
 
   const long long tiles = (a.M + kRows - 1) / kRows;
   // column group 0 owns the row's observation (zeros past the end), fetched one tile ahead
@@ -244,20 +242,41 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_co
       }
     }
   };
-  // D[tmem_d] = A2 . B^T (K = 256 in 16 steps; B is a 128B-swizzled K-major operand with `b_block` bytes per K-block)
-  //           + ONES . Bb^T (the bias step)
-  auto issue_layer = [&](uint32_t tmem_d, int off_b, int b_block, int off_bias, uint32_t id) {
+  // D2 = A2 . W2^T (K = 256 in 16 steps of the 128B-swizzled K-major operands)
+  auto issue_layer2 = [&]() {
 #pragma unroll
     for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {  // K = 16 halves = 32 bytes per step inside the 128-byte swizzle atom
         const uint64_t da = smem_desc(sbase + kOffA2 + kb * (kRows * 128) + ks * 32, 16, 1024, 2);
-        const uint64_t db = smem_desc(sbase + off_b + kb * b_block + ks * 32, 16, 1024, 2);
-        mma_f16(tmem_d, da, db, (uint32_t)((kb | ks) != 0), id);
+        const uint64_t db = smem_desc(sbase + kOffW2 + kb * (kHidden * 128) + ks * 32, 16, 1024, 2);
+        mma_f16(tmem + 256u, da, db, (uint32_t)((kb | ks) != 0), idesc(kHidden));
       }
     }
-    mma_f16(tmem_d, d_ones, smem_desc(sbase + off_bias, 128, 256, 0), 1u, id);
     mma_commit(bar);
+  };
+  // The output heads of this thread's 64 hidden units: h = relu(D2 + b2), partial dot products with W3 in packed FP32
+  // (two heads per FFMA2, W3 / b2 read as warp-wide broadcasts).  Returns (mean0, mean1, log_std0, log_std1) partials.
+  auto head_partials = [&]() {
+    float2 acc01 = make_float2(0.f, 0.f), acc23 = make_float2(0.f, 0.f);
+    const float4* w3f = reinterpret_cast<const float4*>(sm + kOffW3f) + g * 64;
+    const float2* b2f = reinterpret_cast<const float2*>(sm + kOffB2f) + g * 32;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32(lane_addr + 256u + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float2 hb = __fadd2_rn(make_float2(v[2 * k], v[2 * k + 1]), b2f[c * 16 + k]);
+        const float h0 = fmaxf(hb.x, 0.f), h1 = fmaxf(hb.y, 0.f);
+        const float4 wa = w3f[c * 32 + 2 * k], wb = w3f[c * 32 + 2 * k + 1];
+        acc01 = __ffma2_rn(make_float2(h0, h0), make_float2(wa.x, wa.y), acc01);
+        acc23 = __ffma2_rn(make_float2(h0, h0), make_float2(wa.z, wa.w), acc23);
+        acc01 = __ffma2_rn(make_float2(h1, h1), make_float2(wb.x, wb.y), acc01);
+        acc23 = __ffma2_rn(make_float2(h1, h1), make_float2(wb.z, wb.w), acc23);
+      }
+    }
+    return make_float4(acc01.x, acc01.y, acc23.x, acc23.y);
   };
 
   // this thread's share of the layer-1 operand of a tile: the observation row as 16 halves (10 features, 1.0 for
@@ -319,34 +338,33 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_co
     POL_TICK(2)
     if (t == 0) {
       fence_after();
-      issue_layer(tmem + 256u, kOffW2, kHidden * 128, kOffW2b, idesc(kHidden));
+      issue_layer2();
     }
     bar_wait(bar, phase);
     phase ^= 1u;
     fence_after();
     POL_TICK(3)
 
-    // ---- layer 2 epilogue -> A2 (its MMAs are complete, the buffer is free), and the next tile's layer-1 operand
-    relu_to_a2(lane_addr + 256u);
+    // ---- layer 2 epilogue = the output heads, on the CUDA cores; the next tile's layer-1 operand
+    const float4 part = head_partials();
+    if (g != 0) reinterpret_cast<float4*>(sm + kOffPart)[(g - 1) * kRows + r] = part;
     write_a1(o_next);
     load_row(tile + 2 * (long long)gridDim.x, o_next);  // two tiles ahead: in flight for a whole iteration
     fence_async_smem();
     fence_before();
     __syncthreads();
-    if (t == 0) {
+    if (t == 0 && has_next) {  // D1 is free (its epilogue ran at the top of this iteration): layer 1 of the next tile
       fence_after();
-      // output heads into the (now free) first columns of the D2 region, then layer 1 of the next tile into D1
-      issue_layer(tmem + 256u, kOffW3, kOut * 128, kOffW3b, idesc(kOut));
-      if (has_next) issue_layer1();
+      issue_layer1();
     }
-    bar_wait(bar, phase);
-    phase ^= 1u;
-    fence_after();
     POL_TICK(4)
 
     // ---- sample and squash (one thread per row: the column-group-0 warps)
     if (g == 0) {
-      const float4 hd = tmem_ld4(lane_base + 256u);
+      const float4* pp = reinterpret_cast<const float4*>(sm + kOffPart) + r;
+      const float4 p1 = pp[0], p2 = pp[kRows], p3 = pp[2 * kRows], b3 = *reinterpret_cast<const float4*>(sm + kOffB3);
+      const float4 hd = make_float4(part.x + p1.x + p2.x + p3.x + b3.x, part.y + p1.y + p2.y + p3.y + b3.y,
+                                    part.z + p1.z + p2.z + p3.z + b3.z, part.w + p1.w + p2.w + p3.w + b3.w);
       if (live) {
         const float m0 = hd.x, m1 = hd.y;
         const float l0 = fminf(fmaxf(hd.z, -20.f), 2.f);  // LOG_SIG_MIN / LOG_SIG_MAX (model.py:6-7,79)
@@ -369,8 +387,8 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_co
         if (a.head) reinterpret_cast<float4*>(a.head)[row] = make_float4(m0, m1, l0, l1);
       }
     }
-    // the next iteration's first __syncthreads (after its layer-1 epilogue) orders these TMEM reads before the next
-    // layer-2 MMAs overwrite the D2 region
+    // the next iteration's first __syncthreads (after its layer-1 epilogue) orders this iteration's TMEM reads of D2 and
+    // shared-memory reads of the partials before the next layer-2 MMAs / partial writes
     fence_before();
   }
 

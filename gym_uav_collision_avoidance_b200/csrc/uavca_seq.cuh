@@ -112,10 +112,9 @@ __device__ __forceinline__ void seq_reset_env(const KernelArgs& a, int b, unsign
   const size_t m0 = (size_t)b * N;
   const long long env_global = c.env_base + b;
   if (sizeof(P) == 8) {
-    const double pi = 3.141592653589793;
     for (int i = 0; i < N; ++i) {
-      const double th = 2 * i * pi / N;
-      const double px = 20.0 * cos(th), py = 20.0 * sin(th), tx = 23.0 * cos(th + pi), ty = 23.0 * sin(th + pi);
+      const double4 rg = a.ring64[i];  // host-computed: the reference's math.cos / math.sin are glibc's
+      const double px = rg.x, py = rg.y, tx = rg.z, ty = rg.w;
       const size_t m = m0 + i;
       v.pos[2 * m] = (P)px; v.pos[2 * m + 1] = (P)py; v.tgt[2 * m] = (P)tx; v.tgt[2 * m + 1] = (P)ty;
       const double ini = sqrt(sq64(tx - px, ty - py));

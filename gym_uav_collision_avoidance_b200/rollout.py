@@ -78,6 +78,7 @@ class FusedGaussianPolicy:
         # device-side call counter: advanced by a one-element kernel after every act(), so a CUDA-graph replay of the
         # acting step draws fresh noise each time
         self.counter = torch.zeros(1, dtype=torch.int64, device=self.w2.device)
+        self.own_counter = True  # False: somebody else advances `counter` once per step (the replay ring's append counter)
 
     @torch.no_grad()
     def refresh(self):
@@ -122,12 +123,15 @@ class FusedGaussianPolicy:
             out = torch.empty((M, 2), dtype=torch.float32, device=state.device)
         ops.policy_act(state, self.w1, self.w2, self.w2b, self.w3, self.w3b, noise, self.seed, self.calls, self.counter,
                        out, head)
-        self.counter += 1
+        if self.own_counter:
+            self.counter += 1
         return out
 
 
 class BatchedRollout:
-    """obs -> policy -> step(action_mode) -> replay, all on the device; optionally replayed from a CUDA graph."""
+    """obs -> policy -> step(action_mode) -> replay, all on the device; optionally replayed from a CUDA graph (capture an
+    EVEN number of steps: the env alternates between two observation buffers, so that the observation an action was taken
+    on survives the step without a copy)."""
 
     def __init__(self, env, policy: Optional[nn.Module] = None, replay: Optional[DeviceReplay] = None,
                  action_mode="polar", evaluate=False, warmup_uniform=False, precision="fp32"):
@@ -141,10 +145,18 @@ class BatchedRollout:
         self.env, self.policy, self.replay = env, policy, replay
         self.action_mode, self.evaluate, self.warmup_uniform = action_mode, evaluate, warmup_uniform
         B, N, D = env.num_envs, env.num_agents, env.obs_dim
-        self.state = torch.zeros((B, N, D), dtype=torch.float32, device=env.device)  # observation the action was taken on
+        # the observation the action was taken on: env.obs of the previous step.  The env ping-pongs between two
+        # observation buffers (`set_obs_buffer`), so nothing is copied.
+        self.state = env.obs
+        self._spare = torch.zeros((B, N, D), dtype=torch.float32, device=env.device)
         self.action = torch.zeros((B, N, 2), dtype=torch.float32, device=env.device)
         if replay is not None:
             env.enable_final_obs()
+            if self.fused is not None:
+                # the ring's append counter advances once per acting step on the device: the policy's Philox noise is
+                # keyed on it, so no separate counter kernel runs (and CUDA-graph replays still draw fresh noise)
+                self.fused.counter = replay.meta[3:4]
+                self.fused.own_counter = False
         self._graph = None
         self.steps = 0
 
@@ -154,7 +166,7 @@ class BatchedRollout:
 
     def _act(self):
         env = self.env
-        self.state.copy_(env.obs)
+        self.state = env.obs  # acted on now, overwritten only by the step after next
         if self.policy is None or self.warmup_uniform:  # test_sac_multi.py:72-73: uniform actions during warm-up
             self.action.uniform_(-1.0, 1.0)
         else:
@@ -178,6 +190,8 @@ class BatchedRollout:
 
     def _env_step(self):
         env = self.env
+        nxt, self._spare = self._spare, env.obs  # the step writes its observation into the other buffer
+        env.set_obs_buffer(nxt)
         if env.num_agents == 1 and env.obs_dim == 4:
             env.step(self.action, action_mode=self.action_mode)
         else:

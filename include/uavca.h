@@ -201,7 +201,8 @@ int uavca_replay_push(const float* obs, const float* action, const float* reward
                       int64_t capacity, int64_t head, void* stream);
 
 /* The same append with the ring head kept ON THE DEVICE: ring_meta int64[4] (device, zero-initialised by the caller)
- * holds [0] the slot the next append starts at, [1] scratch, [2] the number of transitions held (<= capacity).  The
+ * holds [0] the slot the next append starts at, [1] scratch, [2] the number of transitions held (<= capacity), [3] the
+ * number of appends so far (a per-step device counter, e.g. the `counter_dev` of uavca_policy_act).  The
  * call reads the head from ring_meta and advances it itself, so a CUDA-graph replay of an acting step appends where
  * the previous replay stopped. */
 int uavca_replay_push_dev(const float* obs, const float* action, const float* reward, const float* next_obs,
