@@ -580,11 +580,16 @@ def run_ours(args, wl, rank, world, local_rank):
                    "sample": f"{c_envs} envs x {N} UAVs x {c_steps} steps of the same workload, oracle/uav_oracle.c on 1 thread "
                              f"({dt:.1f} s; host: {cpu_model()}, {os.cpu_count()} logical cores)"}
             lit = literal_baseline(kind, N)
-        traffic = None
+        traffic = None  # DRAM bytes per launch of the headline kernel, from the ncu captures under profiles/
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(args.workload + ("_rollout" if headline_rollout else ""))
+                tj = json.load(f)
+            if headline_rollout:  # recorded per UAV-step (a launch's byte count scales with its K)
+                per_unit = tj.get(f"rollout_{kind}_n{N}_bytes_per_unit")
+                traffic = per_unit * units_per_launch if per_unit else None
+            else:
+                traffic = tj.get(args.workload)
         e2e_bytes_s = e2e_value / world * (D * 4 + 4 + 1 + 8)
         line = {
             "metric": "UAV env-steps/sec", "value": value, "unit": "UAV env-steps/s", "n_gpus": world, "steps": K,

@@ -9,6 +9,7 @@
 // streaming accesses; neighbour interaction stays on chip (per-warp shared-memory ring, uavca_multi.cuh).  No tensor
 // cores: there is no dense contraction anywhere in the step.  (The fused policy kernel, which is GEMM-shaped, lives
 // in uavca_policy.cu.)
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 
@@ -568,54 +569,25 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(StateView s, int B, lon
 
 // Replay ring append: every array is a run of whole rows, so the ring write is a flat copy whose destination index
 // wraps at capacity * row.  V = float2 when both row widths are even and the pointers 8-byte aligned, else float.
+constexpr int kPushThreads = 1024;  // big blocks: one head ticket (a same-address atomic) per block
 template <typename V>
-__global__ void __launch_bounds__(kThreads) replay_push_kernel(const V* obs, const V* act, const float* rew, const V* nxt,
+__global__ void __launch_bounds__(kPushThreads) replay_push_kernel(const V* obs, const V* act, const float* rew, const V* nxt,
                                                                const uint8_t* done, long long M, long long od, long long ad,
                                                                V* r_obs, V* r_act, float* r_rew, V* r_nxt, float* r_mask,
                                                                long long cap, long long head, long long* meta) {
-  // meta (nullable, device): [0] ring head, [1] block ticket, [2] transitions held, [3] appends so far.  With it the head lives on the
-  // device, so a CUDA-graph replay of the push appends where the previous replay stopped; the last block to finish
-  // (every block has read the head by then) advances it.
-  if (meta != nullptr) head = meta[0];
-  // grid-stride: the grid is capped at a few CTAs per SM so that the block ticket below stays a few hundred atomics
-  const long long stride = (long long)gridDim.x * kThreads;
-  for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < M * od; j += stride) {
-    long long d = head * od + j;
-    if (d >= cap * od) d -= cap * od;
-    r_obs[d] = ld_stream(obs + j);
-    r_nxt[d] = ld_stream(nxt + j);
-    if (j < M * ad) {
-      long long da = head * ad + j;
-      if (da >= cap * ad) da -= cap * ad;
-      r_act[da] = ld_stream(act + j);
-    }
-    if (j < M) {
-      long long d1 = head + j;
-      if (d1 >= cap) d1 -= cap;
-      r_rew[d1] = ld_stream(rew + j);
-      r_mask[d1] = done[j] ? 0.0f : 1.0f;
-    }
-  }
-  if (ad > od)  // an action wider than an observation (never the case for the reference's worlds): its tail
-    for (long long j = M * od + (long long)blockIdx.x * kThreads + threadIdx.x; j < M * ad; j += stride) {
-      long long da = head * ad + j;
-      if (da >= cap * ad) da -= cap * ad;
-      r_act[da] = ld_stream(act + j);
-    }
-  if (od < 1)  // no observation columns: rewards and masks on their own
-    for (long long j = (long long)blockIdx.x * kThreads + threadIdx.x; j < M; j += stride) {
-      long long d1 = head + j;
-      if (d1 >= cap) d1 -= cap;
-      r_rew[d1] = ld_stream(rew + j);
-      r_mask[d1] = done[j] ? 0.0f : 1.0f;
-    }
+  // meta (nullable, device): [0] ring head, [1] block ticket, [2] transitions held, [3] appends so far.  With it the head
+  // lives on the device, so a CUDA-graph replay of the push appends where the previous replay stopped.  Every thread
+  // reads the head (an ordinary load: L1 serves all but the first warp of an SM — a volatile load from 25,000 warps made
+  // the one L2 sector a hot spot, 28 us); once all threads of a block HOLD it (the barrier's predicate depends on the
+  // loaded value) the block takes a ticket, and the last ticket holder — every block has read the head by then —
+  // advances it.  Nothing waits for the data stores (the kernel boundary orders them for the consumers).
   if (meta != nullptr) {
-    __syncthreads();
+    asm volatile("ld.global.ca.s64 %0, [%1];" : "=l"(head) : "l"(meta) : "memory");  // exactly one load, L1-cacheable
+    if (__syncthreads_or(head < 0)) return;  // never taken
     if (threadIdx.x == 0) {
-      __threadfence();
       const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(meta + 1), 1ull);
       if (t == (unsigned long long)gridDim.x - 1ull) {
-        long long nh = head + M;
+        const long long nh = head + M;
         meta[0] = nh >= cap ? nh - cap : nh;
         const long long held = meta[2] + M;
         meta[2] = held > cap ? cap : held;
@@ -623,6 +595,24 @@ __global__ void __launch_bounds__(kThreads) replay_push_kernel(const V* obs, con
         meta[1] = 0;
       }
     }
+  }
+  const long long j = (long long)blockIdx.x * kPushThreads + threadIdx.x;
+  if (j < M * od) {
+    long long d = head * od + j;
+    if (d >= cap * od) d -= cap * od;
+    r_obs[d] = ld_stream(obs + j);
+    r_nxt[d] = ld_stream(nxt + j);
+  }
+  if (j < M * ad) {
+    long long d = head * ad + j;
+    if (d >= cap * ad) d -= cap * ad;
+    r_act[d] = ld_stream(act + j);
+  }
+  if (j < M) {
+    long long d = head + j;
+    if (d >= cap) d -= cap;
+    r_rew[d] = ld_stream(rew + j);
+    r_mask[d] = done[j] ? 0.0f : 1.0f;
   }
 }
 
@@ -689,7 +679,7 @@ template <int NT, bool FINAL>
 static cudaError_t launch_step_tma_n(const KernelArgs& a, int num_tiles, cudaStream_t st) {
   using G = TmaGeom<NT, FINAL>;
   constexpr int kMaxDev = 64;
-  static int slots[kMaxDev] = {0};  // resident CTAs per device for this instantiation (0 = not configured yet)
+  static std::atomic<int> slots[kMaxDev];  // resident CTAs per device for this instantiation (0 = not configured yet)
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -706,7 +696,8 @@ static cudaError_t launch_step_tma_n(const KernelArgs& a, int num_tiles, cudaStr
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     slots[dev] = per_sm * sms;
   }
-  const int grid = num_tiles < slots[dev] ? num_tiles : slots[dev];
+  const int n_slots = slots[dev];
+  const int grid = num_tiles < n_slots ? num_tiles : n_slots;
   return launch_pdl(kernel, grid, G::THREADS, G::SMEM_BYTES, st, a, num_tiles);
 }
 
@@ -742,7 +733,7 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 template <int NT>
 static cudaError_t launch_step_pf_n(const KernelArgs& a, int num_tiles, cudaStream_t st) {
   constexpr int kMaxDev = 64;
-  static int slots[kMaxDev] = {0};
+  static std::atomic<int> slots[kMaxDev];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -759,7 +750,8 @@ static cudaError_t launch_step_pf_n(const KernelArgs& a, int num_tiles, cudaStre
     slots[dev] = per_sm * sms;
   }
   const int ctas = (num_tiles + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  return launch_pdl(kernel, ctas < slots[dev] ? ctas : slots[dev], kThreads, 0, st, a, num_tiles);
+  const int n_slots = slots[dev];
+  return launch_pdl(kernel, ctas < n_slots ? ctas : n_slots, kThreads, 0, st, a, num_tiles);
 }
 
 
@@ -929,11 +921,6 @@ cudaError_t launch_map_action(const Consts& c, const float* in, float* out, long
   return cudaGetLastError();
 }
 
-static inline int push_grid(long long n) {
-  const int g = flat_grid(n);
-  return g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8;
-}
-
 cudaError_t launch_replay_push(const float* obs, const float* action, const float* reward, const float* next_obs,
                                const uint8_t* done, long long M, int obs_dim, int act_dim, float* r_obs, float* r_act,
                                float* r_rew, float* r_next, float* r_mask, long long capacity, long long head,
@@ -945,13 +932,13 @@ cudaError_t launch_replay_push(const float* obs, const float* action, const floa
   const long long widest = (long long)(obs_dim > act_dim ? obs_dim : act_dim);
   if (wide) {
     const long long n = M * (widest / 2) > M ? M * (widest / 2) : M;
-    replay_push_kernel<float2><<<push_grid(n), kThreads, 0, st>>>(
+    replay_push_kernel<float2><<<(int)((n + kPushThreads - 1) / kPushThreads), kPushThreads, 0, st>>>(
         reinterpret_cast<const float2*>(obs), reinterpret_cast<const float2*>(action), reward,
         reinterpret_cast<const float2*>(next_obs), done, M, obs_dim / 2, act_dim / 2, reinterpret_cast<float2*>(r_obs),
         reinterpret_cast<float2*>(r_act), r_rew, reinterpret_cast<float2*>(r_next), r_mask, capacity, head, meta);
   } else {
     const long long n = M * (widest > 1 ? widest : 1);
-    replay_push_kernel<float><<<push_grid(n), kThreads, 0, st>>>(obs, action, reward, next_obs, done, M, obs_dim, act_dim,
+    replay_push_kernel<float><<<(int)((n + kPushThreads - 1) / kPushThreads), kPushThreads, 0, st>>>(obs, action, reward, next_obs, done, M, obs_dim, act_dim,
                                                                   r_obs, r_act, r_rew, r_next, r_mask, capacity, head, meta);
   }
   return cudaGetLastError();

@@ -30,6 +30,8 @@
 // absolute on (mean, log_std) — measured 3e-4.
 #include <cuda_fp16.h>
 
+#include <atomic>
+
 #include "uavca_host.h"
 
 namespace uavca {
@@ -414,17 +416,17 @@ cudaError_t launch_policy_act(const float* obs, long long M, const void* w1, con
                               const void* w3b, const float* noise, unsigned long long seed, unsigned long long counter,
                               const unsigned long long* counter_dev, float* action, float* head, cudaStream_t st) {
   if (M <= 0) return cudaSuccess;
-  static bool configured[64] = {false};
+  static std::atomic<bool> configured[64];  // per device; setting the attribute twice is harmless, the flag only skips the call
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   int sms = 0;
   e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (e != cudaSuccess) return e;
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
+  if (dev >= 0 && dev < 64 && !configured[dev].load(std::memory_order_acquire)) {
     e = cudaFuncSetAttribute(pol::policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pol::kSmemAlloc);
     if (e != cudaSuccess) return e;
-    configured[dev] = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   pol::Args a{};
   a.obs = obs;
