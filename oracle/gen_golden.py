@@ -34,6 +34,8 @@ MULTI_CASES = [
     dict(name="multi_n8", N=8, E=8, T=400, seed=108, evaluate=0, reset_mode=0, max_steps=0),
     dict(name="multi_n10_eval_reset_all", N=10, E=4, T=300, seed=110, evaluate=1, reset_mode=O.RESET_ON_ALL_DONE, max_steps=0),
     dict(name="multi_n32", N=32, E=2, T=120, seed=132, evaluate=0, reset_mode=0, max_steps=0),
+    # more UAVs than a warp holds: the general one-thread-per-env kernel (num_agents is unbounded in the reference)
+    dict(name="multi_n40_reset_done0", N=40, E=2, T=90, seed=140, evaluate=0, reset_mode=O.RESET_ON_DONE0, max_steps=60),
 ]
 SINGLE_CASES = [
     dict(name="single_f64_actions", E=12, T=400, seed=201, f32=0),
@@ -227,7 +229,18 @@ def main():
     import sys
 
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    only = sys.argv[1] if len(sys.argv) > 1 else None  # e.g. "circular": regenerate just those cases
+    only = sys.argv[1] if len(sys.argv) > 1 else None  # "circular" or a case name: regenerate just those cases
+    if only and only != "circular":
+        for case in MULTI_CASES:
+            if case["name"] == only:
+                res = run_reference_multi(case)
+                path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+                if res["reset_mask"].sum() == 0:
+                    del res["final_obs"]
+                np.savez_compressed(path, **res)
+                print(f"{case['name']}: done-events={int(res['done'].sum())} resets={int(res['reset_mask'].sum())} "
+                      f"reach={int(res['reach'].max())} coll={int(res['coll'].max())} -> {os.path.getsize(path) / 1e6:.2f} MB")
+        return
     if only == "circular":
         for case in CIRCULAR_CASES:
             res = run_reference_circular(case)

@@ -100,3 +100,45 @@ def test_oracle_matches_live_reference(n):
         assert np.array_equal(out["final_obs"], res["final_obs"][t])
         assert np.array_equal(orc.state.pos, res["pos"][t])
         assert np.array_equal(orc.state.vel, res["vel"][t])
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="needs the reference (checkout or oracle/_ref)")
+@pytest.mark.parametrize("trial", range(6))
+def test_oracle_matches_live_reference_with_random_constructor_arguments(trial):
+    """Non-default worlds against the LITERAL reference, live: box, speed / acceleration bounds, collider radius, sensing
+    range and N drawn at random (crowded enough for collisions, goal reaches and parked UAVs); every output and the
+    whole state compared for exact equality at every step.  (HARD_COLLISION_RADIUS is a module constant of the
+    reference, multi_uav_world_2d.py:8, so it stays 0.5.)"""
+    rng = np.random.default_rng(4100 + trial)
+    n = int(rng.choice([2, 3, 6, 9, 12, 17]))
+    kw = dict(x_size=float(rng.uniform(10, 40)), y_size=float(rng.uniform(10, 40)), max_speed=float(rng.uniform(3, 20)),
+              max_acceleration=float(rng.uniform(1, 12)), collider_radius=float(rng.uniform(0.3, 1.5)),
+              d_sense=float(rng.choice([rng.uniform(1.0, 4.0), rng.uniform(6, 40)])))
+    _, MultiUAVWorld2D = R.load_reference()
+    env = MultiUAVWorld2D(num_agents=n, **kw)
+    env.reset()
+    st = O.sample_multi_states(1, n, rng, x_size=kw["x_size"], y_size=kw["y_size"], collider_radius=kw["collider_radius"],
+                               region=min(kw["x_size"], kw["y_size"]) / 3)
+    R.inject_multi(env, st.pos[0], st.vel[0], st.tgt[0], st.init[0], st.prev[0], st.flags[0])
+    orc = O.Oracle(O.multi_config(1, n, **kw))
+    orc.state = st.copy()
+    assert np.array_equal(orc.observe()[0], np.stack([env._get_obs(a) for a in env.agent_list]))
+    evaluate = bool(trial % 2)
+    events = 0
+    for t in range(250):
+        if t % 3:
+            a = np.clip((orc.state.tgt[0] - orc.state.pos[0]) * 1.2 + rng.normal(0, 0.4, (n, 2)), -kw["max_speed"], kw["max_speed"])
+        else:
+            a = rng.uniform(-kw["max_speed"], kw["max_speed"], (n, 2))
+        a = a.astype(np.float32)
+        o, r, d, _ = env.step([a[i].astype(np.float64) for i in range(n)], evaluate=evaluate)
+        out = orc.step(a[None], evaluate=evaluate)
+        assert np.array_equal(out["done"][0], np.array(d, np.uint8)), f"done flags, step {t}"
+        assert np.array_equal(out["reward"][0], np.array(r, np.float64)), f"reward, step {t}"
+        assert np.array_equal(out["obs"][0], np.stack(o)), f"observation, step {t}"
+        pos, vel, tgt, ini, prv, flg = R.extract_multi(env)
+        assert np.array_equal(orc.state.pos[0], pos) and np.array_equal(orc.state.vel[0], vel), f"state, step {t}"
+        assert np.array_equal(orc.state.prev[0], prv) and np.array_equal(orc.state.flags[0], flg), f"latches, step {t}"
+        assert int(orc.state.coll[0]) == env.collision_count and int(orc.state.reach[0]) == env.target_reach_count
+        events += int(np.sum(d)) + int(flg.sum())
+    assert events > 0
