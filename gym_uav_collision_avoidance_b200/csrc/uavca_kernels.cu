@@ -16,6 +16,7 @@
 #include "uavca_host.h"
 #include "uavca_multi.cuh"
 #include "uavca_seq.cuh"
+#include "uavca_cta.cuh"
 #include "uavca_tma.cuh"
 
 namespace uavca {
@@ -765,6 +766,26 @@ cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launche
   if (wants_seq(a)) {
     if (a.c.circular) step_multi_seq_kernel<double><<<flat_grid(a.B), kThreads, 0, st>>>(a);
     else step_multi_seq_kernel<float><<<flat_grid(a.B), kThreads, 0, st>>>(a);
+    if (launched) *launched = 1;
+    return cudaGetLastError();
+  }
+  if (a.N > 16 && kThreads / a.N >= 5 && path != UAVCA_PATH_PLAIN && path != UAVCA_PATH_PREFETCH && path != UAVCA_PATH_AUTO) {
+    // 17..25 UAVs per env: 5..7 envs packed across the 4 warps of a CTA instead of one env per warp (uavca_cta.cuh).
+    // Measured (B*N = 2 Mi UAVs, one stream): N=17 98 vs 136 us, N=20 101 vs 122, N=24 107 vs 113; from N=26 a CTA
+    // holds 4 envs like 4 warps do and the barriers only cost (N=28 119 vs 108 us), so those stay on the warp kernel.
+    const int envs_per_cta = kThreads / a.N;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((a.B + envs_per_cta - 1) / envs_per_cta);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, step_multi_cta_kernel, a);
+    if (e != cudaSuccess) return e;
     if (launched) *launched = 1;
     return cudaGetLastError();
   }

@@ -387,6 +387,36 @@ def test_prefetch_variant_equals_the_plain_kernel_at_scale(monkeypatch):
     assert torch.equal(e1.state.blob, e2.state.blob)
 
 
+@pytest.mark.parametrize("n", [17, 20, 24, 25])
+def test_cta_packed_kernel_and_warp_kernel_agree(monkeypatch, n):
+    """17 <= N <= 25 runs step_multi_cta_kernel (envs packed across the warps of a CTA) by default and the one-env-per-
+    warp kernel under UAVCA_STEP_PATH=plain (which uavca_rollout also uses): both against the oracle, all three reset
+    triggers, and bit for bit against each other (scores included) on a batch with a ragged last CTA."""
+    for mode in (O.RESET_ON_DONE0, O.RESET_ON_ANY_DONE, O.RESET_ON_ALL_DONE):
+        for path in ("lanes", "plain"):
+            monkeypatch.setenv("UAVCA_STEP_PATH", path)
+            cfg = O.multi_config(1031, n, reset_mode=mode, max_episode_steps=30, seed=300 + n + mode)
+            ev, _ = rollout_vs_oracle(cfg, steps=45, seed=n + mode, check_every=3)
+            assert ev["resets"] > 0
+    G = _b200()
+    B = 40003
+    kw = dict(num_agents=n, seed=99, reset_mode=O.RESET_ON_DONE0, max_episode_steps=9, track_scores=True)
+    monkeypatch.setenv("UAVCA_STEP_PATH", "plain")
+    e1 = G.BatchedMultiUAVWorld2D(B, **kw)
+    monkeypatch.setenv("UAVCA_STEP_PATH", "lanes")
+    e2 = G.BatchedMultiUAVWorld2D(B, **kw)
+    e1.reset()
+    e2.reset()
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    for t in range(12):
+        a = torch.rand((B, n, 2), generator=gen, device="cuda") * 20 - 10
+        e1.step(a)
+        e2.step(a)
+        assert torch.equal(e1.obs, e2.obs) and torch.equal(e1.reward, e2.reward) and torch.equal(e1.done, e2.done)
+        assert torch.equal(e1.reset_mask, e2.reset_mask)
+    assert torch.equal(e1.state.blob, e2.state.blob)
+
+
 @pytest.mark.parametrize("f32", [0, 1])
 def test_single_rollout(f32):
     cfg = O.single_config(65536, reset_mode=O.RESET_ON_ANY_DONE, max_episode_steps=500, seed=21 + f32,
