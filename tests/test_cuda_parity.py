@@ -414,7 +414,13 @@ def test_cta_packed_kernel_and_warp_kernel_agree(monkeypatch, n):
         e2.step(a)
         assert torch.equal(e1.obs, e2.obs) and torch.equal(e1.reward, e2.reward) and torch.equal(e1.done, e2.done)
         assert torch.equal(e1.reset_mask, e2.reset_mask)
-    assert torch.equal(e1.state.blob, e2.state.blob)
+    h1, h2 = e1.state.to_host(), e2.state.to_host()
+    for f in e1.state.FIELDS:
+        assert np.array_equal(h1[f], h2[f]), f"state field {f} differs"
+    assert torch.equal(e1.score, e2.score)  # per-env running scores: same summation order in both kernels
+    s1, s2 = e1.stats(), e2.stats()
+    for k in s1:  # the score totals are double atomics over all envs: equal up to the order of the additions
+        assert s1[k] == s2[k] or (k.startswith("score") and abs(s1[k] - s2[k]) <= 1e-9 * abs(s1[k])), k
 
 
 @pytest.mark.parametrize("f32", [0, 1])
