@@ -32,6 +32,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import copy
 import statistics
 import sys
 import threading
@@ -807,13 +808,18 @@ def measure_acting(args, G, torch, dev, rank, world, dist, barrier, B, N, K):
     rows = {}
     stream = torch.cuda.Stream(device=dev)
     total_launches = 0
-    for precision in ("fp32", "tf32", "fused"):
+    for row in ("fp32", "tf32", "fused", "fused_separate_append"):
+        precision = "fused" if row.startswith("fused") else row
         env = G.BatchedMultiUAVWorld2D(B, num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=1500, seed=0x5EED,
                                        env_index_base=rank * B, device=dev)
         policy = G.GaussianPolicy(10, 2).to(dev)
         replay = G.DeviceReplay(min(B * N * 16, 4_000_000), 10, 2, device=dev)
-        ro = G.BatchedRollout(env, policy, replay, action_mode="polar", precision=precision)
+        # default: the step kernel appends the transitions itself (uavca_step_multi_replay: 2 launches per acting step with
+        # the fused policy); "fused_separate_append" keeps round 2's three launches (policy, step, append) beside it
+        ro = G.BatchedRollout(env, policy, replay, action_mode="polar", precision=precision,
+                              fused_append=row != "fused_separate_append")
         ro.reset()
+        head_err = policy_head_error(G, torch, policy, ro, env) if row in ("tf32", "fused") else None
         with torch.cuda.stream(stream):
             for _ in range(3):
                 ro.step()
@@ -835,12 +841,36 @@ def measure_acting(args, G, torch, dev, rank, world, dist, barrier, B, N, K):
         ts = [sharding.max_over_ranks(t, device=dev) for t in ts] if dist is not None else ts
         med = statistics.median(ts)
         us = med * 1e3 / (q * n_graph)
-        rows[precision] = {"us_per_acting_step": us, "value": world * B * N / us * 1e6, "best_us": min(ts) * 1e3 / (q * n_graph),
-                           "repetitions": len(ts), "steps_per_repetition": q * n_graph, "replay_size": len(replay)}
+        rows[row] = {"us_per_acting_step": us, "value": world * B * N / us * 1e6, "best_us": min(ts) * 1e3 / (q * n_graph),
+                     "repetitions": len(ts), "steps_per_repetition": q * n_graph, "replay_size": len(replay),
+                     "launches_per_acting_step": (2 if ro.fused_append else 3) if precision == "fused" else None}
+        if head_err is not None:
+            rows[row]["head_max_abs_err_vs_fp64"] = head_err
         total_launches += env.launch_count
         del g, ro, replay, env
     torch.backends.cuda.matmul.allow_tf32 = tf32_before
     return rows, total_launches
+
+
+def policy_head_error(G, torch, policy, ro, env):
+    """max |(mean, log_std) - float64 policy| over this env's reset observations: the acting precision of a row.  TF32 and
+    fp16 operands both carry 10 explicit mantissa bits into an fp32 accumulator; this shows the two side by side."""
+    x = env.obs.view(-1, env.obs_dim)[:65536].contiguous()
+    p64 = copy.deepcopy(policy).double()
+    with torch.no_grad():
+        m64, s64 = p64(x.double())
+        if ro.precision == "fused":
+            head = torch.empty((x.shape[0], 4), dtype=torch.float32, device=x.device)
+            ro.fused.act(x, noise=torch.zeros((x.shape[0], 2), dtype=torch.float32, device=x.device), head=head)
+            m, sd = head[:, 0:2], head[:, 2:4]
+        else:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = ro.precision == "tf32"
+            try:
+                m, sd = policy(x)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        return float(torch.maximum((m.double() - m64).abs().max(), (sd.double() - s64).abs().max()))
 
 
 def run_acting(args, wl, G, torch, dev, rank, world, dist, barrier):

@@ -416,6 +416,43 @@ class BatchedMultiUAVWorld2D(_BatchedBase):
         return self.obs, self.reward, self.done, info
 
 
+    def supports_step_replay(self) -> bool:
+        """`step_replay` runs on the warp kernels: up to 32 UAVs per env, float32 world."""
+        return self.num_agents <= 32 and not self.cfg.circular
+
+    def step_replay(self, action: torch.Tensor, prev_obs: torch.Tensor, replay, evaluate: bool = False,
+                    action_mode="cartesian"):
+        """`step(action)` that also appends every UAV's transition (prev_obs, action, reward, next observation before any
+        auto-reset, 1 - done) to `replay` (a `DeviceReplay`) in the SAME launch — env.step followed by the N
+        `memory.push` calls of a training step (test_sac_multi.py:99-103).  `prev_obs` is the observation the action was
+        taken on; it must not be the tensor this step writes (`env.obs`): ping-pong two buffers with `set_obs_buffer`."""
+        action = self._check_action(action)
+        if prev_obs.data_ptr() == self.obs.data_ptr():
+            raise ValueError("prev_obs is the buffer this step writes its observation into (use set_obs_buffer)")
+        if prev_obs.shape != self.obs.shape or prev_obs.dtype != torch.float32 or not prev_obs.is_contiguous():
+            raise ValueError("prev_obs must be a contiguous float32 tensor shaped like env.obs")
+        if replay.obs_dim != self.obs_dim or replay.act_dim != 2 or replay.state.device != self.obs.device:
+            raise ValueError("the replay ring does not match this env (obs_dim / act_dim / device)")
+        if self._direct():
+            sp, op, rp, dp, mp = self._ptrs
+            fp = None if self.final_obs is None else self.final_obs.data_ptr()
+            rc = self._lib.uavca_step_multi_replay(self._h, sp, action.data_ptr(), _ACTION_MODES[action_mode],
+                                                   int(bool(evaluate)), prev_obs.data_ptr(), op, rp, dp, fp, mp,
+                                                   replay.state.data_ptr(), replay.action.data_ptr(), replay.reward.data_ptr(),
+                                                   replay.next_state.data_ptr(), replay.mask.data_ptr(), replay.capacity,
+                                                   replay.meta.data_ptr(), self._stream())
+            if rc:
+                _capi.check(rc, "uavca_step_multi_replay")
+        else:
+            ops.step_multi_replay(self._h, self.state.blob, action, _ACTION_MODES[action_mode], bool(evaluate), prev_obs,
+                                  self.obs, self.reward, self.done, self.final_obs, self.reset_mask, replay.state,
+                                  replay.action, replay.reward, replay.next_state, replay.mask, replay.meta)
+        info = {"distance": 0, "reset_mask": self.reset_mask}
+        if self.final_obs is not None:
+            info["final_obs"] = self.final_obs
+        return self.obs, self.reward, self.done, info
+
+
 class BatchedUAVWorld2D(_BatchedBase):
     """B x UAVWorld2D (uav_world_2d.py:11).  Constructor kwargs follow the reference (:14)."""
 

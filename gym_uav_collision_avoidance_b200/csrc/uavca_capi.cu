@@ -684,6 +684,43 @@ int uavca_replay_push_dev(const float* obs, const float* action, const float* re
                           ring_next_obs, ring_mask, capacity, 0, ring_meta, stream);
 }
 
+int uavca_step_multi_replay(uavca_handle* h, void* state, const float* action, int action_mode, int evaluate,
+                            const float* prev_obs, float* obs, float* reward, uint8_t* done, float* final_obs,
+                            uint8_t* reset_mask, float* ring_obs, float* ring_action, float* ring_reward, float* ring_next_obs,
+                            float* ring_mask, int64_t capacity, int64_t* ring_meta, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (h->cfg.kind != UAVCA_KIND_MULTI) return fail(-1, "uavca_step_multi_replay on a single-UAV handle");
+  if (!state || !action || !prev_obs || !obs || !reward || !done || !ring_obs || !ring_action || !ring_reward ||
+      !ring_next_obs || !ring_mask || !ring_meta)
+    return fail(-1, "null argument");
+  if (prev_obs == obs) return fail(-1, "uavca_step_multi_replay: prev_obs and obs must be different buffers");
+  if (int rc = check_step_alignment(state, action, obs, reward, final_obs)) return rc;
+  if (misaligned(prev_obs, 8) || misaligned(ring_obs, 8) || misaligned(ring_action, 8) || misaligned(ring_next_obs, 8) ||
+      misaligned(ring_meta, 8))
+    return fail(-1, "misaligned buffer: prev_obs and the ring arrays need 8-byte alignment");
+  if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
+  if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
+  if (h->cfg.circular || h->cfg.num_agents > 32)
+    return fail(-2, "uavca_step_multi_replay serves the warp kernels (N <= 32, float32 world): use uavca_step_multi + uavca_replay_push_dev");
+  const int64_t M = (int64_t)h->cfg.num_envs * h->cfg.num_agents;
+  if (capacity < M) return fail(-1, "uavca_step_multi_replay: the ring is smaller than one step's transitions");
+  if (capacity * 10 >= (int64_t)1 << 31) return fail(-2, "uavca_step_multi_replay: ring rows are indexed in 32 bits (capacity * 10 < 2^31)");
+  DeviceGuard g(h->device);
+  KernelArgs a = make_args(h, state);
+  a.io.action = reinterpret_cast<const float2*>(action);
+  a.io.obs = obs; a.io.reward = reward; a.io.done = done; a.io.final_obs = final_obs; a.io.reset_mask = reset_mask;
+  a.io.action_mode = action_mode; a.io.evaluate = evaluate;
+  RingSink r{};
+  r.prev_obs = reinterpret_cast<const float2*>(prev_obs);
+  r.obs = reinterpret_cast<float2*>(ring_obs); r.act = reinterpret_cast<float2*>(ring_action); r.rew = ring_reward;
+  r.nxt = reinterpret_cast<float2*>(ring_next_obs); r.mask = ring_mask;
+  r.meta = reinterpret_cast<long long*>(ring_meta); r.cap = (int)capacity; r.M = (int)M;
+  cudaError_t e = launch_step_multi_ring(a, r, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_step_multi_replay", e);
+  h->launches += 1;
+  return 0;
+}
+
 int uavca_policy_act(const float* obs, int64_t M, const void* w1, const void* w2, const void* w2b, const void* w3,
                      const void* w3b, const float* noise, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
                      float* action, float* head, void* stream) {

@@ -113,6 +113,22 @@ struct RolloutArgs {
   int B;
 };
 
+// Device replay ring fed straight from the step kernel (uavca_step_multi_replay): the step that produced a transition
+// also appends it — (observation acted on, policy-space action, reward, the step's own next observation, 1 - done) as
+// the training loop stores it (test_sac_multi.py:101-103).  Row indices are 32-bit: capacity * 10 < 2^31 is checked on
+// the host.  meta (device int64[4]): ring head, block ticket, transitions held, appends so far (as uavca_replay_push_dev).
+struct RingSink {
+  const float2* prev_obs;  // [M][5]: the observation the action was taken on
+  float2* obs;             // [capacity][5]
+  float2* act;             // [capacity]
+  float* rew;              // [capacity]
+  float2* nxt;             // [capacity][5]
+  float* mask;             // [capacity]
+  long long* meta;
+  int cap;
+  int M;
+};
+
 // ---- exact float32 / float64 primitives ------------------------------------------------------------------
 
 // squared float32 norm the way np.linalg.norm forms it: products and sum rounded separately (never fused)

@@ -11,6 +11,7 @@ namespace uavca {
 // ragged rest; UAVCA_PATH_LANES: per-lane kernel only).  *launched receives the number of kernels launched.
 enum : int { UAVCA_PATH_AUTO = 0, UAVCA_PATH_LANES = 1, UAVCA_PATH_PREFETCH = 2, UAVCA_PATH_PLAIN = 3 };
 cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path);
+cudaError_t launch_step_multi_ring(const KernelArgs& a, const RingSink& g, cudaStream_t st);
 cudaError_t launch_rollout_multi(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st);
 cudaError_t launch_rollout_single(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st);
 cudaError_t launch_sample_actions(const Consts& c, float* out, int B, int N, unsigned long long seed, unsigned long long t,

@@ -96,6 +96,134 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc, int b
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// ---- step + replay append in one launch (uavca_step_multi_replay) ------------------------------------------------
+// I/O policy of step_core that, besides GlobalIO's outputs, appends each UAV's transition to a device replay ring:
+// the launch that computes (reward, next observation, done) is the one that stores them, so the acting step loses a
+// whole pass over the transitions (163,840 x 96 bytes read again and written again) and a launch.  The ring slot of
+// UAV m is (head + m) mod capacity with the head read once per thread from ring_meta; the last CTA to finish advances
+// it (every CTA read the head before it took its ticket), so a CUDA-graph replay appends where the previous one stopped.
+struct RingIO {
+  const KernelArgs& a;
+  const RingSink& g;
+  const Lane& L;
+  float* stage;
+  float2* prev_stage;  // per warp [160]: the rows of prev_obs, in flight (cp.async) while the step is computed
+  int head;
+  __device__ __forceinline__ void fetch_prev() const {
+    const int n2 = L.valid_lanes * 5;
+    const float2* p2 = g.prev_obs + (size_t)L.warp_m0 * 5;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int k = L.lane + 32 * r;
+      if (k < n2) cp_async(prev_stage + k, p2 + k, 8);
+    }
+  }
+  __device__ __forceinline__ int slot() const {
+    const int s = head + L.m;
+    return s >= g.cap ? s - g.cap : s;
+  }
+  __device__ __forceinline__ Uav load_uav() const {
+    fetch_prev();
+    return uavca::load_uav(a.s, L);
+  }
+  __device__ __forceinline__ float2 load_action() const {
+    if (!L.valid) return make_float2(0.f, 0.f);
+    const float2 act = ld_stream(a.io.action + L.m);
+    st_stream(g.act + slot(), act);  // the policy-space action, before the action mapping (what memory.push receives)
+    return act;
+  }
+  __device__ __forceinline__ int load_steps() const { return L.valid ? a.s.steps[L.env] : 0; }
+  __device__ __forceinline__ void loads_done() const { cudaTriggerProgrammaticLaunchCompletion(); }
+  __device__ __forceinline__ void store_reward_done(float r, bool done) const {
+    if (L.valid) {
+      st_stream(a.io.reward + L.m, r);
+      st_stream(a.io.done + L.m, (uint8_t)done);
+      const int s = slot();
+      st_stream(g.rew + s, r);
+      st_stream(g.mask + s, done ? 0.0f : 1.0f);  // mask = float(not done)
+    }
+  }
+  __device__ __forceinline__ bool wants_final() const { return true; }
+  __device__ __forceinline__ void put_own(float2 o01, float2 o23) const { stage_own(stage, L.lane, o01, o23); }
+  __device__ __forceinline__ void put_neighbours(const ObsTail& n) const { stage_neighbours(stage, L.lane, n); }
+  __device__ __forceinline__ void commit_obs() const {
+    __syncwarp();
+    flush_rows(stage, a.io.obs, L);
+    __syncwarp();
+  }
+  // the step's own next observation (before any auto-reset) goes to the ring, and with it the row of the observation
+  // the action was taken on: both are runs of valid_lanes * 5 float2 that may wrap at the end of the ring
+  __device__ __forceinline__ void commit_final() const {
+    __syncwarp();
+    const int n2 = L.valid_lanes * 5, cap2 = g.cap * 5;
+    const int d0 = (head + L.warp_m0 >= g.cap ? head + L.warp_m0 - g.cap : head + L.warp_m0) * 5;
+    const float2* s2 = reinterpret_cast<const float2*>(stage);
+    cp_async_wait_all();  // each lane reads back exactly the elements it fetched
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+      const int k = L.lane + 32 * r;
+      if (k < n2) {
+        int d = d0 + k;
+        d = d >= cap2 ? d - cap2 : d;
+        st_stream(g.nxt + d, s2[k]);
+        st_stream(g.obs + d, prev_stage[k]);
+      }
+    }
+    if (a.io.final_obs != nullptr) flush_rows(stage, a.io.final_obs, L);
+    __syncwarp();
+  }
+  __device__ __forceinline__ void store_state(const Uav& u) const { store_uav(a.s, L, u, false); }
+  __device__ __forceinline__ void store_target(const Uav& u) const {
+    st_stream(a.s.tgt + L.m, make_float2(u.tx, u.ty));
+    st_stream(a.s.init + L.m, u.init);
+  }
+  __device__ __forceinline__ void store_steps(int v, bool leader) const {
+    if (leader) a.s.steps[L.env] = v;
+  }
+  __device__ __forceinline__ void store_reset(bool rs) const {
+    if (a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
+  }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_ring_kernel(const __grid_constant__ KernelArgs a,
+                                                                                    const __grid_constant__ RingSink g) {
+  __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
+  const WarpScratch ws = warp_scratch(smem);
+  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int N = NT > 0 ? NT : a.N;
+  const bool full = uavs_left(a.B, N, warp_global) >= (32 / N) * N;  // warp-uniform
+  cudaGridDependencySynchronize();
+  __shared__ __align__(16) float2 prev_smem[kWarpsPerBlock * 160];
+  float2* const prev_stage = prev_smem + (threadIdx.x >> 5) * 160;
+  int head;  // < capacity < 2^31 / 10: the low word of meta[0]
+  asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(head) : "l"(g.meta) : "memory");  // one load per thread, L1 serves most
+  if (full) {
+    const Lane L = make_lane<NT, true>(a.B, a.N, warp_global);
+    RingIO io{a, g, L, ws.stage, prev_stage, head};
+    step_core<NT>(a, ws, L, io);
+  } else {
+    const Lane L = make_lane<NT, false>(a.B, a.N, warp_global);
+    RingIO io{a, g, L, ws.stage, prev_stage, head};
+    step_core<NT>(a, ws, L, io);
+  }
+  // every warp of this CTA holds the head (its stores used it): take the CTA's ticket; the last one advances the ring
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long*>(g.meta + 1), 1ull);
+    if (t == (unsigned long long)gridDim.x - 1ull) {
+      const long long nh = g.meta[0] + g.M;  // unchanged since every thread read it: only this branch writes it
+      g.meta[0] = nh >= g.cap ? nh - g.cap : nh;
+      const long long held = g.meta[2] + g.M;
+      g.meta[2] = held > g.cap ? g.cap : held;
+      g.meta[3] += 1;
+      g.meta[1] = 0;
+    }
+  }
+}
+
+
+
 // ---- K steps per launch -------------------------------------------------------------------------------------------
 // I/O policy of step_core for uavca_rollout: the state of the warp's UAVs stays in REGISTERS for all K steps (loaded
 // once, stored once), only the per-step outputs stream out, as [K][...] blocks.  Removes the launch, ramp-up and tail
@@ -852,6 +980,31 @@ cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launche
     if (e != cudaSuccess) return e;
     if (launched) *launched += 1;
   }
+  return cudaGetLastError();
+}
+
+template <int NT>
+static cudaError_t launch_step_multi_ring_n(const KernelArgs& a, const RingSink& g, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, step_multi_ring_kernel<NT>, a, g);
+}
+
+// step + replay append in one launch: the warp kernels only (N <= 32, float32 world)
+cudaError_t launch_step_multi_ring(const KernelArgs& a, const RingSink& g, cudaStream_t st) {
+  if (a.B <= 0) return cudaSuccess;
+  if (wants_seq(a)) return cudaErrorNotSupported;
+  cudaError_t e = cudaSuccess;
+  UAVCA_DISPATCH_N(a.N, (e = launch_step_multi_ring_n<NT>(a, g, multi_grid(a.B, a.N), st)));
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

@@ -137,6 +137,26 @@ def replay_push_dev(obs: torch.Tensor, action: torch.Tensor, reward: torch.Tenso
                                                    ring_meta.data_ptr(), _stream(obs)), "uavca_replay_push_dev")
 
 
+@torch.library.custom_op("uavca::step_multi_replay",
+                         mutates_args=("state", "obs", "reward", "done", "final_obs", "reset_mask", "ring_obs", "ring_action",
+                                       "ring_reward", "ring_next_obs", "ring_mask", "ring_meta"))
+def step_multi_replay(handle: int, state: torch.Tensor, action: torch.Tensor, action_mode: int, evaluate: bool,
+                      prev_obs: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor,
+                      final_obs: Optional[torch.Tensor], reset_mask: Optional[torch.Tensor], ring_obs: torch.Tensor,
+                      ring_action: torch.Tensor, ring_reward: torch.Tensor, ring_next_obs: torch.Tensor,
+                      ring_mask: torch.Tensor, ring_meta: torch.Tensor) -> None:
+    """MultiUAVWorld2D.step and the N `memory.push` calls that follow it in a training step (test_sac_multi.py:99-103) as
+    ONE launch: the step kernel appends every UAV's transition to the device replay ring itself."""
+    _need_cuda(state, action, prev_obs, obs, reward, done, final_obs, reset_mask, ring_obs, ring_action, ring_reward,
+               ring_next_obs, ring_mask, ring_meta)
+    _capi.check(_capi.load().uavca_step_multi_replay(handle, state.data_ptr(), action.data_ptr(), action_mode, int(evaluate),
+                                                     prev_obs.data_ptr(), obs.data_ptr(), reward.data_ptr(), done.data_ptr(),
+                                                     _ptr(final_obs), _ptr(reset_mask), ring_obs.data_ptr(),
+                                                     ring_action.data_ptr(), ring_reward.data_ptr(), ring_next_obs.data_ptr(),
+                                                     ring_mask.data_ptr(), ring_reward.numel(), ring_meta.data_ptr(),
+                                                     _stream(state)), "uavca_step_multi_replay")
+
+
 @torch.library.custom_op("uavca::policy_act", mutates_args=("action", "head"))
 def policy_act(obs: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor, w2b: torch.Tensor, w3: torch.Tensor, w3b: torch.Tensor,
                noise: Optional[torch.Tensor], seed: int, counter: int, counter_dev: Optional[torch.Tensor],

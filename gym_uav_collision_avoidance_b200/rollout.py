@@ -134,7 +134,7 @@ class BatchedRollout:
     on survives the step without a copy)."""
 
     def __init__(self, env, policy: Optional[nn.Module] = None, replay: Optional[DeviceReplay] = None,
-                 action_mode="polar", evaluate=False, warmup_uniform=False, precision="fp32"):
+                 action_mode="polar", evaluate=False, warmup_uniform=False, precision="fp32", fused_append=True):
         """precision of the policy forward: "fp32" (the reference's arithmetic: PyTorch default, TF32 off), "tf32"
         (tensor-core GEMMs on fp32 storage), "bf16" (autocast) or "fused" (the one-kernel tcgen05 acting path,
         `FusedGaussianPolicy`).  The env step itself is unaffected."""
@@ -150,8 +150,13 @@ class BatchedRollout:
         self.state = env.obs
         self._spare = torch.zeros((B, N, D), dtype=torch.float32, device=env.device)
         self.action = torch.zeros((B, N, 2), dtype=torch.float32, device=env.device)
+        # step + replay append as ONE launch where the env has it (multi world on the warp kernels): no separate pass over
+        # the transitions, no final_obs buffer
+        self.fused_append = bool(replay is not None and fused_append and replay.capacity * 10 < 2 ** 31 and
+                                 getattr(env, "supports_step_replay", lambda: False)())
         if replay is not None:
-            env.enable_final_obs()
+            if not self.fused_append:
+                env.enable_final_obs()
             if self.fused is not None:
                 # the ring's append counter advances once per acting step on the device: the policy's Philox noise is
                 # keyed on it, so no separate counter kernel runs (and CUDA-graph replays still draw fresh noise)
@@ -192,7 +197,10 @@ class BatchedRollout:
         env = self.env
         nxt, self._spare = self._spare, env.obs  # the step writes its observation into the other buffer
         env.set_obs_buffer(nxt)
-        if env.num_agents == 1 and env.obs_dim == 4:
+        if self.fused_append:
+            # next_state = the step's own observation (before any auto-reset), mask = float(not done): test_sac_multi.py:101-103
+            env.step_replay(self.action, self.state, self.replay, evaluate=self.evaluate, action_mode=self.action_mode)
+        elif env.num_agents == 1 and env.obs_dim == 4:
             env.step(self.action, action_mode=self.action_mode)
         else:
             env.step(self.action, evaluate=self.evaluate, action_mode=self.action_mode)
@@ -200,7 +208,7 @@ class BatchedRollout:
     def step(self):
         self._act()
         self._env_step()
-        if self.replay is not None:
+        if self.replay is not None and not self.fused_append:
             # next_state = the step's own observation (before any auto-reset), mask = float(not done): test_sac_multi.py:101-103
             self.replay.push(self.state, self.action, self.env.reward, self.env.final_obs, self.env.done)
         self.steps += 1

@@ -12,6 +12,7 @@
  *   uavca_observe      <- MultiUAVWorld2D._get_obs :60-109 / UAVWorld2D._get_obs uav_world_2d.py:77-112
  *   uavca_map_action   <- caller-side action mapping      test_sac_multi.py:77-80, test_pytorch_multi.py:80
  *   uavca_rollout      <- the random-action driver loops    run.py:10-16, run_multi.py:10-16 (K x env.step per call)
+ *   uavca_step_multi_replay <- env.step + the N memory.push calls of a training step   test_sac_multi.py:99-103
  *   uavca_stats        <- env.steps / target_reach_count / collision_count  multi_uav_world_2d.py:166-168,209,221,238
  *   uavca_config       <- constructor kwargs              multi_uav_world_2d.py:13-28, uav_world_2d.py:14-26
  *
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define UAVCA_VERSION 200
+#define UAVCA_VERSION 201
 
 /* world kinds */
 #define UAVCA_KIND_MULTI 0  /* MultiUAVWorld2D: N UAVs per env, 10-feature observation */
@@ -209,6 +210,21 @@ int uavca_replay_push_dev(const float* obs, const float* action, const float* re
                           const uint8_t* done, int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs,
                           float* ring_action, float* ring_reward, float* ring_next_obs, float* ring_mask,
                           int64_t capacity, int64_t* ring_meta, void* stream);
+
+/* uavca_step_multi with the replay append folded into the SAME launch ("next" row; MultiUAVWorld2D.step followed by the N
+ * memory.push calls of test_sac_multi.py:99-103).  Besides everything uavca_step_multi writes, UAV m's transition goes to
+ * ring slot (head + m) mod capacity:
+ *   ring_obs[slot]      = prev_obs[m]   (prev_obs float [B][N][10]: the observation `action` was taken on; not `obs`)
+ *   ring_action[slot]   = action[m]     (as handed in, i.e. the policy-space action when action_mode maps it)
+ *   ring_reward[slot]   = reward[m];  ring_next_obs[slot] = the step's own next observation (before any auto-reset);
+ *   ring_mask[slot]     = 1 - done[m]
+ * with the head in ring_meta (device int64[4], exactly as uavca_replay_push_dev keeps it: the two calls can be mixed on
+ * one ring).  Result identical to uavca_step_multi + uavca_replay_push_dev; one pass over the transitions less.
+ * Warp kernels only: num_agents <= 32 and not the float64 world (-2 otherwise: use the two calls); capacity * 10 < 2^31. */
+int uavca_step_multi_replay(uavca_handle* h, void* state, const float* action, int action_mode, int evaluate,
+                            const float* prev_obs, float* obs, float* reward, uint8_t* done, float* final_obs,
+                            uint8_t* reset_mask, float* ring_obs, float* ring_action, float* ring_reward, float* ring_next_obs,
+                            float* ring_mask, int64_t capacity, int64_t* ring_meta, void* stream);
 
 /* Fused acting path of the shared SAC policy ("next" row; replaces the per-UAV SAC.select_action round trips,
  * pytorch_sac_temp/sac.py:38-44, with GaussianPolicy.forward/sample, pytorch_sac_temp/model.py:74-101, for all

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported_and_bound(capi):
         assert hasattr(lib, n), f"{n} declared in include/uavca.h but not exported by libuavca.so"
         assert n in capi.SYMBOLS, f"{n} has no ctypes prototype in _capi.SYMBOLS"
     assert sorted(capi.SYMBOLS) == names
-    assert lib.uavca_version() == 200
+    assert lib.uavca_version() == 201
 
 
 def test_default_configs_follow_the_reference_constructors(capi):

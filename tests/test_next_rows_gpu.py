@@ -190,7 +190,7 @@ def test_rollout_feeds_the_replay_ring_with_the_steps_own_transitions():
     env = G.BatchedMultiUAVWorld2D(B, num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=25, seed=11)
     policy = G.GaussianPolicy(10, 2).cuda()
     rb = G.DeviceReplay(B * N * 8, 10, 2, seed=0)
-    ro = G.BatchedRollout(env, policy, rb, action_mode="polar")
+    ro = G.BatchedRollout(env, policy, rb, action_mode="polar", fused_append=False)
     obs0 = ro.reset().clone()
     ro.step()
     # the first B*N slots: state = reset observation, next_state = the step's own (pre-reset) observation
@@ -207,6 +207,75 @@ def test_rollout_feeds_the_replay_ring_with_the_steps_own_transitions():
     m = env.reset_mask.bool()
     if m.any():
         assert not torch.equal(env.obs[m], env.final_obs[m])
+
+
+@pytest.mark.parametrize("N,B", [(2, 37), (5, 64), (8, 50), (10, 64), (16, 33), (20, 21), (32, 19)])
+def test_step_with_the_replay_append_folded_in_equals_step_then_push(N, B):
+    """uavca_step_multi_replay (one launch) against uavca_step_multi + uavca_replay_push_dev on twin envs: identical env
+    outputs and state, identical ring contents, head and counters, across ring wraps (capacity is not a multiple of B*N),
+    auto-resets (dones[0] / a 25-step limit) and ragged last warps."""
+    import gym_uav_collision_avoidance_b200 as G
+
+    kw = dict(num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=25, seed=5, x_size=30.0, y_size=30.0)
+    M = B * N
+    cap = M * 3 + 7
+    envs = [G.BatchedMultiUAVWorld2D(B, **kw) for _ in range(2)]
+    rings = [G.DeviceReplay(cap, 10, 2, seed=0) for _ in range(2)]
+    ros = [G.BatchedRollout(e, None, r, action_mode="polar", warmup_uniform=True, fused_append=f)
+           for e, r, f in zip(envs, rings, (True, False))]
+    assert ros[0].fused_append and not ros[1].fused_append and envs[0].final_obs is None
+    for ro in ros:
+        ro.reset()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(60):
+        a = torch.rand((B, N, 2), generator=gen, device="cuda") * 2 - 1
+        for ro in ros:
+            ro.action.copy_(a)
+            ro.state = ro.env.obs
+            ro._env_step()
+            if not ro.fused_append:
+                ro.replay.push(ro.state, ro.action, ro.env.reward, ro.env.final_obs, ro.env.done)
+        e0, e1 = envs
+        assert torch.equal(e0.obs, e1.obs) and torch.equal(e0.reward, e1.reward) and torch.equal(e0.done, e1.done), step
+        assert torch.equal(e0.reset_mask, e1.reset_mask) and torch.equal(e0.state.blob, e1.state.blob), step
+        r0, r1 = rings
+        assert torch.equal(r0.meta[[0, 2, 3]], r1.meta[[0, 2, 3]]) and int(r0.meta[1]) == 0, step
+        for name in ("state", "action", "reward", "next_state", "mask"):
+            assert torch.equal(getattr(r0, name), getattr(r1, name)), (step, name)
+    assert len(rings[0]) == cap and rings[0].position == (60 * M) % cap
+    assert envs[0].stats()["episodes"] > 0
+
+
+def test_step_with_the_replay_append_replays_from_a_cuda_graph():
+    """A captured acting step (uniform actions, fused append) appends where the previous replay stopped."""
+    import gym_uav_collision_avoidance_b200 as G
+
+    B, N = 256, 10
+    env = G.BatchedMultiUAVWorld2D(B, num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=40, seed=2)
+    rb = G.DeviceReplay(B * N * 5, 10, 2, seed=0)
+    ro = G.BatchedRollout(env, None, rb, action_mode="polar", warmup_uniform=True)
+    assert ro.fused_append
+    ro.reset()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ro.run(2)
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        ro.run(2)  # an even number of steps: the env alternates between two observation buffers
+    torch.cuda.synchronize()
+    assert rb.position == 2 * B * N  # capturing launches nothing
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert rb.size == B * N * 5 and rb.position == (8 * B * N) % (B * N * 5) and int(rb.meta[3]) == 8
+    # consecutive steps chain: the observation stored as `state` at step t+1 is the policy-side observation of step t,
+    # which equals next_state of step t wherever the env did not auto-reset
+    M = B * N
+    nxt, st, mask = rb.next_state[0:M], rb.state[M:2 * M], rb.mask[0:M]  # steps 5 and 6 (slots wrap at 5 steps)
+    same = (nxt == st).all(dim=1)
+    assert same.float().mean() > 0.9 and same[mask.bool()].float().mean() > 0.9
 
 
 def test_gaussian_policy_matches_the_reference_formulas():
