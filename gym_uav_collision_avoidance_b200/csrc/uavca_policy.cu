@@ -171,9 +171,16 @@ __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+// (relu(x), relu(y)) as fp16x2, x in the low half: the clamp rides in the conversion (F2FP.RELU), no FMNMX
 __device__ __forceinline__ uint32_t relu_pack(float x, float y) {
-  const __half2 h = __floats2half2_rn(fmaxf(x, 0.f), fmaxf(y, 0.f));
-  return *reinterpret_cast<const uint32_t*>(&h);
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(y), "f"(x));
+  return d;
+}
+// tanh(x) = sign(x) (1 - 2 / (e^{2|x|} + 1)) on the SFU exponential and reciprocal: absolute error ~1e-7
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.0f * fabsf(x));
+  return copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
 }
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
@@ -315,9 +322,9 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_co
     for (int c = 0; c < 2; ++c) {
 #pragma unroll
       for (int k4 = 0; k4 < 4; ++k4) {  // four 16-byte chunks of 8 hidden units
-        __half2 h[4];
+        uint32_t h[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(fmaxf(v[c][k4 * 8 + 2 * j], 0.f), fmaxf(v[c][k4 * 8 + 2 * j + 1], 0.f));
+        for (int j = 0; j < 4; ++j) h[j] = relu_pack(v[c][k4 * 8 + 2 * j], v[c][k4 * 8 + 2 * j + 1]);
         *reinterpret_cast<uint4*>(sm + kOffA2 + sw128_chunk(r, g * 8 + c * 4 + k4, kRows * 128)) = *reinterpret_cast<const uint4*>(h);
       }
     }
@@ -423,9 +430,8 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_co
   auto issue_layer1 = [&](uint32_t acc) {
     mma_f16(acc, smem_desc(sbase + kOffA1, 128, 256, 0), smem_desc(sbase + kOffW1, 128, 256, 0), 0u, idesc(kHidden));
   };
-  // barrier 1: all warps; barrier 2: the epilogue warps among themselves
+  // barrier 1: all warps
   auto sync_all = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory"); };
-  auto sync_epi = [&]() { asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory"); };
 
   const int n_my = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // tiles of this CTA (>= 1: grid <= tiles)
   uint32_t phase = 0;
@@ -530,44 +536,49 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(const __grid_co
       fence_before();
       sync_all();
       POL_TICK(2)
+      // ---- while the tensor cores run layer 2 of tile it: the output heads of tile it-1.  The standard-normal draws of
+      // its rows do not depend on the heads: the column-group-0 warps compute them first, so that the Philox / Box-Muller
+      // chain interleaves with the TMEM loads and FMAs of the heads instead of standing alone on the critical path
+      const long long row = (tile - gridDim.x) * kRows + r;
+      const bool samples = has_prev && g == 0 && row < a.M;
+      float e0 = 0.f, e1 = 0.f;
+      if (samples) {
+        if (a.noise) {
+          const float2 z = reinterpret_cast<const float2*>(a.noise)[row];
+          e0 = z.x; e1 = z.y;
+        } else {  // Box-Muller on one Philox4x32-10 block keyed by (seed, row, call counter)
+          const uint4 rn = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), a.seed_lo, a.seed_hi);
+          const float u1 = ((float)(rn.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+          const float u2 = ((float)(rn.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+          const float rad = sqrtf(-2.0f * __logf(u1));
+          float sn, cs;
+          __sincosf(6.28318530717958647692f * u2, &sn, &cs);
+          e0 = rad * cs; e1 = rad * sn;
+        }
+      }
       if (has_prev) {
-        // ---- while the tensor cores run layer 2 of tile it: the output heads of tile it-1
 #if !defined(UAVCA_POLICY_HEADS_MMA)
         heads_fma(acc_prev);
 #else
         heads(acc_prev);
 #endif
         POL_TICK(3)
-        sync_epi();  // the four column groups of every row have met in shared memory
-        POL_TICK(4)
-        // ---- sample and squash (one thread per row: the column-group-0 warps)
-        const long long row = (tile - gridDim.x) * kRows + r;
-        if (g == 0 && row < a.M) {
-          const float4* pp = reinterpret_cast<const float4*>(sm + kOffPart) + r;
-          const float4 p0 = pp[0], p1 = pp[kRows], p2 = pp[2 * kRows], p3 = pp[3 * kRows], b3 = *reinterpret_cast<const float4*>(sm + kOffB3);
-          const float m0 = p0.x + p1.x + p2.x + p3.x + b3.x, m1 = p0.y + p1.y + p2.y + p3.y + b3.y;
-          const float l0 = fminf(fmaxf(p0.z + p1.z + p2.z + p3.z + b3.z, -20.f), 2.f);  // LOG_SIG_MIN / LOG_SIG_MAX (model.py:6-7,79)
-          const float l1 = fminf(fmaxf(p0.w + p1.w + p2.w + p3.w + b3.w, -20.f), 2.f);
-          float e0, e1;
-          if (a.noise) {
-            const float2 z = reinterpret_cast<const float2*>(a.noise)[row];
-            e0 = z.x; e1 = z.y;
-          } else {  // Box-Muller on one Philox4x32-10 block keyed by (seed, row, call counter)
-            const uint4 rn = philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), a.seed_lo, a.seed_hi);
-            const float u1 = ((float)(rn.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float u2 = ((float)(rn.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-            const float rad = sqrtf(-2.0f * __logf(u1));
-            float sn, cs;
-            __sincosf(6.28318530717958647692f * u2, &sn, &cs);
-            e0 = rad * cs; e1 = rad * sn;
-          }
-          const float x0 = fmaf(__expf(l0), e0, m0), x1 = fmaf(__expf(l1), e1, m1);
-          reinterpret_cast<float2*>(a.action)[row] = make_float2(tanhf(x0), tanhf(x1));  // model.py:90-91
-          if (a.head) reinterpret_cast<float4*>(a.head)[row] = make_float4(m0, m1, l0, l1);
-        }
       }
       fence_before();
-      sync_all();  // acc_prev may be overwritten (layer 1 of tile it+1); the partials are rewritten after the next sync_all
+      sync_all();  // acc_prev may be overwritten (layer 1 of tile it+1, which the MMA warp issues now); the four column
+                   // groups of every row have met in shared memory (rewritten only after the next iteration's first barrier)
+      POL_TICK(4)
+      if (samples) {
+        // ---- sample and squash (one thread per row), while the tensor pipe runs layer 1 of the next tile
+        const float4* pp = reinterpret_cast<const float4*>(sm + kOffPart) + r;
+        const float4 p0 = pp[0], p1 = pp[kRows], p2 = pp[2 * kRows], p3 = pp[3 * kRows], b3 = *reinterpret_cast<const float4*>(sm + kOffB3);
+        const float m0 = p0.x + p1.x + p2.x + p3.x + b3.x, m1 = p0.y + p1.y + p2.y + p3.y + b3.y;
+        const float l0 = fminf(fmaxf(p0.z + p1.z + p2.z + p3.z + b3.z, -20.f), 2.f);  // LOG_SIG_MIN / LOG_SIG_MAX (model.py:6-7,79)
+        const float l1 = fminf(fmaxf(p0.w + p1.w + p2.w + p3.w + b3.w, -20.f), 2.f);
+        const float x0 = fmaf(__expf(l0), e0, m0), x1 = fmaf(__expf(l1), e1, m1);
+        reinterpret_cast<float2*>(a.action)[row] = make_float2(tanh_fast(x0), tanh_fast(x1));  // model.py:90-91
+        if (a.head) reinterpret_cast<float4*>(a.head)[row] = make_float4(m0, m1, l0, l1);
+      }
     }
   }
 
