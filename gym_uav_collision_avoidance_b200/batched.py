@@ -288,6 +288,28 @@ class _BatchedBase:
             action = action.clone()
         return action
 
+    def step_f64(self, action: torch.Tensor, evaluate: bool = False):
+        """`step()` fed FLOAT64 cartesian actions ([B,N,2] float64 CUDA; [B,2] / [B,1,2] for the single world) — what the
+        reference's own loops build on the host (test_sac_multi.py:77-80) and `UAVAgent.step` consumes in float64
+        (uav_agent.py:26).  Bit-exact for actions float32 cannot hold; runs on the general one-thread-per-env kernel (the
+        drop-in path: `compat.py` uses it), the float32 `step()` is the throughput path."""
+        B, N = self.num_envs, self.num_agents
+        action = action.to(device=self.device, dtype=torch.float64).contiguous()
+        if action.numel() != B * N * 2:
+            raise ValueError(f"action must hold {B}x{N}x2 values, got shape {tuple(action.shape)}")
+        if action.data_ptr() % 16:
+            action = action.clone()
+        dist = getattr(self, "distance", None)
+        _capi.check(self._lib.uavca_step_f64(self._h, self.state.blob.data_ptr(), action.data_ptr(), int(bool(evaluate)),
+                                             self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                             None if dist is None else dist.data_ptr(),
+                                             None if self.final_obs is None else self.final_obs.data_ptr(),
+                                             self.reset_mask.data_ptr(), self._stream()), "uavca_step_f64")
+        info = {"distance": dist if dist is not None else 0, "reset_mask": self.reset_mask}
+        if self.final_obs is not None:
+            info["final_obs"] = self.final_obs
+        return self.obs, self.reward, self.done, info
+
     def step_host(self, action: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor,
                   action_mode="cartesian", evaluate: bool = False):
         """End-to-end step with HOST tensors (pinned for speed): H2D actions, step, D2H obs/reward/done."""

@@ -9,10 +9,10 @@ reference's loops run unchanged against the CUDA path (parity, migration); throu
 classes in `batched.py`.  Differences, all forced by the design: episodes are drawn from the counter-based Philox
 stream (`seed=` kwarg) instead of the global `np.random`; observations/rewards are float32 values widened to
 float64; in-place edits of a returned array (`agent.location[0] = x`) do not reach the device — assign the
-attribute instead; `render()` opens no window but records the frame into `env.trajectory` (`export_trajectory()`);
-float64 cartesian actions are rounded to float32 before the step (the reference's `(action - v) / tau` then starts
-from the float64 action: bit-identical whenever the action is float32-representable or the acceleration clip is
-active, within 1e-7 relative otherwise).
+attribute instead; `render()` opens no window but records the frame into `env.trajectory` (`export_trajectory()`).
+Actions keep their dtype: python floats / float64 arrays (what the SAC/TD3/DDPG loops build, test_sac_multi.py:77-80) go
+through `uavca_step_f64` and are consumed in float64 like the reference's `(action - v) / tau` (uav_agent.py:26), float32
+arrays (`action_space.sample()`) through the float32 entry points.
 """
 from __future__ import annotations
 
@@ -52,14 +52,26 @@ class _HostIO:
         pin = lambda *shape, dtype=torch.float32: torch.zeros(shape, dtype=dtype).pin_memory()  # noqa: E731
         self.action, self.obs, self.reward = pin(1, N, 2), pin(1, N, D), pin(1, N)
         self.done, self.mask, self.distance = pin(1, N, dtype=torch.uint8), pin(1, dtype=torch.uint8), pin(1)
-        self.np = {k: getattr(self, k).numpy() for k in ("action", "obs", "reward", "done", "distance")}
-        self.ptr = {k: getattr(self, k).data_ptr() for k in ("action", "obs", "reward", "done", "mask", "distance")}
+        self.action64 = pin(1, N, 2, dtype=torch.float64)
+        self.np = {k: getattr(self, k).numpy() for k in ("action", "action64", "obs", "reward", "done", "distance")}
+        self.ptr = {k: getattr(self, k).data_ptr() for k in ("action", "action64", "obs", "reward", "done", "mask", "distance")}
 
     def step(self, b, n_action, evaluate=False):
         from . import _capi
 
-        self.np["action"][...] = np.asarray(n_action, dtype=np.float64).reshape(1, b.num_agents, 2)
+        n_action = np.asarray(n_action)
         p, st = self.ptr, torch.cuda.current_stream(b.device)
+        if n_action.dtype != np.float32:
+            # what the reference's loops hand env.step(): python floats / float64 arrays (test_sac_multi.py:77-80), consumed in
+            # float64 by UAVAgent.step (uav_agent.py:26) — uavca_step_f64 keeps every bit of them
+            self.np["action64"][...] = n_action.astype(np.float64).reshape(1, b.num_agents, 2)
+            rc = b._lib.uavca_step_f64(b._h, b.state.blob.data_ptr(), p["action64"], int(bool(evaluate)), p["obs"], p["reward"],
+                                       p["done"], p["distance"] if b.kind == _capi.KIND_SINGLE else None, None, p["mask"],
+                                       st.cuda_stream)
+            _capi.check(rc, "uavca_step_f64")
+            st.synchronize()
+            return self.np
+        self.np["action"][...] = n_action.reshape(1, b.num_agents, 2)
         if b.kind == _capi.KIND_SINGLE:
             rc = b._lib.uavca_step_single(b._h, b.state.blob.data_ptr(), p["action"], 0, p["obs"], p["reward"], p["done"],
                                           p["distance"], None, p["mask"], st.cuda_stream)

@@ -437,6 +437,32 @@ int uavca_step_single(uavca_handle* h, void* state, const float* action, int act
   return 0;
 }
 
+int uavca_step_f64(uavca_handle* h, void* state, const double* action, int evaluate, float* obs, float* reward, uint8_t* done,
+                   float* distance, float* final_obs, uint8_t* reset_mask, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  if (!state || !action || !obs || !reward || !done) return fail(-1, "null argument");
+  if (int rc = check_step_alignment(state, nullptr, obs, reward, final_obs)) return rc;
+  if (misaligned(action, 16)) return fail(-1, "misaligned buffer: float64 actions need 16-byte alignment");
+  if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
+  DeviceGuard g(h->device);
+  KernelArgs a = make_args(h, state);
+  a.io.action = nullptr;
+  a.io.action64 = reinterpret_cast<const double2*>(action);
+  a.io.obs = obs; a.io.reward = reward; a.io.done = done; a.io.final_obs = final_obs; a.io.reset_mask = reset_mask;
+  a.io.action_mode = UAVCA_ACTION_CARTESIAN; a.io.evaluate = evaluate;
+  cudaError_t e;
+  int launched = 1;
+  if (h->cfg.kind == UAVCA_KIND_SINGLE) {
+    a.io.distance = distance;
+    e = launch_step_single(a, (cudaStream_t)stream);
+  } else {
+    e = launch_step_multi(a, (cudaStream_t)stream, &launched, h->path);  // the general one-thread-per-env kernel
+  }
+  h->launches += launched;
+  if (e != cudaSuccess) return fail_cuda("uavca_step_f64", e);
+  return 0;
+}
+
 int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* out, void* stream) {
   if (int rc = check_handle(h)) return rc;
   if (!in || !out) return fail(-1, "null argument");

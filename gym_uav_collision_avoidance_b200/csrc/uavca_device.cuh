@@ -81,6 +81,7 @@ struct StateView {
 
 struct StepIO {
   const float2* action;
+  const double2* action64;  // nullable: float64 cartesian actions (uavca_step_f64) instead of `action`
   float* obs;
   float* reward;
   uint8_t* done;

@@ -541,12 +541,15 @@ __device__ __forceinline__ void fold_single(const KernelArgs& a, long long b, un
 
 // One UAVWorld2D.step of env b held in registers (uav_world_2d.py:137-173); outputs go to row `o` of the output
 // tensors (o = b for one step per launch, k * B + b inside a rollout).  Returns true when the env auto-reset.
-__device__ __forceinline__ bool step_single_core(const KernelArgs& a, long long b, long long o, SingleEnv& e, float2 act_raw) {
+__device__ __forceinline__ bool step_single_core(const KernelArgs& a, long long b, long long o, SingleEnv& e, float2 act_raw,
+                                                 const double2* act64 = nullptr) {
   const Consts& c = a.c;
   const float2 act = map_action(act_raw, a.io.action_mode, c);
 
   // UAVWorld2D.step (uav_world_2d.py:142-147)
-  if (c.single_f32_first_step && e.steps == 0) {
+  if (act64 != nullptr) {  // a float64 action: float64 arithmetic from the first step on
+    integrate(act64->x, act64->y, e.vx, e.vy, e.px, e.py, c);
+  } else if (c.single_f32_first_step && e.steps == 0) {
     // float32 action against the float32 reset speed: the quotient is formed in float32 (:122,:142)
     const double qx = (double)__fdiv_rn(__fsub_rn(act.x, (float)e.vx), c.tau_f);
     const double qy = (double)__fdiv_rn(__fsub_rn(act.y, (float)e.vy), c.tau_f);
@@ -605,7 +608,13 @@ __global__ void __launch_bounds__(kThreads) step_single_kernel(const __grid_cons
   const long long b = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (b >= a.B) return;
   SingleEnv e = load_single(a.s, b);
-  const bool rs = step_single_core(a, b, b, e, ld_stream(a.io.action + b));
+  bool rs;
+  if (a.io.action64 != nullptr) {
+    const double2 q = a.io.action64[b];
+    rs = step_single_core(a, b, b, e, make_float2(0.f, 0.f), &q);
+  } else {
+    rs = step_single_core(a, b, b, e, ld_stream(a.io.action + b));
+  }
   store_single(a.s, b, e, rs);
 }
 
@@ -885,7 +894,7 @@ static cudaError_t launch_step_pf_n(const KernelArgs& a, int num_tiles, cudaStre
 
 
 // the general one-thread-per-env kernels (uavca_seq.cuh) serve the float64 world and envs wider than a warp
-static inline bool wants_seq(const KernelArgs& a) { return a.c.circular != 0 || a.N > 32; }
+static inline bool wants_seq(const KernelArgs& a) { return a.c.circular != 0 || a.N > 32 || a.io.action64 != nullptr; }
 
 cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path) {
   if (launched) *launched = 0;

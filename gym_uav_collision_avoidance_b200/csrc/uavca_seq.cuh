@@ -209,10 +209,17 @@ __global__ void __launch_bounds__(kThreads) step_multi_seq_kernel(const __grid_c
     const bool parked = (flags & UAVCA_FLAG_PARKED) != 0u;
     P prev_d = (P)0, dist = (P)0;
     if (!parked) {  // UAVAgent.step (uav_agent.py:23-36)
-      const float2 act = map_action(a.io.action[m], a.io.action_mode, c);
+      double ax, ay;  // the action as the reference's float64 arithmetic sees it (uav_agent.py:26)
+      if (a.io.action64 != nullptr) {
+        const double2 q = a.io.action64[m];
+        ax = q.x; ay = q.y;
+      } else {
+        const float2 act = map_action(a.io.action[m], a.io.action_mode, c);
+        ax = (double)act.x; ay = (double)act.y;
+      }
       double vx = vel[2 * i], vy = vel[2 * i + 1];
-      const double dvx = clipd(__ddiv_rn(__dsub_rn((double)act.x, vx), c.tau), -c.amax, c.amax);
-      const double dvy = clipd(__ddiv_rn(__dsub_rn((double)act.y, vy), c.tau), -c.amax, c.amax);
+      const double dvx = clipd(__ddiv_rn(__dsub_rn(ax, vx), c.tau), -c.amax, c.amax);
+      const double dvy = clipd(__ddiv_rn(__dsub_rn(ay, vy), c.tau), -c.amax, c.amax);
       vx = clipd(__dadd_rn(vx, __dmul_rn(dvx, c.tau)), -c.vmax, c.vmax);
       vy = clipd(__dadd_rn(vy, __dmul_rn(dvy, c.tau)), -c.vmax, c.vmax);
       pos[2 * i] = (P)__dadd_rn((double)pos[2 * i], __dmul_rn(vx, c.tau));  // one rounding in either dtype

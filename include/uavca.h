@@ -7,6 +7,7 @@
  *
  *   uavca_step_multi   <- MultiUAVWorld2D.step            gym_uav_collision_avoidance/envs/multi_uav_world_2d.py:177-241
  *                         UAVAgent.step/finish/uavs_in_range  gym_uav_collision_avoidance/envs/uav_agent.py:23-64
+ *   uavca_step_f64     <- either step() fed NumPy float64 actions   uav_agent.py:26, uav_world_2d.py:142
  *   uavca_step_single  <- UAVWorld2D.step                 gym_uav_collision_avoidance/envs/uav_world_2d.py:137-173
  *   uavca_reset        <- MultiUAVWorld2D.reset :116-175 / UAVWorld2D.reset uav_world_2d.py:119-135
  *   uavca_observe      <- MultiUAVWorld2D._get_obs :60-109 / UAVWorld2D._get_obs uav_world_2d.py:77-112
@@ -156,6 +157,14 @@ int uavca_step_multi(uavca_handle* h, void* state, const float* action, int acti
 int uavca_step_single(uavca_handle* h, void* state, const float* action, int action_mode, float* obs,
                       float* reward, uint8_t* done, float* distance, float* final_obs, uint8_t* reset_mask,
                       void* stream);
+
+/* env.step() fed FLOAT64 cartesian actions — what the reference's own loops hand it: NumPy float64 arrays built on the
+ * host (test_sac_multi.py:77-80, run.py:13), which `UAVAgent.step` consumes in float64 (uav_agent.py:26; uav_world_2d.py:142).
+ * action: double [B][N][2] ([B][2] for the single world).  Serves both kinds (distance: single world only, nullable;
+ * evaluate: multi world only).  Runs on the general one-thread-per-env kernel: the drop-in path (compat.py), bit-exact
+ * for actions that float32 cannot hold; the batched float32 entry points above are the throughput path. */
+int uavca_step_f64(uavca_handle* h, void* state, const double* action, int evaluate, float* obs, float* reward, uint8_t* done,
+                   float* distance, float* final_obs, uint8_t* reset_mask, void* stream);
 
 /* The caller-side action mapping on its own: in/out float [B][N][2]. */
 int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* out, void* stream);

@@ -17,6 +17,7 @@ region (soft/hard collisions, goal reaches, parked UAVs being hit), both env kin
 from __future__ import annotations
 
 import json
+import math
 import os
 
 import numpy as np
@@ -37,6 +38,15 @@ MULTI_CASES = [
     # more UAVs than a warp holds: the general one-thread-per-env kernel (num_agents is unbounded in the reference)
     dict(name="multi_n40_reset_done0", N=40, E=2, T=90, seed=140, evaluate=0, reset_mode=O.RESET_ON_DONE0, max_steps=60),
 ]
+# float64 actions that float32 cannot hold — what the reference's SAC loop builds on the host (test_sac_multi.py:77-80: a
+# uniform policy output mapped to polar coordinates in float64) and a float64 go-to-goal controller in the crowded envs
+F64ACT_CASES = [
+    dict(name="f64act_multi_n5", N=5, E=6, T=300, seed=405, evaluate=0, reset_mode=O.RESET_ON_DONE0, max_steps=120, f64act=1),
+    dict(name="f64act_multi_n12_eval", N=12, E=4, T=250, seed=412, evaluate=1, reset_mode=O.RESET_ON_ALL_DONE, max_steps=0, f64act=1),
+]
+F64ACT_SINGLE_CASES = [
+    dict(name="f64act_single", E=8, T=300, seed=451, f32=0, f64act=1),
+]
 SINGLE_CASES = [
     dict(name="single_f64_actions", E=12, T=400, seed=201, f32=0),
     dict(name="single_f32_actions", E=12, T=400, seed=202, f32=1),
@@ -55,6 +65,15 @@ def _actions_multi(rng, st: O.State, b: int, N: int, controller: bool):
         a = (st.tgt[b] - st.pos[b]) * 1.5 + rng.normal(0, 0.3, size=(N, 2))
         return np.clip(a, -10, 10).astype(np.float32)
     return rng.uniform(-10, 10, size=(N, 2)).astype(np.float32)
+
+
+def _actions_multi_f64(rng, st: O.State, b: int, N: int, controller: bool):
+    if controller:
+        return np.clip((st.tgt[b].astype(np.float64) - st.pos[b]) * 1.5 + rng.normal(0, 0.3, size=(N, 2)), -10, 10)
+    u = rng.uniform(-1, 1, size=(N, 2))  # the policy-space action of test_sac_multi.py:72-80
+    v = (u[:, 0] / 2 + 0.5) * np.linalg.norm(np.full(2, 10.0, np.float32))
+    th = u[:, 1] * math.pi
+    return np.stack([v * np.cos(th), v * np.sin(th)], axis=1).astype(np.float64)
 
 
 def run_reference_multi(case) -> dict:
@@ -90,7 +109,11 @@ def run_reference_multi(case) -> dict:
     obs0 = np.stack([np.stack([env._get_obs(a) for a in env.agent_list]) for env in envs])
     for t in range(T):
         for b, env in enumerate(envs):
-            a = _actions_multi(rng, cur, b, N, controller=(b % 2 == 1))
+            if case.get("f64act"):
+                a = _actions_multi_f64(rng, cur, b, N, controller=(b % 2 == 1))
+                out.setdefault("action64", np.zeros((T, E, N, 2), np.float64))[t, b] = a
+            else:
+                a = _actions_multi(rng, cur, b, N, controller=(b % 2 == 1))
             out["action"][t, b] = a
             o, r, d, _ = env.step([a[i].astype(np.float64) for i in range(N)], evaluate=bool(case["evaluate"]))
             o = np.stack(o)
@@ -197,6 +220,10 @@ def run_reference_single(case) -> dict:
                 a = np.clip((cur.tgt[b, 0] - cur.pos[b, 0]) * 0.8 + rng.normal(0, 0.5, 2), -12, 12).astype(np.float32)
             else:
                 a = rng.uniform(-12, 12, 2).astype(np.float32)
+            if case.get("f64act"):  # the same controller / random actions, not rounded to float32
+                a = (np.clip((cur.tgt[b, 0].astype(np.float64) - cur.pos[b, 0]) * 0.8 + rng.normal(0, 0.5, 2), -12, 12)
+                     if b % 2 == 1 else rng.uniform(-12, 12, 2))
+                out.setdefault("action64", np.zeros((T, E, 1, 2), np.float64))[t, b, 0] = a
             out["action"][t, b, 0] = a
             o, r, d, info = env.step(a if case["f32"] else a.astype(np.float64))
             out["final_obs"][t, b, 0] = o
@@ -230,7 +257,7 @@ def main():
 
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     only = sys.argv[1] if len(sys.argv) > 1 else None  # "circular" or a case name: regenerate just those cases
-    if only and only != "circular":
+    if only and only not in ("circular", "f64act"):
         for case in MULTI_CASES:
             if case["name"] == only:
                 res = run_reference_multi(case)
@@ -240,6 +267,21 @@ def main():
                 np.savez_compressed(path, **res)
                 print(f"{case['name']}: done-events={int(res['done'].sum())} resets={int(res['reset_mask'].sum())} "
                       f"reach={int(res['reach'].max())} coll={int(res['coll'].max())} -> {os.path.getsize(path) / 1e6:.2f} MB")
+        return
+    if only == "f64act":
+        for case in F64ACT_CASES:
+            res = run_reference_multi(case)
+            path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+            np.savez_compressed(path, **res)
+            lost = int((res["action64"] != res["action"]).sum())
+            print(f"{case['name']}: done-events={int(res['done'].sum())} resets={int(res['reset_mask'].sum())} "
+                  f"reach={int(res['reach'].max())} coll={int(res['coll'].max())} actions float32 cannot hold={lost} "
+                  f"-> {os.path.getsize(path) / 1e6:.2f} MB")
+        for case in F64ACT_SINGLE_CASES:
+            res = run_reference_single(case)
+            path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
+            np.savez_compressed(path, **res)
+            print(f"{case['name']}: resets={int(res['reset_mask'].sum())} -> {os.path.getsize(path) / 1e6:.2f} MB")
         return
     if only == "circular":
         for case in CIRCULAR_CASES:
@@ -265,11 +307,14 @@ def main():
         print(f"{case['name']}: done-events={int(res['done'].sum())} resets={int(res['reset_mask'].sum())} "
               f"reach={int(res['reach'].max())} coll={int(res['coll'].max())} parked-steps={int((res['flags'] & 1).sum())} "
               f"-> {os.path.getsize(path) / 1e6:.2f} MB")
-    for case in SINGLE_CASES:
+    for case in SINGLE_CASES + F64ACT_SINGLE_CASES:
         res = run_reference_single(case)
         path = os.path.join(GOLDEN_DIR, case["name"] + ".npz")
         np.savez_compressed(path, **res)
         print(f"{case['name']}: resets={int(res['reset_mask'].sum())} -> {os.path.getsize(path) / 1e6:.2f} MB")
+    for case in F64ACT_CASES:
+        res = run_reference_multi(case)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, case["name"] + ".npz"), **res)
 
 
 if __name__ == "__main__":

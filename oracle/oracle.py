@@ -101,7 +101,7 @@ def lib():
         build()
         _lib = C.CDLL(_LIB_PATH)
         for name in ("uavo_reset", "uavo_observe", "uavo_step_multi", "uavo_step_single", "uavo_map_action",
-                     "uavo_max_threads", "uavo_sample_actions"):
+                     "uavo_max_threads", "uavo_sample_actions", "uavo_step_f64act"):
             getattr(_lib, name).restype = C.c_int
     return _lib
 
@@ -229,6 +229,26 @@ class Oracle:
             lib().uavo_step_multi(C.byref(self.cfg), C.byref(st), pp, C.c_int(pn), _ptr(a), C.c_int(action_mode),
                                   C.c_int(1 if evaluate else 0), _ptr(obs), _ptr(reward), _ptr(done), _ptr(final_obs),
                                   _ptr(reset_mask), C.c_int(self.nthreads))
+        return out
+
+    def step_f64(self, action64, evaluate=False, want_final_obs=False):
+        """step() fed float64 cartesian actions [B,N,2] (what the reference's own loops build, test_sac_multi.py:77-80)."""
+        B, N, D = self.B, self.N, self.obs_dim
+        a = np.ascontiguousarray(action64, dtype=np.float64).reshape(B, N, 2)
+        obs = np.zeros((B, N, D), np.float64)
+        reward = np.zeros((B, N), np.float64)
+        done = np.zeros((B, N), np.uint8)
+        final_obs = np.zeros((B, N, D), np.float64) if want_final_obs else None
+        reset_mask = np.zeros(B, np.uint8)
+        dist = np.zeros(B, np.float32)
+        st = self.state._c()
+        pp, pn = self._pool_args()
+        lib().uavo_step_f64act(C.byref(self.cfg), C.byref(st), pp, C.c_int(pn), _ptr(a), C.c_int(1 if evaluate else 0),
+                               _ptr(obs), _ptr(reward), _ptr(done), _ptr(dist), _ptr(final_obs), _ptr(reset_mask),
+                               C.c_int(self.nthreads))
+        out = dict(obs=obs, reward=reward, done=done, reset_mask=reset_mask, final_obs=final_obs)
+        if self.cfg.kind == KIND_SINGLE:
+            out["distance"] = dist
         return out
 
 

@@ -324,7 +324,7 @@ static void reset_env_single(const uavca_config* c, uavo_state* s, const uavo_st
 
 /* ---- step: MultiUAVWorld2D.step (multi_uav_world_2d.py:177-241) + UAVAgent (uav_agent.py:23-64) ----- */
 
-static void step_env_multi(const uavca_config* c, uavo_state* s, int b, const float* action, int action_mode,
+static void step_env_multi(const uavca_config* c, uavo_state* s, int b, const float* action, const double* a64, int action_mode,
                            int evaluate, double* obs, double* reward, uint8_t* done) {
   const int N = c->num_agents;
   float* pos = s->pos + (size_t)b * N * 2;
@@ -347,10 +347,12 @@ static void step_env_multi(const uavca_config* c, uavo_state* s, int b, const fl
     if (parked) {                                             /* uav_agent.py:24-25 returns ints 0, 0 */
       prev_d = 0.f; dist = 0.f;
     } else {
-      float ax, ay;
-      map_action(c, action_mode, action[2 * i], action[2 * i + 1], &ax, &ay);
-      double dvx = clipd(((double)ax - vel[2 * i]) / tau, -amax, amax);       /* uav_agent.py:26 */
-      double dvy = clipd(((double)ay - vel[2 * i + 1]) / tau, -amax, amax);
+      double ax, ay; /* the action as float64 arithmetic sees it: a float32 action widens exactly, a float64 one (a64: what
+                        the reference's own loops build, test_sac_multi.py:77-80) enters as it is */
+      if (a64) { ax = a64[2 * i]; ay = a64[2 * i + 1]; }
+      else { float fx, fy; map_action(c, action_mode, action[2 * i], action[2 * i + 1], &fx, &fy); ax = (double)fx; ay = (double)fy; }
+      double dvx = clipd((ax - vel[2 * i]) / tau, -amax, amax);       /* uav_agent.py:26 */
+      double dvy = clipd((ay - vel[2 * i + 1]) / tau, -amax, amax);
       double vx = clipd(vel[2 * i] + dvx * tau, -vmax, vmax);                 /* :27 */
       double vy = clipd(vel[2 * i + 1] + dvy * tau, -vmax, vmax);
       pos[2 * i] = (float)((double)pos[2 * i] + vx * tau);                    /* :28-29 float32 += float64 */
@@ -430,17 +432,20 @@ static void step_env_multi(const uavca_config* c, uavo_state* s, int b, const fl
 
 /* ---- step: UAVWorld2D.step, uav_world_2d.py:137-173 ------------------------------------------------- */
 
-static void step_env_single(const uavca_config* c, uavo_state* s, int b, const float* action, int action_mode,
+static void step_env_single(const uavca_config* c, uavo_state* s, int b, const float* action, const double* a64, int action_mode,
                             double* obs, double* reward, uint8_t* done, float* distance) {
   float* pos = s->pos + (size_t)b * 2;
   double* vel = s->vel + (size_t)b * 2;
   const float* tgt = s->tgt + (size_t)b * 2;
   const double tau = c->tau, amax = c->max_acceleration, vmax = c->max_speed;
   const double lox = -c->x_size / 2.0, hix = c->x_size / 2.0, loy = -c->y_size / 2.0, hiy = c->y_size / 2.0;
-  float ax, ay;
-  map_action(c, action_mode, action[0], action[1], &ax, &ay);
+  float ax = 0.f, ay = 0.f;
+  if (!a64) map_action(c, action_mode, action[0], action[1], &ax, &ay);
   double qx, qy;
-  if (c->single_f32_first_step && s->steps[b] == 0) {
+  if (a64) { /* a float64 action: float64 arithmetic from the first step on (uav_world_2d.py:142) */
+    qx = (a64[0] - vel[0]) / tau;
+    qy = (a64[1] - vel[1]) / tau;
+  } else if (c->single_f32_first_step && s->steps[b] == 0) {
     /* float32 action minus the float32 reset speed, divided by the weak python float tau: all float32 */
     qx = (double)((ax - (float)vel[0]) / (float)tau);
     qy = (double)((ay - (float)vel[1]) / (float)tau);
@@ -557,7 +562,7 @@ static void reset_env_circular(const uavca_config* c, uavo_state* s, int b) {
   s->episode[b] = ep + 1;
 }
 
-static void step_env_multi_f64(const uavca_config* c, uavo_state* s, int b, const float* action, int action_mode,
+static void step_env_multi_f64(const uavca_config* c, uavo_state* s, int b, const float* action, const double* a64, int action_mode,
                                int evaluate, double* obs, double* reward, uint8_t* done) {
   const int N = c->num_agents;
   double* pos = s->pos64 + (size_t)b * N * 2;
@@ -576,10 +581,11 @@ static void step_env_multi_f64(const uavca_config* c, uavo_state* s, int b, cons
     if (parked) {
       prev_d = 0.0; dist = 0.0;
     } else {
-      float ax, ay;
-      map_action(c, action_mode, action[2 * i], action[2 * i + 1], &ax, &ay);
-      double dvx = clipd(((double)ax - vel[2 * i]) / tau, -amax, amax);
-      double dvy = clipd(((double)ay - vel[2 * i + 1]) / tau, -amax, amax);
+      double ax, ay;
+      if (a64) { ax = a64[2 * i]; ay = a64[2 * i + 1]; }
+      else { float fx, fy; map_action(c, action_mode, action[2 * i], action[2 * i + 1], &fx, &fy); ax = (double)fx; ay = (double)fy; }
+      double dvx = clipd((ax - vel[2 * i]) / tau, -amax, amax);
+      double dvy = clipd((ay - vel[2 * i + 1]) / tau, -amax, amax);
       double vx = clipd(vel[2 * i] + dvx * tau, -vmax, vmax);
       double vy = clipd(vel[2 * i + 1] + dvy * tau, -vmax, vmax);
       pos[2 * i] = pos[2 * i] + vx * tau;                      /* uav_agent.py:28-29 in float64 */
@@ -715,17 +721,20 @@ typedef struct {
   const uavca_config* c; uavo_state* s; const float* action; int action_mode; int evaluate;
   double* obs; double* reward; uint8_t* done; float* distance; double* final_obs;
   const uavo_state* pool; int pool_envs; uint8_t* reset_mask;
+  const double* action64; /* float64 cartesian actions instead of `action` (uavo_step_f64act) */
 } step_ctx;
 static int want_reset(const uavca_config* c, const uint8_t* done, int N, int steps);
 static void step_multi_body(void* p, int b) {
   step_ctx* x = (step_ctx*)p;
   const int N = x->c->num_agents;
   const int f64 = x->c->circular && x->s->pos64;
+  const float* af = x->action ? x->action + (size_t)b * N * 2 : 0;
+  const double* ad = x->action64 ? x->action64 + (size_t)b * N * 2 : 0;
   if (f64)
-    step_env_multi_f64(x->c, x->s, b, x->action + (size_t)b * N * 2, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
+    step_env_multi_f64(x->c, x->s, b, af, ad, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
                        x->reward + (size_t)b * N, x->done + (size_t)b * N);
   else
-    step_env_multi(x->c, x->s, b, x->action + (size_t)b * N * 2, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
+    step_env_multi(x->c, x->s, b, af, ad, x->action_mode, x->evaluate, x->obs + (size_t)b * N * 10,
                    x->reward + (size_t)b * N, x->done + (size_t)b * N);
   if (x->final_obs) memcpy(x->final_obs + (size_t)b * N * 10, x->obs + (size_t)b * N * 10, sizeof(double) * N * 10);
   /* auto-reset in place (envs are independent; the shared totals are folded atomically) */
@@ -748,8 +757,8 @@ static void step_multi_body(void* p, int b) {
 }
 static void step_single_body(void* p, int b) {
   step_ctx* x = (step_ctx*)p;
-  step_env_single(x->c, x->s, b, x->action + (size_t)b * 2, x->action_mode, x->obs + (size_t)b * 4, x->reward + b,
-                  x->done + b, x->distance ? x->distance + b : 0);
+  step_env_single(x->c, x->s, b, x->action ? x->action + (size_t)b * 2 : 0, x->action64 ? x->action64 + (size_t)b * 2 : 0,
+                  x->action_mode, x->obs + (size_t)b * 4, x->reward + b, x->done + b, x->distance ? x->distance + b : 0);
   if (x->final_obs) memcpy(x->final_obs + (size_t)b * 4, x->obs + (size_t)b * 4, sizeof(double) * 4);
   const int rs = want_reset(x->c, x->done + b, 1, x->s->steps[b]);
   if (x->reset_mask) x->reset_mask[b] = (uint8_t)rs;
@@ -816,7 +825,7 @@ int uavo_step_multi(const uavca_config* c, uavo_state* s, const uavo_state* pool
                     int action_mode, int evaluate, double* obs, double* reward, uint8_t* done, double* final_obs,
                     uint8_t* reset_mask, int nthreads) {
   const int N = c->num_agents, B = c->num_envs;
-  step_ctx ctx = {c, s, action, action_mode, evaluate, obs, reward, done, 0, final_obs, pool, pool_envs, reset_mask};
+  step_ctx ctx = {c, s, action, action_mode, evaluate, obs, reward, done, 0, final_obs, pool, pool_envs, reset_mask, 0};
   (void)N; (void)B;
   parallel_for(step_multi_body, &ctx, c->num_envs, nthreads);
   return 0;
@@ -826,8 +835,19 @@ int uavo_step_single(const uavca_config* c, uavo_state* s, const uavo_state* poo
                      int action_mode, double* obs, double* reward, uint8_t* done, float* distance, double* final_obs,
                      uint8_t* reset_mask, int nthreads) {
   const int B = c->num_envs;
-  step_ctx ctx = {c, s, action, action_mode, 0, obs, reward, done, distance, final_obs, pool, pool_envs, reset_mask};
+  step_ctx ctx = {c, s, action, action_mode, 0, obs, reward, done, distance, final_obs, pool, pool_envs, reset_mask, 0};
   parallel_for(step_single_body, &ctx, B, nthreads);
+  return 0;
+}
+
+/* Either world stepped with FLOAT64 cartesian actions (double [B][N][2]): what NumPy hands the reference's step() in its own
+ * training loops (test_sac_multi.py:77-80), consumed in float64 by uav_agent.py:26 / uav_world_2d.py:142. */
+int uavo_step_f64act(const uavca_config* c, uavo_state* s, const uavo_state* pool, int pool_envs, const double* action64,
+                     int evaluate, double* obs, double* reward, uint8_t* done, float* distance, double* final_obs,
+                     uint8_t* reset_mask, int nthreads) {
+  step_ctx ctx = {c, s, 0, UAVCA_ACTION_CARTESIAN, evaluate, obs, reward, done, distance, final_obs, pool, pool_envs, reset_mask,
+                  action64};
+  parallel_for(c->kind == UAVCA_KIND_SINGLE ? step_single_body : step_multi_body, &ctx, c->num_envs, nthreads);
   return 0;
 }
 

@@ -84,11 +84,14 @@ def test_cuda_matches_reference_golden(name):
     obs0 = env.observe().cpu().numpy()
     assert obs_close(obs0, z["obs0"], RTOL, ATOL).all()
     for t in range(case.T):
-        a = torch.from_numpy(z["action"][t]).cuda()
-        if case.kind == "single":
-            env.step(a)
+        if "action64" in z.files:  # f64act_*: float64 actions that float32 cannot hold, through uavca_step_f64
+            env.step_f64(torch.from_numpy(z["action64"][t]).cuda(), evaluate=case.evaluate)
         else:
-            env.step(a, evaluate=case.evaluate)
+            a = torch.from_numpy(z["action"][t]).cuda()
+            if case.kind == "single":
+                env.step(a)
+            else:
+                env.step(a, evaluate=case.evaluate)
         w = f"({name}, step {t})"
         assert np.array_equal(env.done.cpu().numpy(), z["done"][t]), f"done flags differ {w}"
         assert np.array_equal(env.reset_mask.cpu().numpy(), z["reset_mask"][t]), f"reset mask differs {w}"

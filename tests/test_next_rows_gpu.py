@@ -50,6 +50,51 @@ def test_compat_multi_runs_the_reference_loop_on_golden_vectors():
         env.close()
 
 
+def test_compat_keeps_float64_actions():
+    """The reference's SAC loop builds float64 cartesian actions on the host (test_sac_multi.py:77-80) and UAVAgent.step
+    consumes them in float64 (uav_agent.py:26): the drop-in hands them over unrounded (uavca_step_f64) — positions,
+    velocities and flags bit-exact against a golden run of the literal reference whose actions float32 cannot hold."""
+    from gym_uav_collision_avoidance_b200 import compat
+
+    case = Case("f64act_multi_n5")
+    z, N = case.z, case.N
+    assert (z["action64"] != z["action64"].astype(np.float32)).mean() > 0.5
+    for e in (0, 1):
+        env = compat.MultiUAVWorld2D(num_agents=N)
+        env.reset()
+        for i, ag in enumerate(env.agent_list):
+            ag.location, ag.target_location, ag.velocity = z["init_pos"][e, i], z["init_tgt"][e, i], z["init_vel"][e, i]
+            ag.init_distance, ag.prev_distance = z["init_init"][e, i], z["init_prev"][e, i]
+            ag.done, ag.collided = bool(z["init_flags"][e, i] & 1), bool(z["init_flags"][e, i] & 2)
+        env.steps = env.target_reach_count = env.collision_count = 0
+        for t in range(80):
+            if z["reset_mask"][t, e]:
+                break  # the golden harness restarts from its pool there
+            obs, rewards, dones, _ = env.step([z["action64"][t, e, i] for i in range(N)])
+            assert dones == [bool(d) for d in z["done"][t, e]], f"done flags env {e} step {t}"
+            assert np.array_equal(np.stack([a.location for a in env.agent_list]), z["pos"][t, e]), f"positions env {e} step {t}"
+            assert np.array_equal(np.stack([a.velocity for a in env.agent_list]), z["vel"][t, e]), f"velocities env {e} step {t}"
+            assert _close(rewards, z["reward"][t, e]).all()
+            assert obs_close(np.stack(obs), z["obs"][t, e], RTOL, ATOL).all()
+        assert t >= 20
+        env.close()
+    # the single world: float64 actions from the first step on
+    case = Case("f64act_single")
+    z = case.z
+    env = compat.UAVWorld2D()
+    env.reset()
+    env._agent_location, env._target_location = z["init_pos"][0, 0], z["init_tgt"][0, 0]
+    env._agent_speed, env._init_target_distance, env._prev_distance = z["init_vel"][0, 0], z["init_init"][0, 0], z["init_prev"][0, 0]
+    env.steps = 0
+    for t in range(60):
+        if z["reset_mask"][t, 0]:
+            break
+        obs, r, d, info = env.step(z["action64"][t, 0, 0])
+        assert bool(d) == bool(z["done"][t, 0, 0])
+        assert np.array_equal(env._agent_location, z["pos"][t, 0, 0]) and np.array_equal(env._agent_speed, z["vel"][t, 0, 0])
+    env.close()
+
+
 def test_compat_multi_surface():
     from gym_uav_collision_avoidance_b200 import compat
 
