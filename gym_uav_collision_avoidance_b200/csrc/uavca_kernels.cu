@@ -608,13 +608,12 @@ __global__ void __launch_bounds__(kThreads) step_single_kernel(const __grid_cons
   const long long b = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (b >= a.B) return;
   SingleEnv e = load_single(a.s, b);
-  bool rs;
-  if (a.io.action64 != nullptr) {
-    const double2 q = a.io.action64[b];
-    rs = step_single_core(a, b, b, e, make_float2(0.f, 0.f), &q);
-  } else {
-    rs = step_single_core(a, b, b, e, ld_stream(a.io.action + b));
-  }
+  double2 q = make_double2(0.0, 0.0);
+  float2 af = make_float2(0.f, 0.f);
+  const bool f64 = a.io.action64 != nullptr;  // uavca_step_f64 (kernel-uniform)
+  if (f64) q = a.io.action64[b];
+  else af = ld_stream(a.io.action + b);
+  const bool rs = step_single_core(a, b, b, e, af, f64 ? &q : nullptr);
   store_single(a.s, b, e, rs);
 }
 

@@ -7,8 +7,8 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q > gpurun_out/${tag}_tests.log 2>&1; echo "tests rc=$?" | tee -a gpurun_out/${tag}_tests.log
 tail -4 gpurun_out/${tag}_tests.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -1 gpurun_out/${tag}_smoke.log
-python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/${tag}_ref_c3.json 2> gpurun_out/${tag}_ref_c3.err
-python bench.py > gpurun_out/${tag}_bench_c3.json 2> gpurun_out/${tag}_bench_c3.err; echo "bench rc=$?"; tail -2 gpurun_out/${tag}_bench_c3.err
+t0=$(date +%s); python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/${tag}_ref_c3.json 2> gpurun_out/${tag}_ref_c3.err; echo "reference arm wall=$(( $(date +%s) - t0 )) s"
+t0=$(date +%s); python bench.py > gpurun_out/${tag}_bench_c3.json 2> gpurun_out/${tag}_bench_c3.err; echo "bench rc=$? wall=$(( $(date +%s) - t0 )) s"; tail -2 gpurun_out/${tag}_bench_c3.err
 python bench.py --steps 20 --warmup 3 --no-acting --no-cpu-baseline > gpurun_out/${tag}_bench_c3_k20.json 2>/dev/null
 for w in c4 c2 c5; do python bench.py --workload $w --no-cpu-baseline > gpurun_out/${tag}_bench_$w.json 2>/dev/null; done
 python bench.py --workload c1 > gpurun_out/${tag}_bench_c1.json 2>/dev/null
@@ -34,6 +34,8 @@ cap ${tag}_full_step_n8 step_multi_kernel 30 python tools/quick_time.py 8 65536 
 cap ${tag}_full_step_n32 step_multi_kernel 10 python tools/quick_time.py 32 131072 200
 cap ${tag}_full_rollout_single rollout_single 2 python tools/rollout_time.py single 1 65536 64 block 3
 cap ${tag}_full_policy policy_act 3 python tools/policy_bench.py
+cap ${tag}_full_step_ring_n10 step_multi_ring 6 python tools/rollout_bench.py 16384 10 100 fused
+rm -f gpurun_out/${tag}_full_step_ring_n10.ncu-rep
 rm -f gpurun_out/${tag}_full_rollout_n8.ncu-rep gpurun_out/${tag}_full_step_n8.ncu-rep gpurun_out/${tag}_full_rollout_single.ncu-rep gpurun_out/${tag}_full_policy.ncu-rep
 ls gpurun_out | head -60
 echo done
