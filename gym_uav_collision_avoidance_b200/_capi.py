@@ -71,6 +71,7 @@ SYMBOLS = {
     "uavca_step_multi": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP]),
     "uavca_step_single": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "uavca_step_f64": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "uavca_step_sync": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "uavca_map_action": (C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     "uavca_stats": (C.c_int, [_VP, _VP, _VP, _VP]),
     "uavca_step_host": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),

@@ -43,6 +43,14 @@ def register_gym_ids() -> bool:
     return False
 
 
+def _raw_stream(device) -> int:
+    """torch's current stream on `device` as a cudaStream_t (the raw getter costs a fifth of building a Stream object)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device())
+    except AttributeError:
+        return torch.cuda.current_stream(device).cuda_stream
+
+
 class _HostIO:
     """Pinned host tensors the B=1 step reads its action from and writes obs / reward / done into directly (mapped host
     memory: the kernel's loads and stores go through PCIe, one launch + one stream synchronisation per step, no copies)."""
@@ -55,31 +63,27 @@ class _HostIO:
         self.action64 = pin(1, N, 2, dtype=torch.float64)
         self.np = {k: getattr(self, k).numpy() for k in ("action", "action64", "obs", "reward", "done", "distance")}
         self.ptr = {k: getattr(self, k).data_ptr() for k in ("action", "action64", "obs", "reward", "done", "mask", "distance")}
+        self._step_sync = b._lib.uavca_step_sync
+        self._single = b.kind == 1  # UAVCA_KIND_SINGLE: `distance` is an output
 
     def step(self, b, n_action, evaluate=False):
-        from . import _capi
-
+        """One `env.step`: the action into the mapped buffer of its dtype, ONE C call that launches the step and waits for
+        the stream (`uavca_step_sync`), results readable in the mapped output buffers."""
         n_action = np.asarray(n_action)
-        p, st = self.ptr, torch.cuda.current_stream(b.device)
-        if n_action.dtype != np.float32:
+        p = self.ptr
+        f64 = n_action.dtype != np.float32
+        if f64:
             # what the reference's loops hand env.step(): python floats / float64 arrays (test_sac_multi.py:77-80), consumed in
-            # float64 by UAVAgent.step (uav_agent.py:26) — uavca_step_f64 keeps every bit of them
-            self.np["action64"][...] = n_action.astype(np.float64).reshape(1, b.num_agents, 2)
-            rc = b._lib.uavca_step_f64(b._h, b.state.blob.data_ptr(), p["action64"], int(bool(evaluate)), p["obs"], p["reward"],
-                                       p["done"], p["distance"] if b.kind == _capi.KIND_SINGLE else None, None, p["mask"],
-                                       st.cuda_stream)
-            _capi.check(rc, "uavca_step_f64")
-            st.synchronize()
-            return self.np
-        self.np["action"][...] = n_action.reshape(1, b.num_agents, 2)
-        if b.kind == _capi.KIND_SINGLE:
-            rc = b._lib.uavca_step_single(b._h, b.state.blob.data_ptr(), p["action"], 0, p["obs"], p["reward"], p["done"],
-                                          p["distance"], None, p["mask"], st.cuda_stream)
+            # float64 by UAVAgent.step (uav_agent.py:26) — kept unrounded
+            self.np["action64"][...] = n_action.reshape(1, b.num_agents, 2)
         else:
-            rc = b._lib.uavca_step_multi(b._h, b.state.blob.data_ptr(), p["action"], 0, int(bool(evaluate)), p["obs"], p["reward"],
-                                         p["done"], None, p["mask"], st.cuda_stream)
-        _capi.check(rc, "uavca_step")
-        st.synchronize()
+            self.np["action"][...] = n_action.reshape(1, b.num_agents, 2)
+        rc = self._step_sync(b._h, b.state.blob.data_ptr(), p["action64"] if f64 else p["action"], int(f64), 0, int(bool(evaluate)), p["obs"],
+                             p["reward"], p["done"], p["distance"] if self._single else None, None, p["mask"], _raw_stream(b.device))
+        if rc:
+            from . import _capi
+
+            _capi.check(rc, "uavca_step_sync")
         return self.np
 
 

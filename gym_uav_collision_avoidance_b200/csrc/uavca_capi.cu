@@ -463,6 +463,23 @@ int uavca_step_f64(uavca_handle* h, void* state, const double* action, int evalu
   return 0;
 }
 
+int uavca_step_sync(uavca_handle* h, void* state, const void* action, int action_is_f64, int action_mode, int evaluate, float* obs,
+                    float* reward, uint8_t* done, float* distance, float* final_obs, uint8_t* reset_mask, void* stream) {
+  if (int rc = check_handle(h)) return rc;
+  int rc;
+  if (action_is_f64)
+    rc = uavca_step_f64(h, state, static_cast<const double*>(action), evaluate, obs, reward, done, distance, final_obs, reset_mask, stream);
+  else if (h->cfg.kind == UAVCA_KIND_SINGLE)
+    rc = uavca_step_single(h, state, static_cast<const float*>(action), action_mode, obs, reward, done, distance, final_obs, reset_mask, stream);
+  else
+    rc = uavca_step_multi(h, state, static_cast<const float*>(action), action_mode, evaluate, obs, reward, done, final_obs, reset_mask, stream);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_step_sync", e);
+  return 0;
+}
+
 int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* out, void* stream) {
   if (int rc = check_handle(h)) return rc;
   if (!in || !out) return fail(-1, "null argument");

@@ -166,6 +166,13 @@ int uavca_step_single(uavca_handle* h, void* state, const float* action, int act
 int uavca_step_f64(uavca_handle* h, void* state, const double* action, int evaluate, float* obs, float* reward, uint8_t* done,
                    float* distance, float* final_obs, uint8_t* reset_mask, void* stream);
 
+/* The gym call as the reference makes it — `obs, reward, done, info = env.step(action)` returns values (multi_uav_world_2d.py:241,
+ * uav_world_2d.py:173): one of the three steps above (action: float [B][N][2], or double when action_is_f64) followed by a
+ * wait for `stream`, in ONE call.  With obs / reward / done / distance in mapped pinned host memory the results are readable
+ * when it returns; this is what the B=1 drop-in classes call once per step (compat.py). */
+int uavca_step_sync(uavca_handle* h, void* state, const void* action, int action_is_f64, int action_mode, int evaluate, float* obs,
+                    float* reward, uint8_t* done, float* distance, float* final_obs, uint8_t* reset_mask, void* stream);
+
 /* The caller-side action mapping on its own: in/out float [B][N][2]. */
 int uavca_map_action(uavca_handle* h, const float* in, int action_mode, float* out, void* stream);
 
