@@ -291,8 +291,8 @@ class _BatchedBase:
     def step_f64(self, action: torch.Tensor, evaluate: bool = False):
         """`step()` fed FLOAT64 cartesian actions ([B,N,2] float64 CUDA; [B,2] / [B,1,2] for the single world) — what the
         reference's own loops build on the host (test_sac_multi.py:77-80) and `UAVAgent.step` consumes in float64
-        (uav_agent.py:26).  Bit-exact for actions float32 cannot hold; runs on the general one-thread-per-env kernel (the
-        drop-in path: `compat.py` uses it), the float32 `step()` is the throughput path."""
+        (uav_agent.py:26).  Bit-exact for actions float32 cannot hold; same kernels as `step()` (`compat.py` uses it for
+        python floats / float64 arrays)."""
         B, N = self.num_envs, self.num_agents
         action = action.to(device=self.device, dtype=torch.float64).contiguous()
         if action.numel() != B * N * 2:

@@ -66,6 +66,26 @@ struct GlobalIO {
   }
 };
 
+// The same I/O with FLOAT64 cartesian actions (uavca_step_f64): what the reference's own loops hand env.step().
+struct GlobalIO64 : GlobalIO {
+  static constexpr bool kAction64 = true;
+  __device__ __forceinline__ GlobalIO64(const KernelArgs& a_, const Lane& L_, float* stage_) : GlobalIO{a_, L_, stage_} {}
+  __device__ __forceinline__ double2 load_action64() const {
+    return L.valid ? ld_stream(a.io.action64 + L.m) : make_double2(0.0, 0.0);
+  }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_f64_kernel(const __grid_constant__ KernelArgs a) {
+  __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
+  const WarpScratch ws = warp_scratch(smem);
+  const int warp_global = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  cudaGridDependencySynchronize();
+  const Lane L = make_lane<NT, false>(a.B, a.N, warp_global);
+  GlobalIO64 io(a, L, ws.stage);
+  step_core<NT>(a, ws, L, io);
+}
+
 template <int NT>
 __global__ void __launch_bounds__(kThreads, kMinBlocksPerSM) step_multi_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ __align__(16) float smem[kWarpsPerBlock * kScratchFloats];
@@ -893,7 +913,22 @@ static cudaError_t launch_step_pf_n(const KernelArgs& a, int num_tiles, cudaStre
 
 
 // the general one-thread-per-env kernels (uavca_seq.cuh) serve the float64 world and envs wider than a warp
-static inline bool wants_seq(const KernelArgs& a) { return a.c.circular != 0 || a.N > 32 || a.io.action64 != nullptr; }
+static inline bool wants_seq(const KernelArgs& a) { return a.c.circular != 0 || a.N > 32; }
+
+template <int NT>
+static cudaError_t launch_step_multi_f64_n(const KernelArgs& a, int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, step_multi_f64_kernel<NT>, a);
+}
 
 cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launched, int path) {
   if (launched) *launched = 0;
@@ -902,6 +937,12 @@ cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launche
   if (wants_seq(a)) {
     if (a.c.circular) step_multi_seq_kernel<double><<<flat_grid(a.B), kThreads, 0, st>>>(a);
     else step_multi_seq_kernel<float><<<flat_grid(a.B), kThreads, 0, st>>>(a);
+    if (launched) *launched = 1;
+    return cudaGetLastError();
+  }
+  if (a.io.action64 != nullptr) {  // float64 actions: the warp kernel fed by GlobalIO64
+    UAVCA_DISPATCH_N(a.N, (e = launch_step_multi_f64_n<NT>(a, multi_grid(a.B, a.N), st)));
+    if (e != cudaSuccess) return e;
     if (launched) *launched = 1;
     return cudaGetLastError();
   }

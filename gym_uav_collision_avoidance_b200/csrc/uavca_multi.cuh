@@ -645,15 +645,28 @@ static __device__ __forceinline__ double2 finish_velocity(double vx, double vy, 
   return make_double2(fx, fy);
 }
 
+// An I/O policy that declares `static constexpr bool kAction64 = true` hands the step FLOAT64 cartesian actions
+// (`double2 load_action64()`, uavca_step_f64) instead of float32 ones; everything else in step_core is the same code.
+template <class IO, class = void>
+struct io_action64 { static constexpr bool value = false; };
+template <class IO>
+struct io_action64<IO, decltype((void)IO::kAction64)> { static constexpr bool value = IO::kAction64; };
+
 template <int NT, class IO>
 __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch& ws, const Lane& L, IO& io) {
   const Consts& c = a.c;
+  constexpr bool kF64 = io_action64<IO>::value;
 
   Uav u = io.load_uav();
-  float2 act = io.load_action();
+  float2 act = make_float2(0.f, 0.f);
+  double2 act64 = make_double2(0.0, 0.0);
+  if constexpr (kF64) act64 = io.load_action64();
+  else act = io.load_action();
   const int steps_new = io.load_steps() + 1;  // multi_uav_world_2d.py:238
   io.loads_done();
-  if (a.io.action_mode != UAVCA_ACTION_CARTESIAN) act = map_action(act, a.io.action_mode, c);
+  if constexpr (!kF64) {
+    if (a.io.action_mode != UAVCA_ACTION_CARTESIAN) act = map_action(act, a.io.action_mode, c);
+  }
 
   const bool parked = (u.flags & UAVCA_FLAG_PARKED) != 0u;
   const float ox = u.px, oy = u.py;  // position before this step
@@ -662,7 +675,8 @@ __device__ __forceinline__ void step_core(const KernelArgs& a, const WarpScratch
   {
     double vx = u.vx, vy = u.vy;
     float px = u.px, py = u.py;
-    integrate((double)act.x, (double)act.y, vx, vy, px, py, c);
+    if constexpr (kF64) integrate(act64.x, act64.y, vx, vy, px, py, c);
+    else integrate((double)act.x, (double)act.y, vx, vy, px, py, c);
     if (!parked) { u.vx = vx; u.vy = vy; u.px = px; u.py = py; }
   }
   // heading, heading error to the target, distance, |v|^2 (multi_uav_world_2d.py:184-186)

@@ -161,8 +161,9 @@ int uavca_step_single(uavca_handle* h, void* state, const float* action, int act
 /* env.step() fed FLOAT64 cartesian actions — what the reference's own loops hand it: NumPy float64 arrays built on the
  * host (test_sac_multi.py:77-80, run.py:13), which `UAVAgent.step` consumes in float64 (uav_agent.py:26; uav_world_2d.py:142).
  * action: double [B][N][2] ([B][2] for the single world).  Serves both kinds (distance: single world only, nullable;
- * evaluate: multi world only).  Runs on the general one-thread-per-env kernel: the drop-in path (compat.py), bit-exact
- * for actions that float32 cannot hold; the batched float32 entry points above are the throughput path. */
+ * evaluate: multi world only).  Bit-exact for actions that float32 cannot hold.  Same kernels as the float32 entry points
+ * (the warp kernel up to 32 UAVs per env, the general kernel beyond and in the float64 world); no action mapping: the
+ * policy-space modes exist for float32 device policies. */
 int uavca_step_f64(uavca_handle* h, void* state, const double* action, int evaluate, float* obs, float* reward, uint8_t* done,
                    float* distance, float* final_obs, uint8_t* reset_mask, void* stream);
 

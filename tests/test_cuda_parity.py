@@ -111,6 +111,26 @@ def test_cuda_matches_reference_golden(name):
         assert obs_close(env.final_obs.cpu().numpy(), case.final_obs(t), RTOL, ATOL).all(), f"final obs {w}"
 
 
+@pytest.mark.parametrize("N,circular", [(5, False), (32, False), (40, False), (6, True)])
+def test_float64_actions_that_float32_holds_step_like_float32_actions(N, circular):
+    """uavca_step_f64 on every kernel that serves it (warp kernel, general kernel for N > 32 and for the float64 world):
+    float64 actions whose values float32 holds exactly must give the very state the float32 entry point gives."""
+    G = _b200()
+    B = 64
+    kw = dict(num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=40, seed=17, circular=circular)
+    e32, e64 = G.BatchedMultiUAVWorld2D(B, **kw), G.BatchedMultiUAVWorld2D(B, **kw)
+    e32.reset(); e64.reset()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for t in range(120):
+        a = (torch.rand((B, N, 2), generator=gen, device="cuda") * 20 - 10)
+        e32.step(a)
+        e64.step_f64(a.double())
+        assert torch.equal(e32.state.blob, e64.state.blob), f"state differs at step {t}"
+        assert torch.equal(e32.done, e64.done) and torch.equal(e32.reset_mask, e64.reset_mask)
+        assert torch.equal(e32.obs, e64.obs) and torch.equal(e32.reward, e64.reward)
+    assert e32.stats()["episodes"] > 0
+
+
 # ---- rollouts against the oracle, with Philox auto-reset on both sides ----------------------------------------
 
 
