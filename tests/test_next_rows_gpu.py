@@ -291,6 +291,46 @@ def test_step_with_the_replay_append_folded_in_equals_step_then_push(N, B):
     assert envs[0].stats()["episodes"] > 0
 
 
+def test_step_replay_and_push_share_one_ring():
+    """uavca_step_multi_replay and uavca_replay_push_dev keep the ring head the same way: mixed on ONE ring (a second env
+    appending with push between the first env's fused steps) they produce what push alone produces."""
+    import gym_uav_collision_avoidance_b200 as G
+
+    B, N = 48, 5
+    M = B * N
+    kw = dict(num_agents=N, reset_mode=G.RESET_ON_DONE0, max_episode_steps=30, seed=3)
+    cap = 7 * M + 11
+
+    def run(fused):
+        a_env, b_env = G.BatchedMultiUAVWorld2D(B, **kw), G.BatchedMultiUAVWorld2D(B, **dict(kw, seed=4))
+        ring = G.DeviceReplay(cap, 10, 2, seed=0)
+        b_env.enable_final_obs()
+        if not fused:
+            a_env.enable_final_obs()
+        a_env.reset(); b_env.reset()
+        spare = torch.zeros_like(a_env.obs)
+        gen = torch.Generator(device="cuda").manual_seed(8)
+        for _ in range(25):
+            act = torch.rand((B, N, 2), generator=gen, device="cuda") * 2 - 1
+            prev = a_env.obs
+            a_env.set_obs_buffer(spare)
+            if fused:
+                a_env.step_replay(act, prev, ring, action_mode="polar")
+            else:
+                a_env.step(act, action_mode="polar")
+                ring.push(prev, act, a_env.reward, a_env.final_obs, a_env.done)
+            spare = prev
+            prev_b = b_env.obs.clone()
+            b_env.step(act, action_mode="scaled")
+            ring.push(prev_b, act, b_env.reward, b_env.final_obs, b_env.done)
+        return ring
+
+    r0, r1 = run(True), run(False)
+    assert torch.equal(r0.meta, r1.meta) and r0.size == cap and int(r0.meta[3]) == 50
+    for name in ("state", "action", "reward", "next_state", "mask"):
+        assert torch.equal(getattr(r0, name), getattr(r1, name)), name
+
+
 def test_step_with_the_replay_append_replays_from_a_cuda_graph():
     """A captured acting step (uniform actions, fused append) appends where the previous replay stopped."""
     import gym_uav_collision_avoidance_b200 as G
