@@ -198,6 +198,7 @@ struct uavca_handle {
   cudaEvent_t chunk_done[kChunks] = {};
   cudaEvent_t fork = nullptr;  // uavca_step_host: orders the internal streams after the caller's stream
   float* d_action = nullptr;
+  float* d_rollout_action = nullptr;  // uavca_rollout on the general kernel: one step's Philox actions (created lazily)
   float* d_obs = nullptr;
   float* d_reward = nullptr;
   uint8_t* d_done = nullptr;
@@ -331,6 +332,7 @@ int uavca_destroy(uavca_handle* h) {
   for (auto& ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
   if (h->fork) cudaEventDestroy(h->fork);
   if (h->d_action) cudaFree(h->d_action);
+  if (h->d_rollout_action) cudaFree(h->d_rollout_action);
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_reward) cudaFree(h->d_reward);
   if (h->d_done) cudaFree(h->d_done);
@@ -651,9 +653,41 @@ int uavca_rollout(uavca_handle* h, void* state, int32_t K, const float* action_b
   if (action_mode < 0 || action_mode > 2) return fail(-1, "bad action_mode");
   if (h->cfg.reset_mode && h->cfg.reset_source == UAVCA_SOURCE_POOL && !h->pool_blob) return fail(-1, "reset_source is POOL but no pool is set");
   const bool single = h->cfg.kind == UAVCA_KIND_SINGLE;
-  if (!single && (h->cfg.circular || h->cfg.num_agents > 32))
-    return fail(-1, "uavca_rollout serves the warp kernels (num_agents <= 32, float32 world); step circular / larger envs one at a time");
   const long long M = (long long)h->cfg.num_envs * h->cfg.num_agents;
+  if (!single && (h->cfg.circular || h->cfg.num_agents > 32)) {
+    // The float64 world and envs wider than a warp run on the general one-thread-per-env kernel, which has no K loop: the
+    // same call, K launches on the stream, every step's outputs at their [k] offsets (not a throughput path).
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!action_block && !action_out && !h->d_rollout_action) {
+      cudaError_t e = cudaMalloc(&h->d_rollout_action, (size_t)M * 2 * sizeof(float));
+      if (e != cudaSuccess) return fail_cuda("uavca_rollout (action scratch)", e);
+    }
+    KernelArgs a = make_args(h, state);
+    a.io.evaluate = evaluate;
+    a.io.action_mode = (action_block == nullptr && action_mode == UAVCA_ACTION_CARTESIAN) ? UAVCA_ACTION_SCALED : action_mode;
+    for (int32_t k = 0; k < K; ++k) {
+      const float* act_k = action_block ? action_block + (size_t)k * M * 2 : nullptr;
+      if (!act_k) {
+        float* dst = action_out ? action_out + (size_t)k * M * 2 : h->d_rollout_action;
+        cudaError_t e = launch_sample_actions(h->consts, dst, h->cfg.num_envs, h->cfg.num_agents, action_seed, step0 + (uint64_t)k, st);
+        if (e != cudaSuccess) return fail_cuda("uavca_rollout (actions)", e);
+        h->launches += 1;
+        act_k = dst;
+      }
+      a.io.action = reinterpret_cast<const float2*>(act_k);
+      a.io.obs = obs + (size_t)k * M * UAVCA_OBS_DIM_MULTI;
+      a.io.reward = reward + (size_t)k * M;
+      a.io.done = done + (size_t)k * M;
+      a.io.final_obs = final_obs ? final_obs + (size_t)k * M * UAVCA_OBS_DIM_MULTI : nullptr;
+      a.io.reset_mask = reset_mask ? reset_mask + (size_t)k * h->cfg.num_envs : nullptr;
+      int launched = 0;
+      cudaError_t e = launch_step_multi(a, st, &launched, h->path);
+      h->launches += launched;
+      if (e != cudaSuccess) return fail_cuda("uavca_rollout", e);
+    }
+    return 0;
+  }
   // the [K][...] blocks must keep every step's rows aligned for the 16-byte observation stores
   if (!single && (M * UAVCA_OBS_DIM_MULTI * sizeof(float)) % 16 != 0 && K > 1)
     return fail(-1, "uavca_rollout: num_envs * num_agents * 10 floats must be a multiple of 16 bytes for K > 1");

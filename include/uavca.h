@@ -199,7 +199,8 @@ int uavca_step_host(uavca_handle* h, void* state, const float* host_action, int 
  * actions in [-1,1)^2 from Philox4x32-10 keyed by (action_seed, global env index, UAV, step0 + k) and mapped by
  * `action_mode` (UAVCA_ACTION_CARTESIAN then means a * max_speed: action_space.sample()); action_out (nullable)
  * float [K][B][N][2] receives the draws.  Results are bit-identical to K calls of uavca_step_* fed the same actions
- * (uavca_sample_actions reproduces the draws of one step).  K > 1 needs B*N*obs_dim*4 to be a multiple of 16. */
+ * (uavca_sample_actions reproduces the draws of one step).  K > 1 needs B*N*obs_dim*4 to be a multiple of 16.  The float64
+ * world and envs of more than 32 UAVs run on the general kernel, which has no K loop: same call, same results, K launches. */
 int uavca_rollout(uavca_handle* h, void* state, int32_t K, const float* action_block, int action_mode, int evaluate,
                   uint64_t action_seed, uint64_t step0, float* obs, float* reward, uint8_t* done, float* action_out,
                   float* final_obs, uint8_t* reset_mask, float* distance, void* stream);

@@ -88,6 +88,32 @@ def test_rollout_with_philox_actions(n, mode):
     assert float(a.min()) >= -1.0 and float(a.max()) < 1.0 and abs(float(a.mean())) < 0.01
 
 
+@pytest.mark.parametrize("n,circular", [(40, False), (6, True), (33, False)])
+def test_rollout_on_the_general_kernel(n, circular):
+    """Envs wider than a warp and the float64 world: uavca_rollout is the same call (K launches inside), bit-identical to K
+    single steps — with an action block and with the Philox stream."""
+    G = _b200()
+    B, K = 64, 12
+    kw = dict(num_agents=n, reset_mode=O.RESET_ON_DONE0, max_episode_steps=9, seed=70 + n, circular=circular)
+    e1, e2, e3, e4 = (G.BatchedMultiUAVWorld2D(B, **kw) for _ in range(4))
+    for e in (e1, e2, e3, e4):
+        e.reset()
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    acts = torch.rand((K, B, n, 2), generator=gen, device="cuda") * 20 - 10
+    out = e1.rollout(K, acts, want_final_obs=True, want_reset_mask=True)
+    e2.enable_final_obs()
+    for k in range(K):
+        o, r, d, info = e2.step(acts[k])
+        assert torch.equal(out["obs"][k], o) and torch.equal(out["reward"][k], r) and torch.equal(out["done"][k], d), k
+        assert torch.equal(out["reset_mask"][k], info["reset_mask"]) and torch.equal(out["final_obs"][k], info["final_obs"])
+    assert torch.equal(e1.state.blob, e2.state.blob) and int(out["reset_mask"].sum()) >= B
+    out = e3.rollout(K, None, action_mode="polar", action_seed=5, step0=3)  # no action_out: the handle's scratch
+    for k in range(K):
+        o, r, d, _ = e4.step(e4.sample_actions(3 + k, 5), action_mode="polar")
+        assert torch.equal(out["obs"][k], o) and torch.equal(out["reward"][k], r) and torch.equal(out["done"][k], d), k
+    assert torch.equal(e3.state.blob, e4.state.blob)
+
+
 @pytest.mark.parametrize("f32", [False, True])
 def test_rollout_single_world(f32):
     B, K = 4097, 60
