@@ -7,6 +7,7 @@ structure-of-arrays state blob in HBM.  All inputs and outputs are CUDA tensors;
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -522,3 +523,29 @@ class BatchedUAVWorld2D(_BatchedBase):
         if self.final_obs is not None:
             info["final_obs"] = self.final_obs
         return self.obs, self.reward, self.done, info
+
+
+# ---- NVTX ranges (tracing).  Off by default and free when off: with UAVCA_NVTX=1 in the environment the entry
+# points of the batched classes are wrapped once, at import, in `torch.cuda.nvtx` ranges named after the reference call
+# they replace, so a timeline (nsys / ncu --nvtx) shows env.step / env.reset / rollout as named spans around the kernels.
+def _nvtx_wrap(cls, name, label):
+    import functools
+
+    fn = getattr(cls, name)
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kw):
+        torch.cuda.nvtx.range_push(label)
+        try:
+            return fn(self, *args, **kw)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    setattr(cls, name, wrapped)
+
+
+if os.environ.get("UAVCA_NVTX", "0") not in ("", "0"):
+    for _cls, _tag in ((BatchedMultiUAVWorld2D, "MultiUAVWorld2D"), (BatchedUAVWorld2D, "UAVWorld2D")):
+        for _name in ("step", "step_f64", "step_host", "reset", "observe", "rollout", "stats"):
+            _nvtx_wrap(_cls, _name, f"uavca:{_tag}.{_name}")
+    _nvtx_wrap(BatchedMultiUAVWorld2D, "step_replay", "uavca:MultiUAVWorld2D.step+memory.push")

@@ -137,3 +137,19 @@ def test_register_gym_ids_against_a_stub_gym(monkeypatch):
         mod, cls = entry.split(":")
         klass = getattr(importlib.import_module(mod), cls)
         assert "max_speed" in inspect.signature(klass.__init__).parameters
+
+
+def test_nvtx_ranges_are_opt_in():
+    """UAVCA_NVTX=1 wraps the batched entry points in named NVTX ranges at import (tracing); unset, the methods
+    are the plain ones."""
+    import subprocess
+    import sys
+
+    code = ("import gym_uav_collision_avoidance_b200.batched as b; "
+            "print(hasattr(b.BatchedMultiUAVWorld2D.step, '__wrapped__'), hasattr(b.BatchedUAVWorld2D.rollout, '__wrapped__'))")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    on = subprocess.run([sys.executable, "-c", code], env=dict(env, UAVCA_NVTX="1"), capture_output=True, text=True, timeout=300)
+    off = subprocess.run([sys.executable, "-c", code], env={k: v for k, v in env.items() if k != "UAVCA_NVTX"},
+                         capture_output=True, text=True, timeout=300)
+    assert on.stdout.split() == ["True", "True"], on.stderr[-500:]
+    assert off.stdout.split() == ["False", "False"], off.stderr[-500:]
