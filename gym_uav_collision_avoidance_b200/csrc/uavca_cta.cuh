@@ -50,36 +50,18 @@ __device__ __forceinline__ void cta_flush_rows(const float* stage, float* g, int
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 6) step_multi_cta_kernel(const __grid_constant__ KernelArgs a) {
-  __shared__ __align__(16) CtaShared sh;
+// One step of the CTA's envs.  `u` is this thread's UAV (in registers), `act` its action of this step, `row0` the offset of
+// this step's rows in the per-UAV outputs (0, or k * B * N inside a rollout), `env0` the same for the per-env output.
+// ROLL: the state stays in registers between the K steps of a launch (the caller stores it once, at the end).
+template <bool ROLL>
+__device__ __forceinline__ void cta_step(const KernelArgs& a, CtaShared& sh, const Lane& L, int e, int envs_here, Uav& u,
+                                         float2 act, size_t row0, size_t env0) {
   const Consts& c = a.c;
   const int N = a.N;
-  const int E = kThreads / N;  // envs per CTA
   const int t = threadIdx.x;
-  const int e = t / N;
-  Lane L;
-  L.N = N;
-  L.lanes_used = E * N;
-  L.lane = t;                  // index into the CTA's cand / th / stage arrays
-  L.i = t - e * N;
-  L.base = e * N;
-  L.ring = e * (N + 1);
-  L.envmask = (1u << N) - 1u;  // N <= 31
-  L.env = blockIdx.x * E + e;
-  L.warp_m0 = blockIdx.x * E * N;  // first UAV of the CTA
-  const int envs_here = min(E, a.B - blockIdx.x * E);
-  L.valid_lanes = envs_here * N;
-  L.valid = t < L.valid_lanes;
-  L.m = L.warp_m0 + t;
-  if (!L.valid) { L.base = 0; L.ring = 0; L.i = 0; }  // idle threads shadow UAV 0 of the CTA's first env and never store
   const WarpScratch ws{sh.pairs, sh.cand, sh.th, sh.stage};
   const bool leader = L.valid & (L.i == 0);
-
-  cudaGridDependencySynchronize();
-  Uav u = load_uav(a.s, L);
-  float2 act = L.valid ? ld_stream(a.io.action + L.m) : make_float2(0.f, 0.f);
   const int steps_new = (L.valid ? a.s.steps[L.env] : 0) + 1;
-  cudaTriggerProgrammaticLaunchCompletion();
   if (t < kCtaMaxEnvs) { sh.done_bits[t] = 0u; sh.reach_inc[t] = 0; sh.coll_inc[t] = 0; }
   if (t == 0) sh.bad = 0u;
   if (a.io.action_mode != UAVCA_ACTION_CARTESIAN) act = map_action(act, a.io.action_mode, c);
@@ -152,8 +134,8 @@ __global__ void __launch_bounds__(kThreads, 6) step_multi_cta_kernel(const __gri
     stage_neighbours(sh.stage, t, tail);
   }
   if (L.valid) {
-    st_stream(a.io.reward + L.m, r);
-    st_stream(a.io.done + L.m, (uint8_t)done);
+    st_stream(a.io.reward + row0 + L.m, r);
+    st_stream(a.io.done + row0 + L.m, (uint8_t)done);
   }
   const bool bad = (!(fabsf(r) <= 3.4e38f) | !(fabsf(u.px) + fabsf(u.py) <= 3.4e38f)) & L.valid;
   if (done) atomicOr(&sh.done_bits[e], 1u << L.i);
@@ -169,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 6) step_multi_cta_kernel(const __gri
                    (steps_new >= c.steps_limit)) & L.valid;
   unsigned episode = 0;
   if (leader) {
-    if (a.io.reset_mask) a.io.reset_mask[L.env] = (uint8_t)rs;
+    if (a.io.reset_mask) a.io.reset_mask[env0 + L.env] = (uint8_t)rs;
     if (c.track_scores) {
       // the same pairwise order as env_sum of the warp kernels (offsets 1, 2, 4, 8, 16), so both give the same float
       float* v = sh.live + L.base;
@@ -202,25 +184,25 @@ __global__ void __launch_bounds__(kThreads, 6) step_multi_cta_kernel(const __gri
   }
   if (leader) sh.reset_env[e] = rs;
   if (t == 0 && sh.bad) atomicAdd(a.s.stats + 6, (unsigned long long)sh.bad);
-  float* const g_obs = a.io.obs + (size_t)L.warp_m0 * UAVCA_OBS_DIM_MULTI;
+  float* const g_obs = a.io.obs + (row0 + (size_t)L.warp_m0) * UAVCA_OBS_DIM_MULTI;
   const bool aligned16 = ((L.lanes_used * (int)blockIdx.x) & 1) == 0;  // this CTA's first row starts on a 16-byte boundary
-  if (a.io.final_obs) cta_flush_rows(sh.stage, a.io.final_obs + (size_t)L.warp_m0 * UAVCA_OBS_DIM_MULTI, L.valid_lanes, aligned16);
+  if (a.io.final_obs) cta_flush_rows(sh.stage, a.io.final_obs + (row0 + (size_t)L.warp_m0) * UAVCA_OBS_DIM_MULTI, L.valid_lanes, aligned16);
 
   if (!__syncthreads_or(rs)) {  // nobody resets: the common case
     cta_flush_rows(sh.stage, g_obs, L.valid_lanes, aligned16);
-    store_uav(a.s, L, u, false);
+    if (!ROLL) store_uav(a.s, L, u, false);
     return;
   }
 
   // ---- rare: some env of this CTA starts a new episode in place.  Warp w replays the reference's reset for envs
   // w, w + 4 of the CTA (lane i = UAV i) and writes the new state; the barrier makes it visible to the env's own threads.
-  if (!rs) store_uav(a.s, L, u, false);
+  if (!ROLL && !rs) store_uav(a.s, L, u, false);
   for (int e2 = t >> 5; e2 < envs_here; e2 += kWarpsPerBlock) {
     if (!sh.reset_env[e2]) continue;  // warp-uniform
     const int ln = t & 31;
     Lane R;
     R.N = N; R.lanes_used = N; R.lane = ln; R.valid = ln < N; R.i = R.valid ? ln : 0; R.base = 0; R.ring = 0;
-    R.envmask = L.envmask; R.env = blockIdx.x * E + e2; R.warp_m0 = R.env * N; R.valid_lanes = N; R.m = R.warp_m0 + ln;
+    R.envmask = L.envmask; R.env = blockIdx.x * (kThreads / N) + e2; R.warp_m0 = R.env * N; R.valid_lanes = N; R.m = R.warp_m0 + ln;
     Uav nu = u;
     reset_multi(a, R, R.valid, sh.episode[e2], nu);
     store_uav(a.s, R, nu, true);
@@ -245,6 +227,69 @@ __global__ void __launch_bounds__(kThreads, 6) step_multi_cta_kernel(const __gri
   }
   __syncthreads();
   cta_flush_rows(sh.stage, g_obs, L.valid_lanes, aligned16);
+}
+
+// this thread's place in the CTA's packing: env e = t / N of the CTA, UAV t - e N
+__device__ __forceinline__ Lane cta_lane(const KernelArgs& a, int& e, int& envs_here) {
+  const int N = a.N;
+  const int E = kThreads / N;  // envs per CTA
+  const int t = threadIdx.x;
+  e = t / N;
+  Lane L;
+  L.N = N;
+  L.lanes_used = E * N;
+  L.lane = t;                  // index into the CTA's cand / th / stage arrays
+  L.i = t - e * N;
+  L.base = e * N;
+  L.ring = e * (N + 1);
+  L.envmask = (1u << N) - 1u;  // N <= 31
+  L.env = blockIdx.x * E + e;
+  L.warp_m0 = blockIdx.x * E * N;  // first UAV of the CTA
+  envs_here = min(E, a.B - blockIdx.x * E);
+  L.valid_lanes = envs_here * N;
+  L.valid = t < L.valid_lanes;
+  L.m = L.warp_m0 + t;
+  if (!L.valid) { L.base = 0; L.ring = 0; L.i = 0; }  // idle threads shadow UAV 0 of the CTA's first env and never store
+  return L;
+}
+
+__global__ void __launch_bounds__(kThreads, 6) step_multi_cta_kernel(const __grid_constant__ KernelArgs a) {
+  __shared__ __align__(16) CtaShared sh;
+  int e, envs_here;
+  const Lane L = cta_lane(a, e, envs_here);
+  cudaGridDependencySynchronize();
+  Uav u = load_uav(a.s, L);
+  const float2 act = L.valid ? ld_stream(a.io.action + L.m) : make_float2(0.f, 0.f);
+  cudaTriggerProgrammaticLaunchCompletion();
+  cta_step<false>(a, sh, L, e, envs_here, u, act, 0, 0);
+}
+
+// K steps per launch for the same packing (uavca_rollout): the UAV stays in registers, the per-step outputs go to slot k
+// of the [K][...] blocks; actions from the block or the Philox stream, as rollout_multi_kernel draws them.
+__global__ void __launch_bounds__(kThreads, 6) rollout_multi_cta_kernel(const __grid_constant__ KernelArgs a,
+                                                                         const __grid_constant__ RolloutArgs r) {
+  __shared__ __align__(16) CtaShared sh;
+  int e, envs_here;
+  const Lane L = cta_lane(a, e, envs_here);
+  cudaGridDependencySynchronize();
+  Uav u = load_uav(a.s, L);
+  cudaTriggerProgrammaticLaunchCompletion();
+  const long long env_global = a.c.env_base + L.env;
+  uint4 words = make_uint4(0u, 0u, 0u, 0u);
+  for (int k = 0; k < r.K; ++k) {
+    float2 act = make_float2(0.f, 0.f);
+    if (r.action_block != nullptr) {
+      if (L.valid) act = ld_stream(r.action_block + (size_t)k * r.M + L.m);
+    } else {
+      const unsigned long long t = r.step0 + (unsigned long long)k;
+      if (k == 0 || (t & 1ull) == 0ull) words = action_words(r.seed_lo, r.seed_hi, env_global, L.i, t);
+      act = action_from_words(words, t);
+      if (r.action_out != nullptr && L.valid) st_stream(r.action_out + (size_t)k * r.M + L.m, act);
+    }
+    cta_step<true>(a, sh, L, e, envs_here, u, act, (size_t)k * r.M, (size_t)k * r.B);
+    __syncthreads();  // the tables and the staged rows of this step are free again
+  }
+  store_uav(a.s, L, u, true);
 }
 
 }  // namespace uavca

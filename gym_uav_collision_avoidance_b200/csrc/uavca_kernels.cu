@@ -1075,6 +1075,14 @@ static cudaError_t launch_pdl2(Kernel kernel, int grid, cudaStream_t st, const K
 cudaError_t launch_rollout_multi(const KernelArgs& a, const RolloutArgs& r, cudaStream_t st) {
   if (a.B <= 0 || r.K <= 0) return cudaSuccess;
   cudaError_t e = cudaSuccess;
+  // 17..25 UAVs per env: the CTA-packed kernel (5..7 envs on the 128 threads of a CTA instead of one env per warp), as in
+  // launch_step_multi; UAVCA_ROLLOUT_CTA=0 keeps the warp kernel (A/B measurements)
+  static const bool cta_ok = [] { const char* v = getenv("UAVCA_ROLLOUT_CTA"); return !(v && v[0] == '0'); }();
+  if (cta_ok && a.N > 16 && kThreads / a.N >= 5) {
+    const int envs_per_cta = kThreads / a.N;
+    e = launch_pdl2(rollout_multi_cta_kernel, (a.B + envs_per_cta - 1) / envs_per_cta, st, a, r);
+    return e != cudaSuccess ? e : cudaGetLastError();
+  }
   const int grid = multi_grid(a.B, a.N);
   UAVCA_DISPATCH_N(a.N, (e = launch_pdl2(rollout_multi_kernel<NT>, grid, st, a, r)));
   return e != cudaSuccess ? e : cudaGetLastError();

@@ -722,8 +722,8 @@ def test_circular_rollout_vs_oracle_with_scores():
     st = env.stats()
     assert st["episodes"] == int(orc.state.stats[0]) >= B and st["reach"] == int(orc.state.stats[1])
     assert st["collisions"] == int(orc.state.stats[2]) > 0
-    with pytest.raises(G.UavcaError):
-        env.rollout(4, None)  # K steps per launch serves the warp kernels only
+    out = env.rollout(4, None)  # the float64 world has no K loop: the same call issues K launches (tests/test_rollout_gpu.py)
+    assert out["obs"].shape == (4, B, n, 10) and torch.isfinite(out["reward"]).all()
 
 
 @pytest.mark.parametrize("n", [33, 40, 64, 100])

@@ -33,7 +33,8 @@ def _pair(kind, B, N, **kw):
     return a, b
 
 
-@pytest.mark.parametrize("n,B", [(2, 3000), (5, 1026), (7, 2050), (8, 4099), (10, 1500), (16, 1001), (32, 515), (24, 300)])
+@pytest.mark.parametrize("n,B", [(2, 3000), (5, 1026), (7, 2050), (8, 4099), (10, 1500), (16, 1001), (32, 515), (24, 300),
+                                 (17, 131), (20, 262), (25, 77), (28, 90)])
 def test_rollout_with_action_block_equals_single_steps(n, B):
     if (B * n * 10 * 4) % 16:
         B += 1  # K > 1 needs 16-byte aligned step blocks
@@ -56,7 +57,7 @@ def test_rollout_with_action_block_equals_single_steps(n, B):
 
 
 @pytest.mark.parametrize("mode", ["cartesian", "polar", "scaled"])
-@pytest.mark.parametrize("n", [3, 8, 32])
+@pytest.mark.parametrize("n", [3, 8, 20, 32])
 def test_rollout_with_philox_actions(n, mode):
     """On-device actions: the draws equal the oracle's restatement of the stream, the rollout equals K single steps fed
     `sample_actions`, and both agree with the oracle (flags bit-exact, outputs within tolerance)."""
