@@ -15,7 +15,7 @@ echo "# nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -X
 md="$root/profiles/${tag}_sass_stats.md"
 echo "# SASS statistics of the hot kernels (tools/sass_stats.py on the built libuavca.so; static counts up to the first unconditional EXIT = the common path + its rare branches)" > "$md"
 cd "$root"
-for k in 'step_multi_kernelILi8E' 'step_multi_kernelILi32E' 'step_multi_ring_kernelILi10E' 'policy_act_kernel' 'rollout_multi_kernelILi8E' 'rollout_multi_kernelILi32E' 'step_single_kernel' 'rollout_single_kernel'; do
+for k in 'step_multi_kernelILi8E' 'step_multi_kernelILi32E' 'step_multi_ring_kernelILi10E' 'step_multi_cta_kernel' 'rollout_multi_cta_kernel' 'policy_act_kernel' 'rollout_multi_kernelILi8E' 'rollout_multi_kernelILi32E' 'step_single_kernel' 'rollout_single_kernel'; do
   echo -e "\n## $k\n\`\`\`" >> "$md"
   python tools/sass_stats.py gym_uav_collision_avoidance_b200/libuavca.so "$k" | head -2 >> "$md"
   echo '```' >> "$md"
