@@ -23,7 +23,6 @@ for dtype in (np.float32, np.float64):
     print(f"compat.MultiUAVWorld2D N={N} {np.dtype(dtype).name} actions: {dt / K * 1e6:.1f} us per env.step")
     env.close()
 try:
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
     from oracle import ref_loader as R
     _, Ref = R.load_reference()
     env = Ref(num_agents=N)
