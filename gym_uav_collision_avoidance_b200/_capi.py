@@ -80,6 +80,8 @@ SYMBOLS = {
     "uavca_sample_actions": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP, _VP]),
     "uavca_step_multi_replay": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                                            _VP, C.c_int64, _VP, _VP]),
+    "uavca_replay_sample": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_int32, C.c_int32, _VP, C.c_int64, C.c_uint64,
+                                      C.c_uint64, C.c_int, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "uavca_replay_push_dev": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP,
                                         C.c_int64, _VP, _VP]),
     "uavca_replay_push": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int64, C.c_int32, C.c_int32, _VP, _VP, _VP, _VP, _VP,

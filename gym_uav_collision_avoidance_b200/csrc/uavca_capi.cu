@@ -761,6 +761,28 @@ int uavca_replay_push_dev(const float* obs, const float* action, const float* re
                           ring_next_obs, ring_mask, capacity, 0, ring_meta, stream);
 }
 
+int uavca_replay_sample(const float* ring_obs, const float* ring_action, const float* ring_reward, const float* ring_next_obs,
+                        const float* ring_mask, int64_t capacity, int32_t obs_dim, int32_t act_dim, const int64_t* ring_meta,
+                        int64_t batch, uint64_t seed, uint64_t draw, int recency_weighted, float* out_obs, float* out_action,
+                        float* out_reward, float* out_next_obs, float* out_mask, int64_t* out_index, void* stream) {
+  if (!ring_obs || !ring_action || !ring_reward || !ring_next_obs || !ring_mask || !ring_meta || !out_obs || !out_action ||
+      !out_reward || !out_next_obs || !out_mask)
+    return fail(-1, "null argument");
+  if (batch < 0 || obs_dim <= 0 || act_dim <= 0 || capacity <= 0 || capacity >= ((int64_t)1 << 32)) return fail(-1, "bad sizes");
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, ring_obs) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+    cudaGetLastError();
+    return fail(-1, "uavca_replay_sample: ring_obs is not a device pointer");
+  }
+  DeviceGuard g(at.device);
+  cudaError_t e = launch_replay_sample(ring_obs, ring_action, ring_reward, ring_next_obs, ring_mask, capacity, obs_dim, act_dim,
+                                       reinterpret_cast<const long long*>(ring_meta), batch, seed, draw, recency_weighted, out_obs,
+                                       out_action, out_reward, out_next_obs, out_mask, reinterpret_cast<long long*>(out_index),
+                                       (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail_cuda("uavca_replay_sample", e);
+  return 0;
+}
+
 int uavca_step_multi_replay(uavca_handle* h, void* state, const float* action, int action_mode, int evaluate,
                             const float* prev_obs, float* obs, float* reward, uint8_t* done, float* final_obs,
                             uint8_t* reset_mask, float* ring_obs, float* ring_action, float* ring_reward, float* ring_next_obs,

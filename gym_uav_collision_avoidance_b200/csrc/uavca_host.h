@@ -28,6 +28,11 @@ cudaError_t launch_replay_push(const float* obs, const float* action, const floa
                                float* r_rew, float* r_next, float* r_mask, long long capacity, long long head,
                                long long* meta, cudaStream_t st);
 
+cudaError_t launch_replay_sample(const float* r_obs, const float* r_act, const float* r_rew, const float* r_nxt,
+                                 const float* r_mask, long long capacity, int obs_dim, int act_dim, const long long* meta,
+                                 long long batch, unsigned long long seed, unsigned long long draw, int recency, float* o_obs,
+                                 float* o_act, float* o_rew, float* o_nxt, float* o_mask, long long* o_idx, cudaStream_t st);
+
 cudaError_t launch_policy_act(const float* obs, long long M, const void* w1, const void* w2, const void* w2b, const void* w3,
                               const void* w3b, const float* noise, unsigned long long seed, unsigned long long counter,
                               const unsigned long long* counter_dev, float* action, float* head, cudaStream_t st);

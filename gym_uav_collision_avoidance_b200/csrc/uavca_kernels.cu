@@ -773,6 +773,50 @@ __global__ void __launch_bounds__(kPushThreads) replay_push_kernel(const V* obs,
   }
 }
 
+// Replay sampling (ReplayMemory.sample, pytorch_sac_temp/replay_memory.py:21-24; ReplayBuffer.get_batch with its recency
+// weighting, pytorch_ddpg/buffer_tensor.py:65-90): draw `batch` slots and gather the five arrays in ONE launch.  Ring head
+// and fill level are read on the device (ring_meta), the draws come from Philox4x32-10 keyed by (seed, sample, draw +
+// appends so far), so a learner step captured in a CUDA graph samples fresh transitions from the ring as it grows.
+// 16 threads per sample: they share the slot and copy the rows element-wise.
+constexpr int kSampleLanes = 16;
+__global__ void __launch_bounds__(kThreads) replay_sample_kernel(const float* r_obs, const float* r_act, const float* r_rew,
+                                                                 const float* r_nxt, const float* r_mask, long long cap, int od,
+                                                                 int ad, const long long* meta, long long batch, unsigned seed_lo,
+                                                                 unsigned seed_hi, unsigned long long draw, int recency,
+                                                                 float* o_obs, float* o_act, float* o_rew, float* o_nxt,
+                                                                 float* o_mask, long long* o_idx) {
+  const long long j = ((long long)blockIdx.x * kThreads + threadIdx.x) / kSampleLanes;
+  const int l = threadIdx.x % kSampleLanes;
+  if (j >= batch) return;
+  const long long head = meta[0], size = meta[2];
+  const unsigned long long ctr = draw + (unsigned long long)meta[3];
+  const uint4 r = philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32), seed_lo, seed_hi);
+  long long slot = 0;
+  if (size > 0) {
+    if (recency) {
+      // probability rising linearly with recency: inverse CDF of p_i ~ i + 1/2 over insertion order (buffer_tensor.py:78-87)
+      const double u = ((double)r.x + 0.5) * (1.0 / 4294967296.0);
+      long long age = (long long)(sqrt(u) * (double)size);
+      age = age >= size ? size - 1 : age;
+      const long long oldest = size == cap ? head : 0;
+      slot = oldest + age;
+      slot -= slot >= cap ? cap : 0;
+    } else {
+      slot = (long long)(((unsigned long long)r.x * (unsigned long long)size) >> 32);  // uniform over the filled slots (size < 2^32)
+    }
+  }
+  for (int k = l; k < od; k += kSampleLanes) {
+    o_obs[j * od + k] = r_obs[slot * od + k];
+    o_nxt[j * od + k] = r_nxt[slot * od + k];
+  }
+  for (int k = l; k < ad; k += kSampleLanes) o_act[j * ad + k] = r_act[slot * ad + k];
+  if (l == 0) {
+    o_rew[j] = r_rew[slot];
+    o_mask[j] = r_mask[slot];
+    if (o_idx) o_idx[j] = slot;
+  }
+}
+
 // ================================================================================================================
 // Launchers
 // ================================================================================================================
@@ -1149,6 +1193,17 @@ cudaError_t launch_map_action(const Consts& c, const float* in, float* out, long
   if (M <= 0) return cudaSuccess;
   map_action_kernel<<<flat_grid(M), kThreads, 0, st>>>(c, reinterpret_cast<const float2*>(in),
                                                        reinterpret_cast<float2*>(out), M, mode);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_replay_sample(const float* r_obs, const float* r_act, const float* r_rew, const float* r_nxt,
+                                 const float* r_mask, long long capacity, int obs_dim, int act_dim, const long long* meta,
+                                 long long batch, unsigned long long seed, unsigned long long draw, int recency, float* o_obs,
+                                 float* o_act, float* o_rew, float* o_nxt, float* o_mask, long long* o_idx, cudaStream_t st) {
+  if (batch <= 0) return cudaSuccess;
+  replay_sample_kernel<<<flat_grid(batch * kSampleLanes), kThreads, 0, st>>>(
+      r_obs, r_act, r_rew, r_nxt, r_mask, capacity, obs_dim, act_dim, meta, batch, (unsigned)(seed & 0xffffffffull),
+      (unsigned)(seed >> 32), draw, recency, o_obs, o_act, o_rew, o_nxt, o_mask, o_idx);
   return cudaGetLastError();
 }
 

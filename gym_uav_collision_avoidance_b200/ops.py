@@ -137,6 +137,24 @@ def replay_push_dev(obs: torch.Tensor, action: torch.Tensor, reward: torch.Tenso
                                                    ring_meta.data_ptr(), _stream(obs)), "uavca_replay_push_dev")
 
 
+@torch.library.custom_op("uavca::replay_sample",
+                         mutates_args=("out_obs", "out_action", "out_reward", "out_next_obs", "out_mask", "out_index"))
+def replay_sample(ring_obs: torch.Tensor, ring_action: torch.Tensor, ring_reward: torch.Tensor, ring_next_obs: torch.Tensor,
+                  ring_mask: torch.Tensor, ring_meta: torch.Tensor, seed: int, draw: int, recency_weighted: bool,
+                  out_obs: torch.Tensor, out_action: torch.Tensor, out_reward: torch.Tensor, out_next_obs: torch.Tensor,
+                  out_mask: torch.Tensor, out_index: Optional[torch.Tensor]) -> None:
+    """`memory.sample(batch)` (pytorch_sac_temp/replay_memory.py:21-24) in one launch, slots drawn on the device."""
+    _need_cuda(ring_obs, ring_action, ring_reward, ring_next_obs, ring_mask, ring_meta, out_obs, out_action, out_reward,
+               out_next_obs, out_mask, out_index)
+    cap, batch = ring_reward.numel(), out_reward.numel()
+    _capi.check(_capi.load().uavca_replay_sample(ring_obs.data_ptr(), ring_action.data_ptr(), ring_reward.data_ptr(),
+                                                 ring_next_obs.data_ptr(), ring_mask.data_ptr(), cap, ring_obs.numel() // cap,
+                                                 ring_action.numel() // cap, ring_meta.data_ptr(), batch, seed, draw,
+                                                 int(recency_weighted), out_obs.data_ptr(), out_action.data_ptr(),
+                                                 out_reward.data_ptr(), out_next_obs.data_ptr(), out_mask.data_ptr(),
+                                                 _ptr(out_index), _stream(ring_obs)), "uavca_replay_sample")
+
+
 @torch.library.custom_op("uavca::step_multi_replay",
                          mutates_args=("state", "obs", "reward", "done", "final_obs", "reset_mask", "ring_obs", "ring_action",
                                        "ring_reward", "ring_next_obs", "ring_mask", "ring_meta"))

@@ -33,6 +33,7 @@ class DeviceReplay:
         self.gen = torch.Generator(device=self.device)
         if seed is not None:
             self.gen.manual_seed(seed)
+        self._sample_seed, self._draws = int(seed if seed is not None else 0x5A3B1E) & (2 ** 63 - 1), 0  # sample_fused
 
     @property
     def position(self) -> int:
@@ -59,6 +60,23 @@ class DeviceReplay:
             done = done.view(torch.uint8)
         ops.replay_push_dev(state.contiguous(), action.contiguous(), reward.contiguous(), next_state.contiguous(),
                             done.contiguous(), self.state, self.action, self.reward, self.next_state, self.mask, self.meta)
+
+    def sample_fused(self, batch_size: int, recency_weighted: bool = False, out=None, want_index: bool = False):
+        """`memory.sample(batch_size)` in ONE launch with no host synchronisation (`uavca_replay_sample`): the slots are
+        drawn on the device from Philox4x32-10 keyed by (seed, sample, draws so far + appends so far) against the head and
+        fill level in `self.meta`, so a learner step captured in a CUDA graph keeps sampling fresh transitions as the ring
+        grows.  Returns (state, action, reward, next_state, mask[, index]); `out` reuses a previous result's tensors."""
+        if out is None:
+            kw = dict(dtype=torch.float32, device=self.device)
+            out = (torch.empty((batch_size, self.obs_dim), **kw), torch.empty((batch_size, self.act_dim), **kw),
+                   torch.empty(batch_size, **kw), torch.empty((batch_size, self.obs_dim), **kw), torch.empty(batch_size, **kw))
+            if want_index:
+                out = out + (torch.empty(batch_size, dtype=torch.int64, device=self.device),)
+        idx = out[5] if len(out) > 5 else None
+        ops.replay_sample(self.state, self.action, self.reward, self.next_state, self.mask, self.meta, self._sample_seed,
+                          self._draws, bool(recency_weighted), out[0], out[1], out[2], out[3], out[4], idx)
+        self._draws += 1
+        return out
 
     def sample(self, batch_size: int, recency_weighted: bool = False):
         """-> (state [b,obs], action [b,act], reward [b], next_state [b,obs], mask [b]) as `memory.sample` returns them

@@ -14,6 +14,7 @@
  *   uavca_map_action   <- caller-side action mapping      test_sac_multi.py:77-80, test_pytorch_multi.py:80
  *   uavca_rollout      <- the random-action driver loops    run.py:10-16, run_multi.py:10-16 (K x env.step per call)
  *   uavca_step_multi_replay <- env.step + the N memory.push calls of a training step   test_sac_multi.py:99-103
+ *   uavca_replay_push(_dev) / uavca_replay_sample <- ReplayMemory.push / .sample   pytorch_sac_temp/replay_memory.py:15-24
  *   uavca_stats        <- env.steps / target_reach_count / collision_count  multi_uav_world_2d.py:166-168,209,221,238
  *   uavca_config       <- constructor kwargs              multi_uav_world_2d.py:13-28, uav_world_2d.py:14-26
  *
@@ -34,7 +35,7 @@
 extern "C" {
 #endif
 
-#define UAVCA_VERSION 201
+#define UAVCA_VERSION 202
 
 /* world kinds */
 #define UAVCA_KIND_MULTI 0  /* MultiUAVWorld2D: N UAVs per env, 10-feature observation */
@@ -228,6 +229,18 @@ int uavca_replay_push_dev(const float* obs, const float* action, const float* re
                           const uint8_t* done, int64_t M, int32_t obs_dim, int32_t act_dim, float* ring_obs,
                           float* ring_action, float* ring_reward, float* ring_next_obs, float* ring_mask,
                           int64_t capacity, int64_t* ring_meta, void* stream);
+
+/* Draw `batch` transitions from the ring and gather the five arrays in ONE launch ("next" row; replaces ReplayMemory.sample,
+ * pytorch_sac_temp/replay_memory.py:21-24, and ReplayBuffer.get_batch, pytorch_ddpg/buffer_tensor.py:65-90).  Head and fill
+ * level are read from ring_meta on the device; the slots come from Philox4x32-10 keyed by (seed, sample index, draw +
+ * appends so far), uniformly over the filled slots (with replacement) or, with recency_weighted != 0, with probability
+ * rising linearly with recency (the `unbalance_p` scheme of buffer_tensor.py:78-87).  No host synchronisation: safe inside a
+ * CUDA graph of a learner step.  out_*: float [batch][obs_dim] / [batch][act_dim] / [batch]; out_index (nullable) int64
+ * [batch] receives the slots.  An empty ring yields slot 0. */
+int uavca_replay_sample(const float* ring_obs, const float* ring_action, const float* ring_reward, const float* ring_next_obs,
+                        const float* ring_mask, int64_t capacity, int32_t obs_dim, int32_t act_dim, const int64_t* ring_meta,
+                        int64_t batch, uint64_t seed, uint64_t draw, int recency_weighted, float* out_obs, float* out_action,
+                        float* out_reward, float* out_next_obs, float* out_mask, int64_t* out_index, void* stream);
 
 /* uavca_step_multi with the replay append folded into the SAME launch ("next" row; MultiUAVWorld2D.step followed by the N
  * memory.push calls of test_sac_multi.py:99-103).  Besides everything uavca_step_multi writes, UAV m's transition goes to

@@ -227,6 +227,56 @@ def test_replay_recency_weighted_sampling_prefers_new_transitions():
 # ---- batched acting path ----------------------------------------------------------------------------------------------
 
 
+def test_replay_sample_fused_gathers_on_the_device():
+    """`sample_fused` (uavca_replay_sample): one launch, no host sync — slots inside the filled part, rows equal to the ring's
+    rows at the returned slots, uniform and recency-weighted laws, fresh draws per call and per CUDA-graph replay."""
+    import gym_uav_collision_avoidance_b200 as G
+
+    cap, M, od = 5000, 700, 10
+    rb = G.DeviceReplay(cap, od, 2, seed=4)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    pushed = 0
+
+    def push():
+        nonlocal pushed
+        tag = torch.arange(pushed, pushed + M, device="cuda", dtype=torch.float32)  # insertion order, kept in `reward`
+        rb.push(torch.rand((M, od), generator=gen, device="cuda"), torch.rand((M, 2), generator=gen, device="cuda"), tag,
+                torch.rand((M, od), generator=gen, device="cuda"), (torch.rand(M, generator=gen, device="cuda") < 0.1).to(torch.uint8))
+        pushed += M
+
+    for _ in range(3):  # partly filled: 2,100 of 5,000
+        push()
+    s, a, r, n, m, idx = rb.sample_fused(4096, want_index=True)
+    assert int(idx.min()) >= 0 and int(idx.max()) < 2100 and idx.unique().numel() > 1500
+    assert torch.equal(s, rb.state[idx]) and torch.equal(a, rb.action[idx]) and torch.equal(n, rb.next_state[idx])
+    assert torch.equal(r, rb.reward[idx]) and torch.equal(m, rb.mask[idx])
+    assert abs(float(idx.float().mean()) / 2100 - 0.5) < 0.03  # uniform over the filled slots
+    idx2 = rb.sample_fused(4096, want_index=True)[5]
+    assert not torch.equal(idx, idx2)  # every call draws afresh
+    for _ in range(6):  # wrapped: 6,300 pushed into 5,000 slots
+        push()
+    assert rb.size == cap
+    r_u = rb.sample_fused(20000)[2]
+    r_w = rb.sample_fused(20000, recency_weighted=True)[2]
+    oldest = pushed - cap
+    assert float(r_u.min()) >= oldest and float(r_w.min()) >= oldest  # nothing overwritten is ever returned
+    age_u, age_w = (pushed - 1 - r_u) / cap, (pushed - 1 - r_w) / cap  # 0 = newest, 1 = oldest
+    assert abs(float(age_u.mean()) - 0.5) < 0.02 and abs(float(age_w.mean()) - 1 / 3) < 0.02  # p ~ recency: E[age] = 1/3
+    # captured once, replayed while the ring grows: the draws follow the ring's append counter
+    out = rb.sample_fused(512, want_index=True)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        rb.sample_fused(512, out=out)
+    seen = []
+    for _ in range(3):
+        push()
+        g.replay()
+        torch.cuda.synchronize()
+        seen.append(out[5].clone())
+        assert torch.equal(out[0], rb.state[out[5]])
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+
+
 def test_rollout_feeds_the_replay_ring_with_the_steps_own_transitions():
     import gym_uav_collision_avoidance_b200 as G
 
