@@ -17,7 +17,16 @@
 
 namespace uavca {
 
-constexpr int kCtaMaxEnvs = 8;  // floor(128 / 17) = 7
+constexpr int kCtaMaxEnvs = 12;  // floor(128 / 11) = 11
+
+// Which env widths the CTA packing serves: where 128 threads hold clearly more envs than 4 warps do — 17..25 UAVs (5..7
+// envs against 4) and 11 UAVs (11 envs against 8); 12 UAVs (10 against 8) only pays in the K-steps-per-launch kernel.
+// Elsewhere the packing gains at most one env in eight and the CTA barriers cost more than that.  Measured at B*N = 2 Mi
+// UAVs: N=11 96.5 -> 89.6 us per step, rollout 80.1 -> 69.6; N=12 90.7 -> 90.7, rollout 73.8 -> 69.5.
+inline bool cta_packs(int N, bool rollout) {
+  if (N == 11 || (N == 12 && rollout)) return true;
+  return N > 16 && kThreads / N >= 5;
+}
 
 struct CtaShared {
   float4 pairs[kThreads + kCtaMaxEnvs];  // env e at float4 offset e * (N + 1): sum over envs <= 128 + 7

@@ -990,7 +990,7 @@ cudaError_t launch_step_multi(const KernelArgs& a, cudaStream_t st, int* launche
     if (launched) *launched = 1;
     return cudaGetLastError();
   }
-  if (a.N > 16 && kThreads / a.N >= 5 && path != UAVCA_PATH_PLAIN && path != UAVCA_PATH_PREFETCH && path != UAVCA_PATH_AUTO) {
+  if (cta_packs(a.N, false) && path != UAVCA_PATH_PLAIN && path != UAVCA_PATH_PREFETCH && path != UAVCA_PATH_AUTO) {
     // 17..25 UAVs per env: 5..7 envs packed across the 4 warps of a CTA instead of one env per warp (uavca_cta.cuh).
     // Measured (B*N = 2 Mi UAVs, one stream): N=17 98 vs 136 us, N=20 101 vs 122, N=24 107 vs 113; from N=26 a CTA
     // holds 4 envs like 4 warps do and the barriers only cost (N=28 119 vs 108 us), so those stay on the warp kernel.
@@ -1122,7 +1122,7 @@ cudaError_t launch_rollout_multi(const KernelArgs& a, const RolloutArgs& r, cuda
   // 17..25 UAVs per env: the CTA-packed kernel (5..7 envs on the 128 threads of a CTA instead of one env per warp), as in
   // launch_step_multi; UAVCA_ROLLOUT_CTA=0 keeps the warp kernel (A/B measurements)
   static const bool cta_ok = [] { const char* v = getenv("UAVCA_ROLLOUT_CTA"); return !(v && v[0] == '0'); }();
-  if (cta_ok && a.N > 16 && kThreads / a.N >= 5) {
+  if (cta_ok && cta_packs(a.N, true)) {
     const int envs_per_cta = kThreads / a.N;
     e = launch_pdl2(rollout_multi_cta_kernel, (a.B + envs_per_cta - 1) / envs_per_cta, st, a, r);
     return e != cudaSuccess ? e : cudaGetLastError();

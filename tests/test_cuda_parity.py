@@ -167,7 +167,7 @@ def rollout_vs_oracle(cfg: O.Config, steps, seed, evaluate=False, crowd=None, nt
     return events, orc
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 10, 13, 16, 17, 24, 31, 32])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 12, 13, 16, 17, 24, 31, 32])
 def test_multi_rollout_all_agent_counts(n):
     """Every N in 1..32 maps to a different lane layout (specialised or generic kernel, ragged last warp)."""
     B = 257  # not a multiple of any envs-per-warp: exercises the tail
@@ -410,7 +410,7 @@ def test_prefetch_variant_equals_the_plain_kernel_at_scale(monkeypatch):
     assert torch.equal(e1.state.blob, e2.state.blob)
 
 
-@pytest.mark.parametrize("n", [17, 20, 24, 25])
+@pytest.mark.parametrize("n", [11, 17, 20, 24, 25])
 def test_cta_packed_kernel_and_warp_kernel_agree(monkeypatch, n):
     """17 <= N <= 25 runs step_multi_cta_kernel (envs packed across the warps of a CTA) by default and the one-env-per-
     warp kernel under UAVCA_STEP_PATH=plain (which uavca_rollout also uses): both against the oracle, all three reset

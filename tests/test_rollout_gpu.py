@@ -34,7 +34,7 @@ def _pair(kind, B, N, **kw):
 
 
 @pytest.mark.parametrize("n,B", [(2, 3000), (5, 1026), (7, 2050), (8, 4099), (10, 1500), (16, 1001), (32, 515), (24, 300),
-                                 (17, 131), (20, 262), (25, 77), (28, 90)])
+                                 (17, 131), (20, 262), (25, 77), (28, 90), (11, 190), (12, 170)])
 def test_rollout_with_action_block_equals_single_steps(n, B):
     if (B * n * 10 * 4) % 16:
         B += 1  # K > 1 needs 16-byte aligned step blocks
