@@ -133,9 +133,10 @@ def test_oracle_matches_live_reference_with_random_constructor_arguments(trial):
             a = np.clip((orc.state.tgt[0] - orc.state.pos[0]) * 1.2 + rng.normal(0, 0.4, (n, 2)), -kw["max_speed"], kw["max_speed"])
         else:
             a = rng.uniform(-kw["max_speed"], kw["max_speed"], (n, 2))
-        a = a.astype(np.float32)
+        f64 = trial >= 3  # half of the trials feed float64 actions that float32 cannot hold (uavo_step_f64act)
+        a = a.astype(np.float64) if f64 else a.astype(np.float32)
         o, r, d, _ = env.step([a[i].astype(np.float64) for i in range(n)], evaluate=evaluate)
-        out = orc.step(a[None], evaluate=evaluate)
+        out = orc.step_f64(a[None], evaluate=evaluate) if f64 else orc.step(a[None], evaluate=evaluate)
         assert np.array_equal(out["done"][0], np.array(d, np.uint8)), f"done flags, step {t}"
         assert np.array_equal(out["reward"][0], np.array(r, np.float64)), f"reward, step {t}"
         assert np.array_equal(out["obs"][0], np.stack(o)), f"observation, step {t}"
