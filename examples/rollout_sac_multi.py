@@ -4,12 +4,12 @@ Reference, per env step (one env, N agents):            Here, per env step (B en
   for i in range(N): agents[i].select_action(states[i])    one policy kernel over [B*N, 10]            (FusedGaussianPolicy)
   v, theta -> [v cos, v sin] on the host (:77-80)          polar map fused into the step kernel         (action_mode="polar")
   env.step(converted_actions)            (:99)             env.step(action)                             (one launch)
-  memory.push(...) for i in range(N)     (:101-103)        replay.push(obs, action, reward, next, done) (one launch)
+  memory.push(...) for i in range(N)     (:101-103)        appended by the step kernel itself           (same launch)
   reset when dones[0] or 1500 steps      (:111-119)        auto-reset inside the step (RESET_ON_DONE0, max_episode_steps)
   every 10 episodes: 10 evaluation episodes, SR / CR       evaluation batch with RESET_ON_ALL_DONE, evaluate=True
 
 The learner (SAC.update_parameters, pytorch_sac_temp/sac.py:46-98) is stock PyTorch and out of scope; `replay.sample(256)`
-returns exactly the five tensors it consumes.
+/ `replay.sample_fused(256)` (one launch, slots drawn on the device) return exactly the five tensors it consumes.
 
     python examples/rollout_sac_multi.py [--envs 16384] [--agents 10] [--steps 2000]
 """
@@ -48,7 +48,7 @@ def main(argv=None):
     ro.run(args.steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    batch = replay.sample(256)                                                # what SAC.update_parameters consumes (:48)
+    batch = replay.sample_fused(256)                                          # what SAC.update_parameters consumes (:48)
     print(f"collected {args.steps * args.envs * args.agents:,} transitions in {dt:.2f} s "
           f"({args.steps * args.envs / dt:,.0f} env-steps/s, eager launches); replay holds {len(replay):,}; "
           f"sampled batch shapes {[tuple(t.shape) for t in batch]}")
